@@ -1,0 +1,85 @@
+/* qw.h -- C ABI of the B200-native Quantum-Whisper hot path (libqw_b200.so).
+ *
+ * Drop-in boundary for the reference's QuantumConv1d operator and the log-mel front end.  The reference
+ * is pure Python (PennyLane QNode inside an nn.Module); its FFI for this path is therefore "whatever a
+ * torch.autograd.Function can call with raw device pointers".  Each entry point cites the reference code it
+ * replaces (paths relative to /root/reference/).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; tensors are dense row-major;
+ *   - the library never allocates or frees device memory and keeps no pointer after a call returns
+ *     (except *_host entry points, which use an internal per-device staging pool);
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no implicit sync;
+ *   - return value: 0 ok; <0 bad argument (-1 null/shape, -2 unsupported configuration, -3 workspace too
+ *     small); >0 a cudaError_t.  Nothing throws across the ABI.  qw_last_error() gives a thread-local text.
+ *   - embedding: 0 = amplitude (the reference circuit), 1 = angle (extension).
+ *   - quantum weights qw: (n_layers, q, 3) = [phi, theta, omega] per wire; n_layers = 1 is the reference.
+ */
+#ifndef QW_B200_H
+#define QW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QW_EMB_AMPLITUDE 0
+#define QW_EMB_ANGLE 1
+#define QW_ABI_VERSION 1
+
+/* ABI version / build info. */
+int qw_abi_version(void);
+const char* qw_last_error(void);
+/* Number of kernels this library has launched from the calling process since load (for bench gpu_launches). */
+long long qw_launch_count(void);
+
+/* ---- QuantumConv1d.forward  (quantum_whisper.py:95-128; circuit :64-85; params :58-59,88)
+ * x (B,C,L) -> y (B,O,L_out), L_out = (L+2P-K)/S+1 (:103).  w_pre (q, C*K) with column c*K+k (:58,:111),
+ * b_pre (q), qw (n_layers,q,3), w_post (O,q), b_post (O).  pre_save: (B*L_out, q) or NULL -- the pre_conv
+ * outputs, kept for the backward pass.  q must already be min(n_qubits, C*K) (:55). */
+int qw_conv1d_forward(const float* x, const float* w_pre, const float* b_pre, const float* qw, const float* w_post,
+                      const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O,
+                      int q, int n_layers, int embedding, void* stream);
+int qw_conv1d_forward_f64(const double* x, const double* w_pre, const double* b_pre, const double* qw,
+                          const double* w_post, const double* b_post, double* y, double* pre_save, int B, int C, int L,
+                          int K, int S, int P, int O, int q, int n_layers, int embedding, void* stream);
+
+/* ---- backward of the same (autograd through :107-126 and PennyLane backprop) by adjoint
+ * differentiation.  gy (B,O,L_out).  gx (B,C,L) or NULL to skip (conv1's input is data).  Parameter
+ * gradients are OVERWRITTEN (not accumulated).  workspace: qw_conv1d_workspace_bytes(...) bytes. */
+size_t qw_conv1d_workspace_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int elem_size);
+int qw_conv1d_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qw,
+                       const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post,
+                       float* gb_post, void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P,
+                       int O, int q, int n_layers, int embedding, void* stream);
+int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_save, const double* w_pre,
+                           const double* qw, const double* w_post, double* gx, double* gw_pre, double* gb_pre,
+                           double* gqw, double* gw_post, double* gb_post, void* workspace, size_t ws_bytes, int B,
+                           int C, int L, int K, int S, int P, int O, int q, int n_layers, int embedding, void* stream);
+
+/* ---- the QNode alone (quantum_whisper.py:64-85), batched over W windows: pre (W,q) -> out (W,q);
+ * backward: gout (W,q) -> gpre (W,q) and gqw (n_layers,q,3) (overwritten).  BASELINE.json config 4. */
+size_t qw_circuit_workspace_bytes(long long W, int q, int n_layers, int elem_size);
+int qw_circuit_forward(const float* pre, const float* qw, float* out, long long W, int q, int n_layers, int embedding,
+                       void* stream);
+int qw_circuit_backward(const float* pre, const float* qw, const float* gout, float* gpre, float* gqw, void* workspace,
+                        size_t ws_bytes, long long W, int q, int n_layers, int embedding, void* stream);
+int qw_circuit_forward_f64(const double* pre, const double* qw, double* out, long long W, int q, int n_layers,
+                           int embedding, void* stream);
+int qw_circuit_backward_f64(const double* pre, const double* qw, const double* gout, double* gpre, double* gqw,
+                            void* workspace, size_t ws_bytes, long long W, int q, int n_layers, int embedding,
+                            void* stream);
+
+/* ---- whisper.log_mel_spectrogram (whisper/whisper/audio.py:110-157), batched, max taken per utterance.
+ * audio (B, n_samples) fp32, n_samples % 160 == 0; filters (n_mels, 201) fp32 (audio.py:91-107);
+ * mel (B, n_mels, n_samples/160).  workspace: qw_log_mel_workspace_bytes(B, n_samples, n_mels). */
+size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels);
+int qw_log_mel(const float* audio, const float* filters, float* mel, void* workspace, size_t ws_bytes, int B,
+               int n_samples, int n_mels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QW_B200_H */

@@ -1,0 +1,83 @@
+"""ctypes binding of libqw_b200.so (the C ABI declared in include/qw.h).
+
+There is NO CPU fallback: if the shared library is missing it is built in-tree with nvcc, and if that is
+impossible the import of the op raises.  Every function returns an int status that `check()` turns into a
+Python exception carrying `qw_last_error()`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqw_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_LL = ctypes.c_longlong
+_SZ = ctypes.c_size_t
+
+_CONV_DIMS = [_I] * 10  # B C L K S P O q n_layers embedding
+
+_SIGNATURES = {
+    "qw_abi_version": (_I, []),
+    "qw_last_error": (ctypes.c_char_p, []),
+    "qw_launch_count": (_LL, []),
+    "qw_conv1d_forward": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
+    "qw_conv1d_forward_f64": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
+    "qw_conv1d_workspace_bytes": (_SZ, [_I] * 10),
+    "qw_conv1d_backward": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [_P]),
+    "qw_conv1d_backward_f64": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [_P]),
+    "qw_circuit_workspace_bytes": (_SZ, [_LL, _I, _I, _I]),
+    "qw_circuit_forward": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),
+    "qw_circuit_forward_f64": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),
+    "qw_circuit_backward": (_I, [_P] * 5 + [_P, _SZ, _LL, _I, _I, _I, _P]),
+    "qw_circuit_backward_f64": (_I, [_P] * 5 + [_P, _SZ, _LL, _I, _I, _I, _P]),
+    "qw_log_mel_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "qw_log_mel": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class QwError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) libqw_b200.so.  Raises if it cannot be had."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise QwError(f"{LIB_PATH} is missing; run `python -m qasr_ijcnlp_b200.build`")
+            from . import build as _build
+
+            _build.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        if lib.qw_abi_version() != 1:
+            raise QwError("libqw_b200.so ABI version mismatch; rebuild with `python -m qasr_ijcnlp_b200.build --force`")
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    msg = load().qw_last_error().decode("utf-8", "replace")
+    kind = "bad argument" if status < 0 else f"cudaError {status}"
+    raise QwError(f"{what} failed ({kind}, status {status}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().qw_launch_count())

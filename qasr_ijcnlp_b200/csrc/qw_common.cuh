@@ -1,0 +1,87 @@
+// Shared host/device helpers for libqw_b200.so
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+namespace qw {
+
+// ---- error text (thread local) and launch counter
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int num_sms();
+
+#define QW_CHECK_ARG(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      ::qw::set_error(__VA_ARGS__);   \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define QW_CUDA_OK(expr)                                                        \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      ::qw::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));          \
+      return (int)_e;                                                           \
+    }                                                                           \
+  } while (0)
+
+__host__ __device__ inline int floor_div(int a, int b) {
+  int q = a / b, r = a % b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- small vector load/store of Q contiguous elements (16-byte aligned when Q*sizeof(T) % 16 == 0)
+template <typename T, int Q>
+__device__ __forceinline__ void ld_vec(const T* __restrict__ p, T (&v)[Q]) {
+  if constexpr (sizeof(T) == 4 && Q == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (sizeof(T) == 4 && Q == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else if constexpr (sizeof(T) == 8 && Q == 4) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else if constexpr (sizeof(T) == 8 && Q == 2) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    v[0] = a.x; v[1] = a.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) v[j] = p[j];
+  }
+}
+template <typename T, int Q>
+__device__ __forceinline__ void st_vec(T* __restrict__ p, const T (&v)[Q]) {
+  if constexpr (sizeof(T) == 4 && Q == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (sizeof(T) == 4 && Q == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else if constexpr (sizeof(T) == 8 && Q == 4) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+  } else if constexpr (sizeof(T) == 8 && Q == 2) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) p[j] = v[j];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming (evict-first) global store / load for data touched exactly once
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+
+}  // namespace qw

@@ -1,0 +1,222 @@
+// Host dispatcher + C ABI for QuantumConv1d (kernels: qw_conv1d_kernels.cuh; instantiations: qw_conv1d_inst.cu).
+#include <mutex>
+
+#include "../../include/qw.h"
+#include "qw_conv1d_plan.cuh"
+
+namespace qw {
+
+static std::mutex g_mu;
+static int g_num_sms = 0;
+
+int num_sms() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else {
+      (void)cudaGetLastError();
+      g_num_sms = 148;  // B200
+    }
+  }
+  return g_num_sms;
+}
+
+static Plan make_plan(const ConvDims& d) {
+  Plan p{};
+  const int sms = num_sms();
+  const long long W = (long long)d.B * d.Lout;
+  p.wpt = (W >= 128LL * sms * 4) ? 4 : (W >= 64LL * sms * 4) ? 2 : 1;
+  p.tw = 32 * p.wpt;
+  p.tiles_per_utt = (d.Lout + p.tw - 1) / p.tw;
+  p.num_tiles = d.B * p.tiles_per_utt;
+  p.gridF = p.num_tiles < sms * 16 ? p.num_tiles : sms * 16;
+  // bwd A: persistent CTAs with equal tile counts
+  {
+    const int cap = sms * 6;
+    const int tpc = (p.num_tiles + cap - 1) / cap;
+    p.gridA = (p.num_tiles + tpc - 1) / tpc;
+  }
+  p.KT = (d.K == 3) ? 3 : 8;
+  p.ptiles_per_utt = (d.L + kTP - 1) / kTP;
+  p.num_ptiles = d.B * p.ptiles_per_utt;
+  p.nchunks = (d.C + 31) / 32;
+  p.Cpad = p.nchunks * 32;
+  {
+    int cap = sms * 8 / p.nchunks;
+    if (cap < 1) cap = 1;
+    const int tpc = (p.num_ptiles + cap - 1) / cap;
+    p.gridBx = (p.num_ptiles + tpc - 1) / tpc;
+  }
+  p.PA = partA_len(d.O, d.Q, d.Lq);
+  p.PB = p.Cpad * d.Q * p.KT;
+  return p;
+}
+
+static int check_dims(ConvDims& d) {
+  QW_CHECK_ARG(d.B > 0 && d.C > 0 && d.L > 0 && d.K > 0 && d.S > 0 && d.P >= 0 && d.O > 0, -1,
+               "bad shape B=%d C=%d L=%d K=%d S=%d P=%d O=%d", d.B, d.C, d.L, d.K, d.S, d.P, d.O);
+  QW_CHECK_ARG(d.L + 2 * d.P >= d.K, -1, "kernel_size %d larger than padded length %d", d.K, d.L + 2 * d.P);
+  d.Lout = (d.L + 2 * d.P - d.K) / d.S + 1;
+  QW_CHECK_ARG(d.Q >= 1 && d.Q <= (long long)d.C * d.K, -1, "n_qubits=%d must be in [1, C*K=%d]", d.Q, d.C * d.K);
+  QW_CHECK_ARG(d.Q <= 4, -2, "fused QuantumConv1d kernels support n_qubits <= 4 (got %d)", d.Q);
+  QW_CHECK_ARG(d.Lq >= 1 && d.Lq <= 8, -2, "n_layers=%d must be in [1,8]", d.Lq);
+  QW_CHECK_ARG(d.emb == kEmbAmplitude, -2, "embedding=%d not supported by the fused kernels (amplitude only)", d.emb);
+  QW_CHECK_ARG((long long)d.B * d.C * d.L < (1LL << 40) && (long long)d.B * d.O * d.Lout < (1LL << 40), -1, "tensor too large");
+  return 0;
+}
+
+template <typename T>
+static int conv1d_forward_impl(const T* x, const T* w_pre, const T* b_pre, const T* qwts, const T* w_post, const T* b_post,
+                               T* y, T* pre_save, ConvDims d, void* stream) {
+  QW_CHECK_ARG(x && w_pre && b_pre && qwts && w_post && b_post && y, -1, "null pointer argument");
+  if (int e = check_dims(d)) return e;
+  const Plan p = make_plan(d);
+  FwdArgs<T> a{x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, p.tiles_per_utt, p.num_tiles};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d.Q) {
+    case 1: return fwd_tq<T, 1>(a, p, st);
+    case 2: return fwd_tq<T, 2>(a, p, st);
+    case 3: return fwd_tq<T, 3>(a, p, st);
+    default: return fwd_tq<T, 4>(a, p, st);
+  }
+}
+
+template <typename T>
+static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* qwts, const T* w_post,
+                                T* gx, T* gw_pre, T* gb_pre, T* gqw, T* gw_post, T* gb_post, void* workspace,
+                                size_t ws_bytes, ConvDims d, void* stream) {
+  QW_CHECK_ARG(gy && x && pre_save && w_pre && qwts && w_post && gw_pre && gb_pre && gqw && gw_post && gb_post && workspace,
+               -1, "null pointer argument");
+  if (int e = check_dims(d)) return e;
+  QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
+  const Plan p = make_plan(d);
+  const WsLayout<T> wl = ws_layout<T>(d, p);
+  QW_CHECK_ARG(ws_bytes >= wl.total, -3, "workspace too small: %zu < %zu", ws_bytes, wl.total);
+  QW_CHECK_ARG(((uintptr_t)workspace & 15) == 0, -1, "workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  switch (d.Q) {
+    case 1: return bwd_tq<T, 1>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, p, st);
+    case 2: return bwd_tq<T, 2>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, p, st);
+    case 3: return bwd_tq<T, 3>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, p, st);
+    default: return bwd_tq<T, 4>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, p, st);
+  }
+}
+
+static int circ_grid(long long W) {
+  const long long need = (W + kThreads - 1) / kThreads;
+  const long long cap = (long long)num_sms() * 8;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+static int circ_PA(int q, int Lq) { return (int)align_up((size_t)Lq * q * 8, 32); }
+
+template <typename T>
+static int circuit_forward_impl(const T* pre, const T* qwts, T* out, long long W, int q, int Lq, int emb, void* stream) {
+  QW_CHECK_ARG(pre && qwts && out && W > 0, -1, "null pointer or empty batch");
+  QW_CHECK_ARG(q >= 1 && q <= 4, -2, "circuit kernels support n_qubits in [1,4] (got %d)", q);
+  QW_CHECK_ARG(Lq >= 1 && Lq <= 8, -2, "n_layers=%d must be in [1,8]", Lq);
+  QW_CHECK_ARG(emb == kEmbAmplitude, -2, "embedding=%d not supported", emb);
+  CircArgs<T> a{pre, qwts, nullptr, out, nullptr, nullptr, W, q, Lq, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = circ_grid(W);
+  switch (q) {
+    case 1: return circ_fwd_tq<T, 1>(a, grid, st);
+    case 2: return circ_fwd_tq<T, 2>(a, grid, st);
+    case 3: return circ_fwd_tq<T, 3>(a, grid, st);
+    default: return circ_fwd_tq<T, 4>(a, grid, st);
+  }
+}
+
+template <typename T>
+static int circuit_backward_impl(const T* pre, const T* qwts, const T* gout, T* gpre, T* gqw, void* workspace, size_t ws_bytes,
+                                 long long W, int q, int Lq, int emb, void* stream) {
+  QW_CHECK_ARG(pre && qwts && gout && gpre && gqw && workspace && W > 0, -1, "null pointer or empty batch");
+  QW_CHECK_ARG(q >= 1 && q <= 4, -2, "circuit kernels support n_qubits in [1,4] (got %d)", q);
+  QW_CHECK_ARG(Lq >= 1 && Lq <= 8, -2, "n_layers=%d must be in [1,8]", Lq);
+  QW_CHECK_ARG(emb == kEmbAmplitude, -2, "embedding=%d not supported", emb);
+  const int grid = circ_grid(W), PA = circ_PA(q, Lq);
+  QW_CHECK_ARG(ws_bytes >= (size_t)grid * PA * sizeof(T), -3, "workspace too small");
+  CircArgs<T> a{pre, qwts, gout, nullptr, gpre, (T*)workspace, W, q, Lq, PA};
+  cudaStream_t st = (cudaStream_t)stream;
+  int e = 0;
+  switch (q) {
+    case 1: e = circ_bwd_tq<T, 1>(a, grid, st); break;
+    case 2: e = circ_bwd_tq<T, 2>(a, grid, st); break;
+    case 3: e = circ_bwd_tq<T, 3>(a, grid, st); break;
+    default: e = circ_bwd_tq<T, 4>(a, grid, st); break;
+  }
+  if (e) return e;
+  circuit_finalize_kernel<T><<<PA / 32, kFinThreads, 0, st>>>((const T*)workspace, qwts, gqw, grid, PA, q, Lq);
+  count_launch();
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace qw
+
+// =============================================================================================== C ABI
+using qw::ConvDims;
+
+extern "C" {
+
+int qw_conv1d_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
+                      const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O, int q,
+                      int n_layers, int embedding, void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  return qw::conv1d_forward_impl<float>(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, stream);
+}
+int qw_conv1d_forward_f64(const double* x, const double* w_pre, const double* b_pre, const double* qwts, const double* w_post,
+                          const double* b_post, double* y, double* pre_save, int B, int C, int L, int K, int S, int P, int O,
+                          int q, int n_layers, int embedding, void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  return qw::conv1d_forward_impl<double>(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, stream);
+}
+
+size_t qw_conv1d_workspace_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int elem_size) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, 0, 0};
+  if (qw::check_dims(d)) return 0;
+  const qw::Plan p = qw::make_plan(d);
+  return elem_size == 8 ? qw::ws_layout<double>(d, p).total : qw::ws_layout<float>(d, p).total;
+}
+
+int qw_conv1d_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
+                       const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
+                       void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O, int q, int n_layers,
+                       int embedding, void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  return qw::conv1d_backward_impl<float>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
+                                         workspace, ws_bytes, d, stream);
+}
+int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_save, const double* w_pre, const double* qwts,
+                           const double* w_post, double* gx, double* gw_pre, double* gb_pre, double* gqw, double* gw_post,
+                           double* gb_post, void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O,
+                           int q, int n_layers, int embedding, void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  return qw::conv1d_backward_impl<double>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
+                                          workspace, ws_bytes, d, stream);
+}
+
+size_t qw_circuit_workspace_bytes(long long W, int q, int n_layers, int elem_size) {
+  if (W <= 0 || q < 1 || n_layers < 1) return 0;
+  return (size_t)qw::circ_grid(W) * qw::circ_PA(q, n_layers) * (size_t)(elem_size == 8 ? 8 : 4);
+}
+int qw_circuit_forward(const float* pre, const float* qwts, float* out, long long W, int q, int n_layers, int embedding,
+                       void* stream) {
+  return qw::circuit_forward_impl<float>(pre, qwts, out, W, q, n_layers, embedding, stream);
+}
+int qw_circuit_forward_f64(const double* pre, const double* qwts, double* out, long long W, int q, int n_layers, int embedding,
+                           void* stream) {
+  return qw::circuit_forward_impl<double>(pre, qwts, out, W, q, n_layers, embedding, stream);
+}
+int qw_circuit_backward(const float* pre, const float* qwts, const float* gout, float* gpre, float* gqw, void* workspace,
+                        size_t ws_bytes, long long W, int q, int n_layers, int embedding, void* stream) {
+  return qw::circuit_backward_impl<float>(pre, qwts, gout, gpre, gqw, workspace, ws_bytes, W, q, n_layers, embedding, stream);
+}
+int qw_circuit_backward_f64(const double* pre, const double* qwts, const double* gout, double* gpre, double* gqw,
+                            void* workspace, size_t ws_bytes, long long W, int q, int n_layers, int embedding, void* stream) {
+  return qw::circuit_backward_impl<double>(pre, qwts, gout, gpre, gqw, workspace, ws_bytes, W, q, n_layers, embedding, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""Drop-in `QuantumConv1d` (host mirror of /root/reference/quantum_whisper.py:45-128).
+
+Same constructor, attributes, forward signature and state_dict layout as the reference:
+``pre_conv.weight (q, C*K)``, ``pre_conv.bias (q)``, ``post_conv.weight (O, q)``, ``post_conv.bias (O)``,
+``quantum_weights (q, 3)``.  The forward/backward are hand-written sm_100a kernels reached through the C ABI
+in ``include/qw.h`` (no PennyLane, no Python loop, no CPU fallback).
+
+Extensions (keyword-only, defaults == the reference): ``n_layers`` (``quantum_weights`` becomes
+``(n_layers, q, 3)`` when > 1) and ``embedding`` ("amplitude" | "angle").
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+EMBEDDINGS = {"amplitude": 0, "angle": 1}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def out_length(L: int, K: int, S: int, P: int) -> int:
+    """quantum_whisper.py:103"""
+    return (L + 2 * P - K) // S + 1
+
+
+class _QuantumConv1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_pre, b_pre, qw, w_post, b_post, K, S, P, n_layers, emb):
+        lib = _lib.load()
+        B, C, L = x.shape
+        O, q = w_post.shape
+        Lout = out_length(L, K, S, P)
+        if Lout <= 0:
+            raise ValueError(f"kernel_size {K} does not fit the padded input length {L + 2 * P}")
+        f64 = x.dtype == torch.float64
+        x = x.contiguous()
+        params = [t.contiguous() for t in (w_pre, b_pre, qw, w_post, b_post)]
+        y = torch.empty(B, O, Lout, device=x.device, dtype=x.dtype)
+        need_bwd = any(ctx.needs_input_grad[:6])
+        pre_save = torch.empty(B * Lout, q, device=x.device, dtype=x.dtype) if need_bwd else None
+        fn = lib.qw_conv1d_forward_f64 if f64 else lib.qw_conv1d_forward
+        with torch.cuda.device(x.device):
+            st = fn(_ptr(x), *[_ptr(p) for p in params], _ptr(y), _ptr(pre_save),
+                    B, C, L, K, S, P, O, q, n_layers, emb, _stream())
+        _lib.check(st, "qw_conv1d_forward")
+        if need_bwd:
+            ctx.save_for_backward(x, pre_save, *params)
+            ctx.cfg = (B, C, L, K, S, P, O, q, n_layers, emb, f64)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, pre_save, w_pre, b_pre, qw, w_post, b_post = ctx.saved_tensors
+        B, C, L, K, S, P, O, q, n_layers, emb, f64 = ctx.cfg
+        gy = gy.contiguous()
+        dev, dt = x.device, x.dtype
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw_pre = torch.empty_like(w_pre)
+        gb_pre = torch.empty_like(b_pre)
+        gqw = torch.empty_like(qw)
+        gw_post = torch.empty_like(w_post)
+        gb_post = torch.empty_like(b_post)
+        nbytes = lib.qw_conv1d_workspace_bytes(B, C, L, K, S, P, O, q, n_layers, 8 if f64 else 4)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        fn = lib.qw_conv1d_backward_f64 if f64 else lib.qw_conv1d_backward
+        with torch.cuda.device(dev):
+            st = fn(_ptr(gy), _ptr(x), _ptr(pre_save), _ptr(w_pre), _ptr(qw), _ptr(w_post), _ptr(gx), _ptr(gw_pre),
+                    _ptr(gb_pre), _ptr(gqw), _ptr(gw_post), _ptr(gb_post), _ptr(ws), nbytes,
+                    B, C, L, K, S, P, O, q, n_layers, emb, _stream())
+        _lib.check(st, "qw_conv1d_backward")
+        return gx, gw_pre, gb_pre, gqw, gw_post, gb_post, None, None, None, None, None
+
+
+def quantum_conv1d(x, w_pre, b_pre, quantum_weights, w_post, b_post, kernel_size, stride=1, padding=0,
+                   n_layers=1, embedding="amplitude"):
+    """Functional form.  x: (B, C, L) CUDA float32 (or float64 for the validation build)."""
+    if x.dim() != 3:
+        raise ValueError(f"expected input of shape (batch, channels, length), got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("QuantumConv1d (B200 build) has no CPU path: move the module and input to a CUDA device")
+    if x.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"QuantumConv1d supports float32 (and float64 validation) inputs, got {x.dtype}")
+    q = w_post.shape[1]
+    C = x.shape[1]
+    if w_pre.shape != (q, C * kernel_size):
+        raise ValueError(f"pre_conv.weight has shape {tuple(w_pre.shape)}, expected {(q, C * kernel_size)} "
+                         f"for {C} input channels and kernel_size {kernel_size}")
+    for name, p in (("pre_conv.weight", w_pre), ("pre_conv.bias", b_pre), ("quantum_weights", quantum_weights),
+                    ("post_conv.weight", w_post), ("post_conv.bias", b_post)):
+        if p.device != x.device or p.dtype != x.dtype:
+            raise RuntimeError(f"{name} is {p.dtype} on {p.device} but the input is {x.dtype} on {x.device}")
+    if quantum_weights.numel() != n_layers * q * 3:
+        raise ValueError(f"quantum_weights has {quantum_weights.numel()} elements, expected {n_layers}*{q}*3")
+    return _QuantumConv1dFn.apply(x, w_pre, b_pre, quantum_weights, w_post, b_post, int(kernel_size), int(stride),
+                                  int(padding), int(n_layers), EMBEDDINGS[embedding])
+
+
+class QuantumConv1d(nn.Module):
+    """Quantum 1D convolution replacing Whisper's Conv1d (quantum_whisper.py:45-128)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, stride: int = 1, padding: int = 0,
+                 n_qubits: int = 4, *, n_layers: int = 1, embedding: str = "amplitude"):
+        super().__init__()
+        if embedding not in EMBEDDINGS:
+            raise ValueError(f"embedding must be one of {sorted(EMBEDDINGS)}, got {embedding!r}")
+        if n_layers < 1:
+            raise ValueError("n_layers must be >= 1")
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.padding = padding
+        self.n_qubits = min(n_qubits, in_channels * kernel_size)  # :55
+        self.n_layers = n_layers
+        self.embedding = embedding
+        # same construction order as the reference so the same seed gives the same parameters (:58-59,:88)
+        self.pre_conv = nn.Linear(in_channels * kernel_size, self.n_qubits)
+        self.post_conv = nn.Linear(self.n_qubits, out_channels)
+        shape = (self.n_qubits, 3) if n_layers == 1 else (n_layers, self.n_qubits, 3)
+        self.quantum_weights = nn.Parameter(torch.randn(*shape))
+
+    def to(self, *args, **kwargs):  # the reference overrides .to(device) and returns self (:90-93)
+        super().to(*args, **kwargs)
+        return self
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() == 3 and x.shape[1] != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[1]}")
+        return quantum_conv1d(x, self.pre_conv.weight, self.pre_conv.bias, self.quantum_weights,
+                              self.post_conv.weight, self.post_conv.bias, self.kernel_size, self.stride,
+                              self.padding, self.n_layers, self.embedding)
+
+    def extra_repr(self) -> str:
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, n_qubits={self.n_qubits}, n_layers={self.n_layers}, "
+                f"embedding={self.embedding!r}")
+
+
+class _CircuitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pre, qw, n_layers, emb):
+        lib = _lib.load()
+        W, q = pre.shape
+        f64 = pre.dtype == torch.float64
+        pre = pre.contiguous()
+        qw = qw.contiguous()
+        out = torch.empty_like(pre)
+        fn = lib.qw_circuit_forward_f64 if f64 else lib.qw_circuit_forward
+        with torch.cuda.device(pre.device):
+            st = fn(_ptr(pre), _ptr(qw), _ptr(out), W, q, n_layers, emb, _stream())
+        _lib.check(st, "qw_circuit_forward")
+        ctx.save_for_backward(pre, qw)
+        ctx.cfg = (W, q, n_layers, emb, f64)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        pre, qw = ctx.saved_tensors
+        W, q, n_layers, emb, f64 = ctx.cfg
+        gout = gout.contiguous()
+        gpre = torch.empty_like(pre)
+        gqw = torch.empty_like(qw)
+        nbytes = lib.qw_circuit_workspace_bytes(W, q, n_layers, 8 if f64 else 4)
+        ws = torch.empty(max(nbytes, 16), device=pre.device, dtype=torch.uint8)
+        fn = lib.qw_circuit_backward_f64 if f64 else lib.qw_circuit_backward
+        with torch.cuda.device(pre.device):
+            st = fn(_ptr(pre), _ptr(qw), _ptr(gout), _ptr(gpre), _ptr(gqw), _ptr(ws), nbytes, W, q, n_layers, emb,
+                    _stream())
+        _lib.check(st, "qw_circuit_backward")
+        return gpre, gqw, None, None
+
+
+def quantum_circuit(pre: torch.Tensor, quantum_weights: torch.Tensor, n_layers: int = 1,
+                    embedding: str = "amplitude") -> torch.Tensor:
+    """The QNode alone, batched: pre (W, q) -> <Z_i> (W, q)  (quantum_whisper.py:64-85)."""
+    if not pre.is_cuda:
+        raise RuntimeError("quantum_circuit (B200 build) has no CPU path")
+    if pre.dim() != 2:
+        raise ValueError("pre must be (windows, n_qubits)")
+    return _CircuitFn.apply(pre, quantum_weights, int(n_layers), EMBEDDINGS[embedding])

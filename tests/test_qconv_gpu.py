@@ -1,0 +1,266 @@
+"""Parity of the CUDA QuantumConv1d / circuit kernels (through the C ABI) against the fp64 oracle.
+
+Tolerances (BASELINE.json north_star): fp32 <= 1e-5 abs on <Z_i> and per-window gradients, fp64 validation
+build <= 1e-10, window indexing bit-exact.  For quantities that are sums over many windows (layer outputs
+after post_conv are not, weight gradients are) the bound is relative to the largest reference entry and is
+written next to each assert (SURVEY.md 8c "Tolerances").
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qconv_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from qasr_ijcnlp_b200 import _lib, quantum_conv1d as qc
+    return _lib, qc
+
+
+def _kat(golden_dir):
+    with open(os.path.join(golden_dir, "qconv_kat.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float64, 1e-10)])
+def test_circuit_known_answers(cuda, golden_dir, dtype, tol):
+    _, qc = _mods()
+    kat = _kat(golden_dir)
+    pre = torch.tensor([kat["pre"]], dtype=dtype, device=cuda, requires_grad=True)
+    for name in ("kat0", "kat1"):
+        k = kat[name]
+        w = torch.tensor(k["quantum_weights"], dtype=dtype, device=cuda, requires_grad=True)
+        out = qc.quantum_circuit(pre, w)
+        assert np.abs(out.detach().cpu().numpy()[0] - np.array(k["out"])).max() <= tol
+        if "cotangent" in k:
+            g = torch.tensor([k["cotangent"]], dtype=dtype, device=cuda)
+            gp, gw = torch.autograd.grad(out, [pre, w], g)
+            assert np.abs(gp.cpu().numpy()[0] - np.array(k["grad_pre"])).max() <= tol
+            assert np.abs(gw.cpu().numpy() - np.array(k["grad_quantum_weights"])).max() <= tol
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 4])
+@pytest.mark.parametrize("n_layers", [1, 2, 3])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float64, 1e-10)])
+def test_circuit_random_vs_oracle(cuda, q, n_layers, dtype, tol):
+    _, qc = _mods()
+    g = torch.Generator().manual_seed(100 * q + n_layers)
+    W = 3001  # ragged vs the 128-thread blocks
+    pre64 = torch.randn(W, q, generator=g, dtype=torch.float64)
+    shape = (q, 3) if n_layers == 1 else (n_layers, q, 3)
+    w64 = torch.randn(*shape, generator=g, dtype=torch.float64)
+    cot64 = torch.randn(W, q, generator=g, dtype=torch.float64)
+    # the oracle sees exactly the values the kernel sees (rounded to the kernel dtype)
+    pre_o = pre64.to(dtype).double().requires_grad_(True)
+    w_o = w64.to(dtype).double().requires_grad_(True)
+    out_o = qo.circuit_expvals(pre_o, w_o)
+    gp_o, gw_o = torch.autograd.grad(out_o, [pre_o, w_o], cot64.to(dtype).double())
+    pre = pre64.to(dtype).to(cuda).requires_grad_(True)
+    w = w64.to(dtype).to(cuda).requires_grad_(True)
+    out = qc.quantum_circuit(pre, w, n_layers=n_layers)
+    gp, gw = torch.autograd.grad(out, [pre, w], cot64.to(dtype).to(cuda))
+    assert (out.detach().cpu().double() - out_o.detach()).abs().max().item() <= tol
+    # per-window gradients: |d out / d pre| scales with 1/||pre||; bound relative to that scale
+    scale = (1.0 / pre_o.detach().norm(dim=1, keepdim=True)).clamp(min=1.0)
+    assert ((gp.cpu().double() - gp_o) / scale).abs().max().item() <= tol
+    # weight gradient is a sum over W windows: bound relative to its largest entry
+    assert (gw.cpu().double() - gw_o).abs().max().item() <= tol * max(1.0, gw_o.abs().max().item()) * 4
+
+
+def test_circuit_identities(cuda):
+    """SURVEY.md 8c identities: omega-invariance, scale invariance, product-state channels."""
+    _, qc = _mods()
+    g = torch.Generator().manual_seed(5)
+    pre = torch.randn(513, 4, generator=g).to(cuda)
+    w = torch.randn(4, 3, generator=g).to(cuda)
+    out = qc.quantum_circuit(pre, w)
+    w2 = w.clone()
+    w2[:, 2] += torch.randn(4, generator=g).to(cuda)  # omega on every wire
+    w2[0, 0] += 0.7  # phi on wires < q - m
+    w2[1, 0] -= 1.3
+    assert (qc.quantum_circuit(pre, w2) - out).abs().max().item() <= 1e-5
+    assert (qc.quantum_circuit(-3.7 * pre, w) - out).abs().max().item() <= 1e-5
+    c0 = torch.cos(w[0, 1])
+    c1 = torch.cos(w[1, 1])
+    assert (out[:, 0] - c0).abs().max().item() <= 1e-5
+    assert (out[:, 1] - c0 * c1).abs().max().item() <= 1e-5
+
+
+GEOMS = [
+    # (B, C, L, K, S, P, O, q) -- Whisper-Tiny stem geometries at reduced length + ragged/edge cases
+    (2, 80, 200, 3, 1, 1, 384, 4),
+    (2, 384, 203, 3, 2, 1, 384, 4),
+    (3, 5, 77, 3, 1, 1, 9, 4),
+    (1, 7, 64, 3, 2, 0, 33, 3),
+    (2, 4, 50, 5, 3, 2, 6, 2),
+    (2, 3, 31, 1, 1, 0, 5, 1),
+    (1, 33, 130, 4, 2, 3, 65, 4),
+]
+
+
+def _run_layer(cuda, geom, dtype, n_layers=1, seed=0):
+    _, qc = _mods()
+    B, C, L, K, S, P, O, q = geom
+    params64 = qo.make_params(C, O, K, q, n_layers=n_layers, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x64 = torch.randn(B, C, L, generator=g, dtype=torch.float64)
+    Lo = qo.out_length(L, K, S, P)
+    gy64 = torch.randn(B, O, Lo, generator=g, dtype=torch.float64)
+    # oracle on the dtype-rounded values
+    xr = x64.to(dtype).double()
+    pr = [p.to(dtype).double() for p in params64]
+    ref = qo.qconv1d_grads(xr, pr, gy64.to(dtype).double(), K, S, P)
+    x = x64.to(dtype).to(cuda).requires_grad_(True)
+    ps = [p.to(dtype).to(cuda).requires_grad_(True) for p in params64]
+    y = qc.quantum_conv1d(x, *ps, kernel_size=K, stride=S, padding=P, n_layers=n_layers)
+    grads = torch.autograd.grad(y, [x] + ps, gy64.to(dtype).to(cuda))
+    got = dict(zip(["x", "w_pre", "b_pre", "qweights", "w_post", "b_post"], [t.cpu().double() for t in grads]))
+    got["y"] = y.detach().cpu().double()
+    return got, ref
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_layer_f64_validation_build(cuda, geom):
+    got, ref = _run_layer(cuda, geom, torch.float64)
+    for k in ("y", "x", "w_pre", "b_pre", "qweights", "w_post", "b_post"):
+        assert _rel(got[k], ref[k]) <= 1e-10, k  # fp64 validation build: 1e-10 (relative to max(1,|ref|))
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_layer_f32(cuda, geom):
+    got, ref = _run_layer(cuda, geom, torch.float32)
+    # y = post_conv(<Z>) with |w_post| <= 1/sqrt(q): 1e-5 on <Z> -> <= ~2e-5 on y; the fp32 pre_conv
+    # reduction adds O(1e-6 / ||pre||) per window, so the bound used is 5e-5 abs.
+    assert (got["y"] - ref["y"]).abs().max().item() <= 5e-5
+    # gradients are sums over up to B*L_out windows / O channels: bound relative to the largest entry
+    for k in ("x", "w_pre", "b_pre", "qweights", "w_post", "b_post"):
+        assert _rel(got[k], ref[k]) <= 5e-5, k
+
+
+@pytest.mark.parametrize("n_layers", [2, 3])
+def test_layer_multilayer_extension(cuda, n_layers):
+    got, ref = _run_layer(cuda, (2, 80, 150, 3, 1, 1, 384, 4), torch.float64, n_layers=n_layers, seed=3)
+    for k in ("y", "x", "w_pre", "b_pre", "qweights", "w_post", "b_post"):
+        assert _rel(got[k], ref[k]) <= 1e-10, k
+
+
+@pytest.mark.parametrize("geom", [(2, 80, 3000, 3, 1, 1, 384, 4), (2, 384, 3000, 3, 2, 1, 384, 4), (3, 6, 100, 5, 3, 2, 4, 4)])
+def test_window_indexing_bit_exact(cuda, geom):
+    """One-hot pre_conv rows turn pre_save into a gather of x: must equal F.unfold bit for bit
+    (quantum_whisper.py:99-111; feature f = c*K + k; zero padding both sides)."""
+    _lib, qc = _mods()
+    lib = _lib.load()
+    B, C, L, K, S, P, O, q = geom
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, L, generator=g)
+    Lo = qo.out_length(L, K, S, P)
+    ref_win = torch.nn.functional.unfold(x[:, :, None, :], (1, K), padding=(0, P), stride=(1, S))  # (B, C*K, Lo)
+    feats = torch.randint(0, C * K, (8, q), generator=g).tolist() + [[0, 1, C * K - 2, C * K - 1][:q]]
+    for fsel in feats:
+        w_pre = torch.zeros(q, C * K)
+        for j, f in enumerate(fsel):
+            w_pre[j, f] = 1.0
+        dev = [t.to(cuda).contiguous() for t in (x, w_pre, torch.zeros(q), torch.randn(q, 3, generator=g),
+                                                 torch.randn(O, q, generator=g), torch.zeros(O))]
+        y = torch.empty(B, O, Lo, device=cuda)
+        pre_save = torch.empty(B * Lo, q, device=cuda)
+        st = lib.qw_conv1d_forward(*[ctypes.c_void_p(t.data_ptr()) for t in dev], ctypes.c_void_p(y.data_ptr()),
+                                   ctypes.c_void_p(pre_save.data_ptr()), B, C, L, K, S, P, O, q, 1, 0,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(st, "qw_conv1d_forward")
+        got = pre_save.cpu().reshape(B, Lo, q)
+        want = ref_win[:, fsel, :].permute(0, 2, 1)
+        assert torch.equal(got, want)
+
+
+def test_config1_full_size_parity(cuda):
+    """BASELINE.json configs[0]: QuantumConv1d(80,384,3,padding=1,n_qubits=4), x = randn(2,80,3000), seed 0,
+    module-default init; y, per-window <Z> (on the kernel's own fp32 pre_conv output) and all grads."""
+    _, qc = _mods()
+    torch.manual_seed(0)
+    m = qc.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4)
+    x = torch.randn(2, 80, 3000)
+    for xin in (x, (torch.rand(2, 80, 3000) * 3 - 1.5)):
+        params = [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias]
+        p64 = [p.detach().double() for p in params]
+        gy = torch.randn(2, 384, 3000)
+        ref = qo.qconv1d_grads(xin.double(), p64, gy.double(), 3, 1, 1)
+        md = m.to(cuda)
+        xc = xin.to(cuda).requires_grad_(True)
+        y = md(xc)
+        grads = torch.autograd.grad(y, [xc] + list(md.parameters()), gy.to(cuda))
+        names = ["x"] + [n for n, _ in md.named_parameters()]
+        assert names == ["x", "quantum_weights", "pre_conv.weight", "pre_conv.bias", "post_conv.weight", "post_conv.bias"]
+        key = {"quantum_weights": "qweights", "pre_conv.weight": "w_pre", "pre_conv.bias": "b_pre",
+               "post_conv.weight": "w_post", "post_conv.bias": "b_post", "x": "x"}
+        assert (y.detach().cpu().double() - ref["y"]).abs().max().item() <= 5e-5
+        for n, gr in zip(names, grads):
+            assert _rel(gr.cpu().double(), ref[key[n]]) <= 5e-5, n
+        m = m.to("cpu")
+
+
+def test_full_size_properties_conv2(cuda):
+    """Whisper-Tiny conv2 at batch 16 (BASELINE configs[1]/[2] stem shape): size-independent properties.
+    (i) scale invariance of the embedding: x * grad_x sums to 0 per window set -> <x, gx> == 0 when b_pre = 0;
+    (ii) linearity of the backward in gy; (iii) parity of a random subset of windows with the oracle."""
+    _, qc = _mods()
+    torch.manual_seed(3)
+    m = qc.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    with torch.no_grad():
+        m.pre_conv.bias.zero_()
+    x = torch.randn(16, 384, 3000, device=cuda, requires_grad=True)
+    y = m(x)
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, [x, m.pre_conv.weight], gy, retain_graph=True)
+    # (i) y is invariant under x -> (1+eps) x when b_pre = 0, so <x, dL/dx> = 0 (up to fp32 rounding of a 18M-term sum)
+    dot = (x.detach().double() * gx.double()).sum().item()
+    scale = (x.detach().double().abs() * gx.double().abs()).sum().item()
+    assert abs(dot) <= 1e-5 * scale
+    # same for the pre_conv weight: <W, dL/dW> = 0
+    dotw = (m.pre_conv.weight.detach().double() * gw.double()).sum().item()
+    scalew = (m.pre_conv.weight.detach().double().abs() * gw.double().abs()).sum().item()
+    assert abs(dotw) <= 1e-4 * scalew
+    # (ii) linearity in gy
+    gx2, = torch.autograd.grad(y, [x], 2.0 * gy, retain_graph=True)
+    assert (gx2 - 2.0 * gx).abs().max().item() <= 1e-6 * max(1.0, gx.abs().max().item())
+    # (iii) oracle on utterances 0 and 15, first 256 input columns (128 windows; window 127 needs col 254)
+    for b in (0, 15):
+        xs = x.detach()[b:b + 1, :, :256].cpu().double()
+        p64 = [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias]
+        yo = qo.qconv1d_forward(xs, *[p.detach().cpu().double() for p in p64], K=3, S=2, P=1)
+        assert (y.detach()[b, :, :127].cpu().double() - yo[0, :, :127]).abs().max().item() <= 5e-5
+
+
+def test_errors(cuda):
+    _lib, qc = _mods()
+    m = qc.QuantumConv1d(8, 16, 3, padding=1, n_qubits=4)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 8, 10))  # CPU input: no CPU path
+    m = m.to(cuda)
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 7, 10, device=cuda))
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 8, 10, device=cuda).half())
+    # q is clamped like the reference (quantum_whisper.py:55)
+    assert qc.QuantumConv1d(1, 4, 2, n_qubits=4).n_qubits == 2
+    # non-contiguous input is accepted
+    x = torch.randn(2, 10, 8, device=cuda).transpose(1, 2)
+    assert m(x).shape == (2, 16, 10)
+    # zero window -> NaN, exactly like the reference's unguarded normalisation (quantum_whisper.py:74)
+    with torch.no_grad():
+        m.pre_conv.bias.zero_()
+    y = m(torch.zeros(1, 8, 10, device=cuda))
+    assert torch.isnan(y).all()
+    lib = _lib.load()
+    assert lib.qw_conv1d_forward(None, None, None, None, None, None, None, None, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, None) == -1
+    assert b"null" in lib.qw_last_error()
