@@ -1,0 +1,574 @@
+#!/usr/bin/env python
+"""bench.py -- QuantumConv1d windows/s forward+backward on the Whisper-Tiny quantum stem (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 16]
+
+One "step" = one pass of the hot path over one batch of synthetic input: conv1 (80->384, k3 s1 p1, 3000 frames)
+forward + backward and conv2 (384->384, k3 s2 p1) forward + backward (with grad_x), n_qubits = 4, at
+`--batch` utterances per GPU (BASELINE.json configs[1]/[2]: batch 16, 80 mel x 3000 frames) = 4500 windows per
+utterance per step.
+
+  value      windows/s with every input already resident in HBM; the step is one CUDA graph of the C-ABI calls,
+             replayed over `nsets` rotating buffer sets so no kernel finds its input in L2.
+  roofline   the dominant kernel (largest share of the step), timed with CUDA events inside the library
+             (qw_profile_*), algorithmic bytes / duration against the measured HBM peak.
+  e2e        the same step through the public nn.Module API with HOST input: pinned mel batch -> H2D -> conv1 ->
+             GELU -> conv2 -> loss -> backward -> D2H of loss and the quantum-layer gradients, all inside the
+             timed region.
+  cpu_baseline  the literal-loop fp64 restatement of the reference (oracle/, PennyLane is not installable) on a
+             bounded sample, on this box's host cores.
+`--impl reference` times that same literal-loop restatement as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "qconv_windows_per_sec_fwd_bwd"
+UNIT = "windows/s"
+N_MELS, N_STATE, N_FRAMES, Q = 80, 384, 3000, 4
+LAYERS = {
+    "conv1": dict(C=N_MELS, O=N_STATE, K=3, S=1, P=1, L=N_FRAMES, Lout=3000, need_gx=False),
+    "conv2": dict(C=N_STATE, O=N_STATE, K=3, S=2, P=1, L=N_FRAMES, Lout=1500, need_gx=True),
+}
+WINDOWS_PER_UTT = 4500
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
+    ap.add_argument("--nsets", type=int, default=4, help="rotating buffer sets (L2 defeat)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoder", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+def load_traffic():
+    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return {}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                    pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        return out
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# --------------------------------------------------------------------------------------------- B200 arm
+class StemBuffers:
+    """HBM-resident inputs/outputs of one step, for one rotating set."""
+
+    def __init__(self, B, dev, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.t = {}
+        for name, cfg in LAYERS.items():
+            C, O, L, Lout = cfg["C"], cfg["O"], cfg["L"], cfg["Lout"]
+            self.t[name] = dict(
+                x=torch.randn(B, C, L, device=dev, generator=g),
+                y=torch.empty(B, O, Lout, device=dev),
+                gy=torch.randn(B, O, Lout, device=dev, generator=g),
+                pre=torch.empty(B * Lout, Q, device=dev),
+                gx=torch.empty(B, C, L, device=dev) if cfg["need_gx"] else None,
+            )
+
+
+class StemParams:
+    def __init__(self, dev, seed=0):
+        from qasr_ijcnlp_b200 import QuantumConv1d
+
+        torch.manual_seed(seed)
+        self.mods = {
+            "conv1": QuantumConv1d(N_MELS, N_STATE, kernel_size=3, padding=1, n_qubits=Q).to(dev),
+            "conv2": QuantumConv1d(N_STATE, N_STATE, kernel_size=3, stride=2, padding=1, n_qubits=Q).to(dev),
+        }
+        self.p, self.g = {}, {}
+        for name, m in self.mods.items():
+            ps = [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias]
+            self.p[name] = [t.detach().contiguous() for t in ps]
+            self.g[name] = [torch.empty_like(t) for t in self.p[name]]
+
+
+class StemRunner:
+    def __init__(self, B, dev, nsets):
+        from qasr_ijcnlp_b200 import _lib
+
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.B, self.dev = B, dev
+        self.params = StemParams(dev)
+        self.sets = [StemBuffers(B, dev, 100 + s) for s in range(nsets)]
+        self.ws = {}
+        for name, cfg in LAYERS.items():
+            n = self.lib.qw_conv1d_workspace_bytes(B, cfg["C"], cfg["L"], cfg["K"], cfg["S"], cfg["P"], cfg["O"], Q, 1, 4)
+            self.ws[name] = (torch.empty(n, device=dev, dtype=torch.uint8), n)
+
+    def _dims(self, cfg):
+        return (self.B, cfg["C"], cfg["L"], cfg["K"], cfg["S"], cfg["P"], cfg["O"], Q, 1, 0)
+
+    def fwd(self, name, s):
+        cfg, t, p = LAYERS[name], self.sets[s].t[name], self.params.p[name]
+        st = self.lib.qw_conv1d_forward(_p(t["x"]), *[_p(w) for w in p], _p(t["y"]), _p(t["pre"]), *self._dims(cfg),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check(st, "qw_conv1d_forward")
+
+    def bwd(self, name, s):
+        cfg, t, p, g = LAYERS[name], self.sets[s].t[name], self.params.p[name], self.params.g[name]
+        ws, n = self.ws[name]
+        st = self.lib.qw_conv1d_backward(_p(t["gy"]), _p(t["x"]), _p(t["pre"]), _p(p[0]), _p(p[2]), _p(p[3]), _p(t["gx"]),
+                                         _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(ws), n, *self._dims(cfg),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check(st, "qw_conv1d_backward")
+
+    def step(self, s):
+        for name in ("conv1", "conv2"):
+            self.fwd(name, s)
+            self.bwd(name, s)
+
+    LAUNCHES_PER_STEP = 2 * (1 + 3)  # per layer: fwd kernel + bwd_post + bwd_pre + finalize
+
+
+def algorithmic_bytes(kernel, layer, B):
+    """Algorithmic HBM bytes of ONE launch (SURVEY.md 8d per-window figures x windows per launch)."""
+    cfg = LAYERS[layer]
+    W = B * cfg["Lout"]
+    x_per_win = 4.0 * cfg["C"] * cfg["L"] / cfg["Lout"]
+    y_per_win = 4.0 * cfg["O"]
+    if kernel == "qconv_fwd_kernel":
+        return W * (x_per_win + y_per_win)
+    if kernel == "qconv_bwd_post_kernel":
+        return W * y_per_win  # reads gy once
+    if kernel == "qconv_bwd_pre_kernel":
+        return W * x_per_win * (2.0 if cfg["need_gx"] else 1.0)  # re-read x (+ write grad_x)
+    return 0.0
+
+
+def time_events(fn, steps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(steps):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, dev):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_b200(args):
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from qasr_ijcnlp_b200 import _lib
+
+    B, K, Wm, nsets = args.batch, args.steps, max(args.warmup, 3), args.nsets
+    runner = StemRunner(B, dev, nsets)
+    windows_per_step = B * WINDOWS_PER_UTT
+
+    # ---- warm up eagerly (also sets function attributes), then capture one CUDA graph per buffer set
+    for i in range(2):
+        runner.step(i % nsets)
+    torch.cuda.synchronize()
+    graphs = []
+    side = torch.cuda.Stream()
+    for s in range(nsets):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            runner.step(s)
+        graphs.append(g)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    for i in range(Wm):
+        graphs[i % nsets].replay()
+    barrier(world)
+    ms = time_events(lambda i: graphs[i % nsets].replay(), K)
+    barrier(world)
+    ms = max_over_ranks(ms, world, dev)
+    value = world * windows_per_step * K / (ms * 1e-3)
+    gpu_launches = K * StemRunner.LAUNCHES_PER_STEP
+
+    # ---- per-kernel durations (CUDA events inside the library, eager launches, same rotating buffers)
+    kern = {}
+    calls = {}
+    for layer in ("conv1", "conv2"):
+        for what, fn in (("fwd", runner.fwd), ("bwd", runner.bwd)):
+            for i in range(3):
+                fn(layer, i % nsets)
+            torch.cuda.synchronize()
+            _lib.profile_read(reset=True)
+            _lib.profile_enable(True)
+            call_ms = time_events(lambda i: fn(layer, i % nsets), K)
+            _lib.profile_enable(False)
+            prof = _lib.profile_read(reset=True)
+            calls[f"{layer}.{what}"] = call_ms / K
+            for kname, (tot, n) in prof.items():
+                kern[(layer, kname)] = tot / n
+    peak, peak_src, peaks_raw = load_peaks()
+    step_kernel_ms = sum(kern.values())
+    dom = max(kern, key=lambda k: kern[k])
+    dom_bytes = algorithmic_bytes(dom[1], dom[0], B)
+    achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9
+    traffic = load_traffic().get(f"{dom[0]}.{dom[1]}")
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "traffic": traffic, "kernel": f"{dom[1]}[{dom[0]}]", "kernel_ms": round(kern[dom], 5),
+        "kernel_share_of_step": round(kern[dom] / step_kernel_ms, 4), "algorithmic_bytes_per_launch": dom_bytes,
+        "peak_source": peak_src,
+    }
+    kernels = {}
+    for (layer, kname), t in sorted(kern.items()):
+        ab = algorithmic_bytes(kname, layer, B)
+        kernels[f"{layer}.{kname}"] = {"ms": round(t, 5), "share": round(t / step_kernel_ms, 4),
+                                       "GBps": round(ab / (t * 1e-3) / 1e9, 1) if ab else None,
+                                       "frac": round(ab / (t * 1e-3) / 1e9 / peak, 4) if ab else None}
+    # whole-step roofline: algorithmic bytes of the step (3712 + 12288/2 ... per window) / step time
+    step_bytes = B * (3000 * 3712 + 1500 * 12288)
+    step_frac = step_bytes / (ms / K * 1e-3) / 1e9 / peak
+
+    # ---- e2e through the nn.Module API with host buffers
+    e2e = run_e2e(runner, B, K, Wm, world, dev)
+
+    # ---- encoder forward utt/s (BASELINE.json configs[1])
+    enc = None
+    if not args.no_encoder:
+        try:
+            enc = run_encoder_fwd(B, max(3, min(K, 20)), dev, world)
+        except Exception as e:  # keep the headline line alive
+            enc = {"error": repr(e)[:200]}
+
+    # ---- clocks: make sure the sampler saw the workload for >= 1.5 s
+    if rank == 0:
+        t0 = time.time()
+        i = 0
+        while time.time() - t0 < 1.5:
+            graphs[i % nsets].replay()
+            i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else {}
+    barrier(world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(target_s=12.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"Whisper-Tiny quantum stem: QuantumConv1d conv1(80->384,k3,s1,p1)+conv2(384->384,k3,s2,p1) "
+                            f"fwd+bwd, n_qubits=4, batch {B}/GPU x 80 mel x 3000 frames (BASELINE configs[1]/[2] shape)",
+                "windows_per_step_per_gpu": windows_per_step, "batch_per_gpu": B, "n_qubits": Q, "n_layers": 1,
+                "l2": f"{nsets} rotating buffer sets ({nsets} x {runner_bytes(B) / 1e6:.0f} MB > 126 MB L2)",
+                "launch": "one CUDA graph per step (8 kernels)", "parallelism": f"dp{world} (batch shard, no collective)",
+            },
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "step_roofline_frac": round(step_frac, 4), "kernels": kernels,
+            "calls_ms": {k: round(v, 5) for k, v in calls.items()},
+            "encoder_fwd": enc, "launch_count_check": _lib.launch_count() - launches0,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def runner_bytes(B):
+    n = 0
+    for cfg in LAYERS.values():
+        n += B * cfg["C"] * cfg["L"] * 4 * (2 if cfg["need_gx"] else 1) + 2 * B * cfg["O"] * cfg["Lout"] * 4
+    return n
+
+
+def run_e2e(runner, B, K, Wm, world, dev):
+    """Stem training step through the public nn.Module API from pinned host memory."""
+    mods = runner.params.mods
+    conv1, conv2 = mods["conv1"], mods["conv2"]
+    params = list(conv1.parameters()) + list(conv2.parameters())
+    nhost = 3
+    g = torch.Generator().manual_seed(7)
+    host_in = [torch.randn(B, N_MELS, N_FRAMES, generator=g).pin_memory() for _ in range(nhost)]
+    n_grad = sum(p.numel() for p in params)
+    host_out = [torch.empty(1 + n_grad).pin_memory() for _ in range(nhost)]
+    dev_in = [torch.empty(B, N_MELS, N_FRAMES, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+
+    def issue_copy(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[slot])
+            dev_in[slot].copy_(host_in[i % nhost], non_blocking=True)
+            ev_copied[slot].record(copy_stream)
+
+    def compute(i):
+        slot = i % 2
+        main.wait_event(ev_copied[slot])
+        x = dev_in[slot]
+        y2 = conv2(torch.nn.functional.gelu(conv1(x)))
+        loss = y2.square().mean()
+        grads = torch.autograd.grad(loss, params)
+        ev_free[slot].record(main)
+        flat = torch.cat([loss.reshape(1)] + [gr.reshape(-1) for gr in grads])
+        host_out[i % nhost].copy_(flat, non_blocking=True)
+
+    def loop(n):
+        for s in range(2):
+            ev_free[s].record(main)
+        issue_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_copy(i + 1)
+            compute(i)
+
+    loop(Wm)
+    barrier(world)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    loop(K)
+    b.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b), world, dev)
+    barrier(world)
+    val = world * B * WINDOWS_PER_UTT * K / (ms * 1e-3)
+    return {"value": round(val, 1), "unit": UNIT, "h2d_bytes_per_step": B * N_MELS * N_FRAMES * 4,
+            "d2h_bytes_per_step": 4 * (1 + n_grad), "ms_per_step": round(ms / K, 5),
+            "api": "QuantumConv1d nn.Module x2 + GELU + MSE-style loss, torch.autograd, pinned host in/out, "
+                   "H2D double-buffered on a copy stream", "loss": float(host_out[(K - 1) % nhost][0])}
+
+
+def run_encoder_fwd(B, K, dev, world):
+    """BASELINE.json configs[1]: Quantum Whisper-Tiny encoder forward + 35-class head on Speech-Commands-shaped
+    clips (1 s of 0.1*randn audio zero-padded to 30 s), log-mel computed on the GPU by qw_log_mel."""
+    from qasr_ijcnlp_b200 import QuantumWhisper, QuantumWhisperClassifier, get_whisper_tiny_dims
+    from qasr_ijcnlp_b200 import audio as qa
+
+    torch.manual_seed(1)
+    model = QuantumWhisperClassifier(QuantumWhisper(get_whisper_tiny_dims(), n_qubits=Q), 35).to(dev).eval()
+    audio = torch.zeros(B, 480000)
+    audio[:, :16000] = 0.1 * torch.randn(B, 16000)
+    audio = audio.pin_memory()
+
+    def step(_):
+        with torch.no_grad():
+            mel = qa.log_mel_spectrogram(audio.to(dev, non_blocking=True))
+            return model(mel)
+
+    for i in range(3):
+        step(i)
+    ms = max_over_ranks(time_events(step, K), world, dev)
+    return {"value": round(world * B * K / (ms * 1e-3), 2), "unit": "utt/s", "ms_per_step": round(ms / K, 4),
+            "workload": f"log-mel + QuantumWhisper-Tiny encoder fwd + Linear(384,35), batch {B}, host audio in"}
+
+
+# --------------------------------------------------------------------------------------------- CPU legs
+def _literal_step(layers_cols, seed=0):
+    """One bounded sample of the stem through the literal-loop restatement of the reference (fwd + bwd)."""
+    from oracle import qconv_oracle as qo
+
+    n = 0
+    for name, cols in layers_cols.items():
+        cfg = LAYERS[name]
+        params = [p.requires_grad_(True) for p in qo.make_params(cfg["C"], cfg["O"], cfg["K"], Q, seed=seed)]
+        g = torch.Generator().manual_seed(seed + 1)
+        Lneed = cols * cfg["S"] + cfg["K"]
+        x = torch.randn(2, cfg["C"], Lneed, generator=g, dtype=torch.float64, requires_grad=cfg["need_gx"])
+        y = qo.qconv1d_literal(x, *params, K=cfg["K"], S=cfg["S"], P=cfg["P"], max_windows=cols)
+        y[:, :, :cols].square().sum().backward()
+        n += 2 * cols
+    return n
+
+
+def cpu_baseline(target_s=12.0):
+    cores = torch.get_num_threads()
+    t0 = time.perf_counter()
+    n = _literal_step({"conv1": 16, "conv2": 8})
+    dt = time.perf_counter() - t0
+    rate = n / dt
+    scale = max(1, int(target_s * rate / 48))
+    cols = {"conv1": 16 * scale, "conv2": 8 * scale}
+    t0 = time.perf_counter()
+    n = _literal_step(cols)
+    dt = time.perf_counter() - t0
+    out = {"value": round(n / dt, 2), "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"literal-loop fp64 restatement of quantum_whisper.py:107-126 (PennyLane unavailable), fwd+bwd, "
+                     f"batch 2, first {cols['conv1']} conv1 + {cols['conv2']} conv2 output columns = {n} windows in {dt:.1f} s; "
+                     f"torch threads={cores}, os.cpu_count()={os.cpu_count()} (the loop is scalar Python: ~1 core busy)"}
+    # stronger secondary CPU baseline: vectorised fp64 oracle (unfold + batched statevector), all torch threads
+    try:
+        from oracle import qconv_oracle as qo
+
+        cfg = LAYERS["conv1"]
+        params = [p.requires_grad_(True) for p in qo.make_params(cfg["C"], cfg["O"], 3, Q, seed=0)]
+        x = torch.randn(2, cfg["C"], 3000, dtype=torch.float64)
+        t0 = time.perf_counter()
+        y = qo.qconv1d_forward(x, *params, K=3, S=1, P=1)
+        y.square().sum().backward()
+        dtv = time.perf_counter() - t0
+        out["vectorised_oracle"] = {"value": round(6000 / dtv, 1), "unit": UNIT, "cores": cores,
+                                    "sample": f"conv1 geometry, batch 2 x 3000 windows fwd+bwd in {dtv:.2f} s"}
+    except Exception as e:
+        out["vectorised_oracle"] = {"error": repr(e)[:200]}
+    return out
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    K, Wm = args.steps, args.warmup
+    cores = torch.get_num_threads()
+    cols = {"conv1": 32, "conv2": 16}
+    # keep the whole run within a few minutes: calibrate the per-step sample on the first warm-up step
+    t0 = time.perf_counter()
+    n = _literal_step(cols)
+    dt = time.perf_counter() - t0
+    budget = 150.0 / max(1, K + Wm)
+    if dt > budget:
+        f = max(1, int(32 * budget / dt))
+        cols = {"conv1": 2 * max(1, f // 2), "conv2": max(1, f // 2)}
+    for _ in range(max(0, Wm - 1)):
+        _literal_step(cols)
+    t0 = time.perf_counter()
+    n = 0
+    for i in range(K):
+        n += _literal_step(cols, seed=i)
+    dt = time.perf_counter() - t0
+    val = n / dt
+    sample = (f"literal-loop fp64 restatement of quantum_whisper.py:107-126 (PennyLane unavailable), fwd+bwd, batch 2, "
+              f"{cols['conv1']} conv1 + {cols['conv2']} conv2 output columns per step = {n // max(1, K)} windows/step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": Wm, "ms_per_step": round(dt / max(1, K) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Whisper-Tiny quantum stem conv1+conv2 fwd+bwd, n_qubits=4 (bounded sample of the "
+                               "batch-16 workload; cost per window is constant in the reference's Python loop)"},
+        "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

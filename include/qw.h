@@ -34,6 +34,11 @@ int qw_abi_version(void);
 const char* qw_last_error(void);
 /* Number of kernels this library has launched from the calling process since load (for bench gpu_launches). */
 long long qw_launch_count(void);
+/* Optional per-kernel CUDA-event timing used by bench.py's roofline leg (not valid during stream capture).
+ * qw_profile_read synchronises on the recorded events; kernel ids 0..qw_kernel_name()!="" . */
+void qw_profile_enable(int on);
+int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset);
+const char* qw_kernel_name(int kernel_id);
 
 /* ---- QuantumConv1d.forward  (quantum_whisper.py:95-128; circuit :64-85; params :58-59,88)
  * x (B,C,L) -> y (B,O,L_out), L_out = (L+2P-K)/S+1 (:103).  w_pre (q, C*K) with column c*K+k (:58,:111),

@@ -27,6 +27,9 @@ _SIGNATURES = {
     "qw_abi_version": (_I, []),
     "qw_last_error": (ctypes.c_char_p, []),
     "qw_launch_count": (_LL, []),
+    "qw_profile_enable": (None, [_I]),
+    "qw_profile_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_LL), _I]),
+    "qw_kernel_name": (ctypes.c_char_p, [_I]),
     "qw_conv1d_forward": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_forward_f64": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_workspace_bytes": (_SZ, [_I] * 10),
@@ -81,3 +84,24 @@ def check(status: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().qw_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().qw_profile_enable(1 if on else 0)
+
+
+def profile_read(reset: bool = True) -> dict:
+    """{kernel name: (total_ms, launches)} for every kernel timed since the last reset."""
+    lib = load()
+    out = {}
+    kid = 0
+    while True:
+        name = lib.qw_kernel_name(kid)
+        if not name:
+            break
+        ms, n = ctypes.c_double(0.0), _LL(0)
+        lib.qw_profile_read(kid, ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0)
+        if n.value:
+            out[name.decode()] = (ms.value, int(n.value))
+        kid += 1
+    return out

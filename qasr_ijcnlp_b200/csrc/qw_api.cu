@@ -1,5 +1,7 @@
 // Library-wide state: thread-local error text, launch counter, ABI version.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 
@@ -17,10 +19,70 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-kernel event timing.  Events are recorded on the launching stream around each kernel and resolved
+// lazily in qw_profile_read (which synchronises on them).  Not usable during stream capture.
+struct ProfRec {
+  cudaEvent_t a, b;
+};
+static std::mutex g_pmu;
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs[kKCount];
+static cudaEvent_t g_open[kKCount];
+
+bool profiling_enabled() { return g_prof; }
+void profile_begin(int id, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_pmu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_open[id] = e;
+}
+void profile_end(int id, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_pmu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_recs[id].push_back({g_open[id], e});
+}
 }  // namespace qw
 
 extern "C" {
 int qw_abi_version(void) { return QW_ABI_VERSION; }
 const char* qw_last_error(void) { return qw::g_err; }
 long long qw_launch_count(void) { return qw::g_launches.load(std::memory_order_relaxed); }
+
+void qw_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(qw::g_pmu);
+  qw::g_prof = on != 0;
+}
+int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset) {
+  if (kernel_id < 0 || kernel_id >= qw::kKCount || !total_ms || !count) return -1;
+  std::lock_guard<std::mutex> lk(qw::g_pmu);
+  double tot = 0.0;
+  long long n = 0;
+  for (auto& r : qw::g_recs[kernel_id]) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+  }
+  *total_ms = tot;
+  *count = n;
+  if (reset) {
+    for (auto& r : qw::g_recs[kernel_id]) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    qw::g_recs[kernel_id].clear();
+  }
+  return 0;
+}
+const char* qw_kernel_name(int kernel_id) {
+  static const char* names[] = {"qconv_fwd_kernel", "qconv_bwd_post_kernel", "qconv_bwd_pre_kernel", "qconv_bwd_finalize_kernel",
+                                "circuit_fwd_kernel", "circuit_bwd_kernel", "circuit_finalize_kernel", "logmel_stft_kernel",
+                                "logmel_finish_kernel"};
+  return (kernel_id >= 0 && kernel_id < qw::kKCount) ? names[kernel_id] : "";
+}
 }

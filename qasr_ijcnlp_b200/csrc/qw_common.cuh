@@ -12,6 +12,24 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
 
+// Optional per-kernel CUDA-event timing (qw_profile_enable): KernelTimer brackets one launch on `st`.
+enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKCount };
+bool profiling_enabled();
+void profile_begin(int id, cudaStream_t st);
+void profile_end(int id, cudaStream_t st);
+struct KernelTimer {
+  int id;
+  cudaStream_t st;
+  bool on;
+  KernelTimer(int id_, cudaStream_t st_) : id(id_), st(st_), on(profiling_enabled()) {
+    if (on) profile_begin(id, st);
+  }
+  ~KernelTimer() {
+    count_launch();
+    if (on) profile_end(id, st);
+  }
+};
+
 #define QW_CHECK_ARG(cond, code, ...) \
   do {                                \
     if (!(cond)) {                    \

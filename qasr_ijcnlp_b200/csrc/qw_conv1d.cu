@@ -148,8 +148,10 @@ static int circuit_backward_impl(const T* pre, const T* qwts, const T* gout, T* 
     default: e = circ_bwd_tq<T, 4>(a, grid, st); break;
   }
   if (e) return e;
-  circuit_finalize_kernel<T><<<PA / 32, kFinThreads, 0, st>>>((const T*)workspace, qwts, gqw, grid, PA, q, Lq);
-  count_launch();
+  {
+    KernelTimer kt(kKCircFinalize, st);
+    circuit_finalize_kernel<T><<<PA / 32, kFinThreads, 0, st>>>((const T*)workspace, qwts, gqw, grid, PA, q, Lq);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -19,8 +19,10 @@ static int launch_fwd(const FwdArgs<T>& a, const Plan& p, cudaStream_t st) {
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "forward needs %zu bytes of shared memory (C*K too large)", smem);
   auto k = qconv_fwd_kernel<T, Q, KT, WPT>;
   if (int e = set_smem(k, smem)) return e;
-  k<<<p.gridF, kThreads, smem, st>>>(a);
-  count_launch();
+  {
+    KernelTimer kt(kKFwd, st);
+    k<<<p.gridF, kThreads, smem, st>>>(a);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -43,8 +45,10 @@ static int launch_bwdA(const BwdAArgs<T>& a, const Plan& p, cudaStream_t st) {
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "backward(post) needs %zu bytes of shared memory", smem);
   auto k = qconv_bwd_post_kernel<T, Q, WPT>;
   if (int e = set_smem(k, smem)) return e;
-  k<<<p.gridA, kThreads, smem, st>>>(a);
-  count_launch();
+  {
+    KernelTimer kt(kKBwdPost, st);
+    k<<<p.gridA, kThreads, smem, st>>>(a);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -61,8 +65,10 @@ static int launch_bwdB(const BwdBArgs<T>& a, const Plan& p, cudaStream_t st) {
   const size_t smem = bwdB_smem_elems<T, Q, KT>() * sizeof(T);
   auto k = qconv_bwd_pre_kernel<T, Q, KT>;
   if (int e = set_smem(k, smem)) return e;
-  k<<<dim3(p.gridBx, p.nchunks), kThreads, smem, st>>>(a);
-  count_launch();
+  {
+    KernelTimer kt(kKBwdPre, st);
+    k<<<dim3(p.gridBx, p.nchunks), kThreads, smem, st>>>(a);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -82,8 +88,10 @@ int bwd_tq(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* 
   FinArgs<T> fa{partA, partB, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridA, p.PA, p.gridBx, p.PB,
                 d.C, d.K, d.O, d.Q, d.Lq, p.KT};
   const int nblk = p.PA / 32 + (p.PB + 31) / 32;
-  qconv_bwd_finalize_kernel<T><<<nblk, kFinThreads, 0, st>>>(fa);
-  count_launch();
+  {
+    KernelTimer kt(kKBwdFinalize, st);
+    qconv_bwd_finalize_kernel<T><<<nblk, kFinThreads, 0, st>>>(fa);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -91,8 +99,10 @@ int bwd_tq(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* 
 
 template <typename T, int Q>
 int circ_fwd_tq(const CircArgs<T>& a, int grid, cudaStream_t st) {
-  circuit_fwd_kernel<T, Q><<<grid, kThreads, 0, st>>>(a);
-  count_launch();
+  {
+    KernelTimer kt(kKCircFwd, st);
+    circuit_fwd_kernel<T, Q><<<grid, kThreads, 0, st>>>(a);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -101,8 +111,10 @@ int circ_bwd_tq(const CircArgs<T>& a, int grid, cudaStream_t st) {
   const size_t smem = ((size_t)a.Lq * Q * kGateStride + (size_t)a.Lq * Q * 8 * (kThreads + 1)) * sizeof(T);
   auto k = circuit_bwd_kernel<T, Q>;
   if (int e = set_smem(k, smem)) return e;
-  k<<<grid, kThreads, smem, st>>>(a);
-  count_launch();
+  {
+    KernelTimer kt(kKCircBwd, st);
+    k<<<grid, kThreads, smem, st>>>(a);
+  }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
