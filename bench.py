@@ -157,7 +157,7 @@ class StemBuffers:
                 x=torch.randn(B, C, L, device=dev, generator=g),
                 y=torch.empty(B, O, Lout, device=dev),
                 gy=torch.randn(B, O, Lout, device=dev, generator=g),
-                pre=torch.empty(B * Lout, Q, device=dev),
+                pre=torch.empty(2, B * Lout, Q, device=dev),
                 gx=torch.empty(B, C, L, device=dev) if cfg["need_gx"] else None,
             )
 

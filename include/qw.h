@@ -39,11 +39,14 @@ long long qw_launch_count(void);
 void qw_profile_enable(int on);
 int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset);
 const char* qw_kernel_name(int kernel_id);
+/* 1 (default): use the TMA fast path when the shape qualifies (fp32, q=4, K=3, stride 1|2, L%4==0, L_out%4==0,
+ * O%4==0, O<=576, 16-byte aligned tensors; the forward additionally needs padding==1); 0: always use the generic kernels (used by the parity tests). */
+void qw_set_fast_path(int enable);
 
 /* ---- QuantumConv1d.forward  (quantum_whisper.py:95-128; circuit :64-85; params :58-59,88)
  * x (B,C,L) -> y (B,O,L_out), L_out = (L+2P-K)/S+1 (:103).  w_pre (q, C*K) with column c*K+k (:58,:111),
- * b_pre (q), qw (n_layers,q,3), w_post (O,q), b_post (O).  pre_save: (B*L_out, q) or NULL -- the pre_conv
- * outputs, kept for the backward pass.  q must already be min(n_qubits, C*K) (:55). */
+ * b_pre (q), qw (n_layers,q,3), w_post (O,q), b_post (O).  pre_save: (2, B*L_out, q) or NULL -- plane 0 the
+ * pre_conv outputs, plane 1 the <Z_i> readouts, kept for the backward pass.  q must already be min(n_qubits, C*K) (:55). */
 int qw_conv1d_forward(const float* x, const float* w_pre, const float* b_pre, const float* qw, const float* w_post,
                       const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O,
                       int q, int n_layers, int embedding, void* stream);

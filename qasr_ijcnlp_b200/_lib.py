@@ -30,6 +30,7 @@ _SIGNATURES = {
     "qw_profile_enable": (None, [_I]),
     "qw_profile_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_LL), _I]),
     "qw_kernel_name": (ctypes.c_char_p, [_I]),
+    "qw_set_fast_path": (None, [_I]),
     "qw_conv1d_forward": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_forward_f64": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_workspace_bytes": (_SZ, [_I] * 10),

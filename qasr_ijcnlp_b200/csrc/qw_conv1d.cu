@@ -72,9 +72,12 @@ static int conv1d_forward_impl(const T* x, const T* w_pre, const T* b_pre, const
                                T* y, T* pre_save, ConvDims d, void* stream) {
   QW_CHECK_ARG(x && w_pre && b_pre && qwts && w_post && b_post && y, -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if constexpr (sizeof(T) == 4) {
+    if (fast_eligible(d, x, y, pre_save, true)) return fast_forward(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, st);
+  }
   const Plan p = make_plan(d);
   FwdArgs<T> a{x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, p.tiles_per_utt, p.num_tiles};
-  cudaStream_t st = (cudaStream_t)stream;
   switch (d.Q) {
     case 1: return fwd_tq<T, 1>(a, p, st);
     case 2: return fwd_tq<T, 2>(a, p, st);
@@ -91,12 +94,19 @@ static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, cons
                -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
   QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
+  QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  if constexpr (sizeof(T) == 4) {
+    if (fast_eligible(d, x, gy, gx, false) && (((uintptr_t)pre_save) & 15) == 0) {
+      const FastPlan fp = make_fast_plan(d);
+      QW_CHECK_ARG(ws_bytes >= fp.ws_bytes, -3, "workspace too small: %zu < %zu", ws_bytes, fp.ws_bytes);
+      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st);
+    }
+  }
   const Plan p = make_plan(d);
   const WsLayout<T> wl = ws_layout<T>(d, p);
   QW_CHECK_ARG(ws_bytes >= wl.total, -3, "workspace too small: %zu < %zu", ws_bytes, wl.total);
-  QW_CHECK_ARG(((uintptr_t)workspace & 15) == 0, -1, "workspace must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned char* ws = (unsigned char*)workspace;
   switch (d.Q) {
     case 1: return bwd_tq<T, 1>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, p, st);
     case 2: return bwd_tq<T, 2>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, p, st);
@@ -163,6 +173,8 @@ using qw::ConvDims;
 
 extern "C" {
 
+void qw_set_fast_path(int enable) { qw::set_fast_path(enable != 0); }
+
 int qw_conv1d_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
                       const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O, int q,
                       int n_layers, int embedding, void* stream) {
@@ -180,7 +192,10 @@ size_t qw_conv1d_workspace_bytes(int B, int C, int L, int K, int S, int P, int O
   ConvDims d{B, C, L, K, S, P, O, q, n_layers, 0, 0};
   if (qw::check_dims(d)) return 0;
   const qw::Plan p = qw::make_plan(d);
-  return elem_size == 8 ? qw::ws_layout<double>(d, p).total : qw::ws_layout<float>(d, p).total;
+  if (elem_size == 8) return qw::ws_layout<double>(d, p).total;
+  const size_t generic = qw::ws_layout<float>(d, p).total;
+  const size_t fast = qw::make_fast_plan(d).ws_bytes;
+  return generic > fast ? generic : fast;
 }
 
 int qw_conv1d_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,

@@ -1,0 +1,833 @@
+// Fast path of QuantumConv1d for the Whisper stem regime: fp32, n_qubits = 4, kernel_size = 3, stride 1 or 2,
+// amplitude embedding, L % 4 == 0, L_out % 4 == 0, O % 4 == 0, O <= 576, 16-byte aligned tensors.
+// Everything else goes through the generic kernels in qw_conv1d_kernels.cuh.
+//
+// All four streaming kernels are persistent (grid ~ 2-3 CTAs per SM, static round-robin tile assignment) and
+// move their tiles with the TMA engine (cp.async.bulk[.tensor]) through mbarrier-synchronised shared-memory
+// rings, so HBM latency is hidden by the ring depth rather than by occupancy:
+//
+//   fast_fwd_kernel<S,RC>   x tile ring (3-D tensor map, zero padding by OOB fill) -> pre_conv partials with a
+//                           "4 rows x 8 lanes x 4 adjacent windows" lane layout -> circuit (thread/window) ->
+//                           post_conv with 128-bit coalesced stores.
+//   fast_bwd_gy_kernel<RPT> streams gy once (SWIZZLE_128B tiles, conflict-free in both orientations):
+//                           gout = post_conv^T gy (time-major lanes) and grad post_conv.{weight,bias}
+//                           (channel-major lanes, register accumulators for the whole CTA lifetime).
+//   fast_bwd_adj_kernel     adjoint differentiation of the circuit, one thread per window -> gpre (halo-padded).
+//   fast_bwd_pre_kernel<S,PAR,GX>  x tile ring in, grad_x written in place and stored back by TMA; lanes along
+//                           channels hold pre_conv weights and their gradient accumulators in registers.
+//   fast_finalize_kernel    deterministic reduction of the per-CTA partial rows.
+#include "../../include/qw.h"
+#include "qw_conv1d_plan.cuh"
+#include "qw_tma.cuh"
+
+namespace qw {
+
+constexpr int FQ = 4;     // n_qubits on the fast path
+constexpr int FTW = 32;   // windows per tile (forward, gy streaming)
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ unsigned char* align1024(unsigned char* p) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// =============================================================================================== forward
+struct FastFwdArgs {
+  const float *w_pre, *b_pre, *qw, *w_post, *b_post;
+  float *y, *pre_save, *qout_save;
+  int B, C, L, P, O, Lq, Lout;
+  int tiles_per_utt, num_tiles, chunks_per_tile;
+};
+
+constexpr int kFwdStages = 4;
+// x tile columns: the TMA box must start on a 16-byte boundary, so it starts 4 columns before window i0 tap 0 + P
+// (P == 1 on the fast path: tap k of local window w sits in column 3 + w*S + k).
+template <int S> __host__ __device__ constexpr int fwd_xw() { return S == 1 ? 40 : 72; }
+
+template <int S, int RC>
+__host__ __device__ constexpr size_t fast_fwd_smem_bytes(int CK, int O, int Lq) {
+  return 1024 + (size_t)kFwdStages * RC * fwd_xw<S>() * 4 +
+         ((size_t)CK * FQ + (size_t)O * FQ + align_up(O, 4) + 4 + (size_t)Lq * FQ * kGateStride + kWarps * FTW * FQ + FTW * FQ) * 4 +
+         2 * kFwdStages * 8;
+}
+
+template <int S, int RC>
+__global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const FastFwdArgs a) {
+  constexpr int XW = fwd_xw<S>();
+  constexpr int STAGE_ELEMS = RC * XW;
+  constexpr int ITS = RC / 16;  // 4 warps x 4 rows per iteration
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = align1024(smem_dyn);
+  float* stage = reinterpret_cast<float*>(base);                    // [kFwdStages][RC][XW]
+  float* wpre_t = stage + (size_t)kFwdStages * STAGE_ELEMS;         // [C*3][4]
+  const int CK = a.C * 3;
+  float* wpost = wpre_t + (size_t)CK * FQ;                          // [O][4]
+  float* bpost = wpost + (size_t)a.O * FQ;                          // [O]
+  float* bpre = bpost + align_up(a.O, 4);                           // [4]
+  float* gates = bpre + 4;                                          // [Lq][4][16]
+  float* part = gates + (size_t)a.Lq * FQ * kGateStride;            // [kWarps][32][4]
+  float* outs = part + kWarps * FTW * FQ;                           // [32][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(outs + FTW * FQ);    // [kFwdStages]
+  uint64_t* empty = full + kFwdStages;                              // [kFwdStages]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rr = lane >> 3, tl = lane & 7;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    for (int s = 0; s < kFwdStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kWarps);
+    }
+    fence_mbar_init();
+  }
+  for (int idx = tid; idx < CK * FQ; idx += kThreads) {
+    const int j = idx / CK, f = idx - j * CK;
+    wpre_t[f * FQ + j] = a.w_pre[idx];
+  }
+  for (int idx = tid; idx < a.O * FQ; idx += kThreads) wpost[idx] = a.w_post[idx];
+  for (int idx = tid; idx < a.O; idx += kThreads) bpost[idx] = a.b_post[idx];
+  if (tid < FQ) bpre[tid] = a.b_pre[tid];
+  if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  __syncthreads();
+
+  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_chunks = my_tiles * a.chunks_per_tile;
+
+  // producer (thread 0): chunk g of this CTA -> stage g % kFwdStages
+  auto issue = [&](int g) {
+    const int n = g / a.chunks_per_tile, ch = g - n * a.chunks_per_tile;
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int s = g % kFwdStages;
+    mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * 4);
+    tma_load_3d(stage + (size_t)s * STAGE_ELEMS, &tm_x, i0 * S - 4, ch * RC, b, &full[s]);
+  };
+  if (tid == 0)
+    for (int g = 0; g < kFwdStages - 1 && g < total_chunks; ++g) issue(g);
+
+  int g = 0;  // running chunk counter
+  for (int n = 0; n < my_tiles; ++n) {
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+
+    // ---- phase 1: pre_conv partial sums over the channel chunks of this tile
+    float acc[4][FQ];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) acc[w][j] = 0.f;
+
+    for (int ch = 0; ch < a.chunks_per_tile; ++ch, ++g) {
+      if (tid == 0) {
+        const int gn = g + kFwdStages - 1;
+        if (gn < total_chunks) {
+          if (gn >= kFwdStages) mbar_wait(&empty[gn % kFwdStages], ((gn / kFwdStages) - 1) & 1);
+          issue(gn);
+        }
+      }
+      const int s = g % kFwdStages;
+      mbar_wait(&full[s], (g / kFwdStages) & 1);
+      const float* st = stage + (size_t)s * STAGE_ELEMS;
+#pragma unroll
+      for (int it = 0; it < ITS; ++it) {
+        const int rl = it * 16 + warp * 4 + rr;  // row inside the chunk
+        const int c = ch * RC + rl;              // channel (rows >= C are zero-filled by TMA; weights masked)
+        const float* xr = st + rl * XW;
+        float xc[S == 1 ? 6 : 9];
+        if constexpr (S == 1) {
+          const float4 v0 = ld4(xr + 4 * tl + 4);
+          xc[0] = xr[4 * tl + 3];
+          xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
+          xc[5] = xr[4 * tl + 8];
+        } else {
+          const float4 v0 = ld4(xr + 8 * tl + 4), v1 = ld4(xr + 8 * tl + 8);
+          xc[0] = xr[8 * tl + 3];
+          xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
+          xc[5] = v1.x; xc[6] = v1.y; xc[7] = v1.z; xc[8] = v1.w;
+        }
+        if (c < a.C) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float4 wv = ld4(wpre_t + (size_t)(c * 3 + k) * FQ);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float xv = xc[w * S + k];
+              acc[w][0] = fmaf(wv.x, xv, acc[w][0]);
+              acc[w][1] = fmaf(wv.y, xv, acc[w][1]);
+              acc[w][2] = fmaf(wv.z, xv, acc[w][2]);
+              acc[w][3] = fmaf(wv.w, xv, acc[w][3]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // reduce over the 4 row classes of the warp, then across warps through shared memory
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) {
+        float v = acc[w][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        acc[w][j] = v;
+      }
+    if (rr == 0) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        st4(part + ((size_t)warp * FTW + 4 * tl + w) * FQ, make_float4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]));
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per window: bias, circuit, <Z_i>
+    if (tid < FTW) {
+      const int i = i0 + tid;
+      float out[FQ] = {0.f, 0.f, 0.f, 0.f};
+      if (i < a.Lout) {
+        float pre[FQ];
+#pragma unroll
+        for (int j = 0; j < FQ; ++j) pre[j] = bpre[j];
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const float4 pv = ld4(part + ((size_t)w * FTW + tid) * FQ);
+          pre[0] += pv.x; pre[1] += pv.y; pre[2] += pv.z; pre[3] += pv.w;
+        }
+        float re[1 << FQ], im[1 << FQ];
+        circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+        const size_t wi = (size_t)b * a.Lout + i;
+        if (a.pre_save) st4(a.pre_save + wi * FQ, make_float4(pre[0], pre[1], pre[2], pre[3]));
+        if (a.qout_save) st4(a.qout_save + wi * FQ, make_float4(out[0], out[1], out[2], out[3]));
+      }
+      st4(outs + (size_t)tid * FQ, make_float4(out[0], out[1], out[2], out[3]));
+    }
+    __syncthreads();
+
+    // ---- phase 3: post_conv, 4 output rows x (8 lanes x 4 adjacent windows) per warp instruction
+    float ov[4][FQ];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float4 v = ld4(outs + (size_t)(4 * tl + w) * FQ);
+      ov[w][0] = v.x; ov[w][1] = v.y; ov[w][2] = v.z; ov[w][3] = v.w;
+    }
+    const bool store_ok = (i0 + 4 * tl) < a.Lout;  // Lout % 4 == 0: a lane's 4 windows are all valid or all invalid
+    float* __restrict__ yb = a.y + (size_t)b * a.O * a.Lout + i0 + 4 * tl;
+    const int ngroups = a.O >> 2;
+#pragma unroll 4
+    for (int og = warp; og < ngroups; og += kWarps) {
+      const int o = og * 4 + rr;
+      const float4 wv = ld4(wpost + (size_t)o * FQ);
+      const float bv = bpost[o];
+      float4 r;
+      r.x = fmaf(wv.w, ov[0][3], fmaf(wv.z, ov[0][2], fmaf(wv.y, ov[0][1], fmaf(wv.x, ov[0][0], bv))));
+      r.y = fmaf(wv.w, ov[1][3], fmaf(wv.z, ov[1][2], fmaf(wv.y, ov[1][1], fmaf(wv.x, ov[1][0], bv))));
+      r.z = fmaf(wv.w, ov[2][3], fmaf(wv.z, ov[2][2], fmaf(wv.y, ov[2][1], fmaf(wv.x, ov[2][0], bv))));
+      r.w = fmaf(wv.w, ov[3][3], fmaf(wv.z, ov[3][2], fmaf(wv.y, ov[3][1], fmaf(wv.x, ov[3][0], bv))));
+      if (store_ok) st4(yb + (size_t)o * a.Lout, r);
+    }
+    // `part` / `outs` are rewritten only after the next tile's phase 1, which every warp enters after this point;
+    // the __syncthreads() before phase 2 of the next tile orders those writes against these reads of `outs`.
+    __syncthreads();
+  }
+}
+
+// =============================================================================================== backward: gy streaming
+struct FastGyArgs {
+  const float* w_post;
+  float *gout, *part;  // gout: [W][4]; part: [gridDim.x][PA1]
+  int B, O, Lout, tiles_per_utt, num_tiles, PA1, nbox;  // nbox = ceil(O/64) row boxes per tile
+};
+constexpr int kGyThreads = 192;
+constexpr int kGyWarps = kGyThreads / 32;
+constexpr int kGySlots = 2;
+
+__host__ __device__ constexpr size_t fast_gy_smem_bytes(int O) {
+  return 1024 + (size_t)kGySlots * ((O + 63) / 64) * 64 * 128 + (size_t)kGySlots * FTW * FQ * 4 + (size_t)O * FQ * 4 +
+         (size_t)2 * kGyWarps * FTW * FQ * 4 + 2 * kGySlots * 8;
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(kGyThreads) fast_bwd_gy_kernel(const __grid_constant__ CUtensorMap tm_gy,
+                                                                 const __grid_constant__ CUtensorMap tm_qout, const FastGyArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = align1024(smem_dyn);
+  const int slot_elems = a.nbox * 64 * 32;
+  float* slots = reinterpret_cast<float*>(base);                       // [kGySlots][nbox*64][32] swizzled
+  float* outs = slots + (size_t)kGySlots * slot_elems;                 // [kGySlots][32][4]
+  float* wpost = outs + kGySlots * FTW * FQ;                           // [O][4]
+  float* gred = wpost + (size_t)a.O * FQ;                              // [2][kGyWarps][32][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(gred + 2 * kGyWarps * FTW * FQ);
+  uint64_t* empty = full + kGySlots;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rr = lane >> 3, tl = lane & 7;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_gy);
+    tma_prefetch_desc(&tm_qout);
+    for (int s = 0; s < kGySlots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGyWarps);
+    }
+    fence_mbar_init();
+  }
+  for (int idx = tid; idx < a.O * FQ; idx += kGyThreads) wpost[idx] = a.w_post[idx];
+  __syncthreads();
+
+  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto issue = [&](int n) {
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int s = n % kGySlots;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(slot_elems + FTW * FQ) * 4);
+    for (int bx = 0; bx < a.nbox; ++bx) tma_load_3d(slots + (size_t)s * slot_elems + bx * 64 * 32, &tm_gy, i0, bx * 64, b, &full[s]);
+    tma_load_3d(outs + s * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
+  };
+  if (tid == 0 && my_tiles > 0) issue(0);
+
+  float wacc[RPT][FQ + 1];
+#pragma unroll
+  for (int m = 0; m < RPT; ++m)
+#pragma unroll
+    for (int j = 0; j <= FQ; ++j) wacc[m][j] = 0.f;
+
+  const int ngroups = a.O >> 2;
+  for (int n = 0; n < my_tiles; ++n) {
+    if (tid == 0 && n + 1 < my_tiles) {
+      if (n + 1 >= kGySlots) mbar_wait(&empty[(n + 1) % kGySlots], (((n + 1) / kGySlots) - 1) & 1);
+      issue(n + 1);
+    }
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int s = n % kGySlots;
+    mbar_wait(&full[s], (n / kGySlots) & 1);
+    const float* gs = slots + (size_t)s * slot_elems;
+    const float* os = outs + s * FTW * FQ;
+
+    // ---- gout = post_conv^T gy : lanes (4 rows x 8 chunks of 4 windows)
+    float gacc[4][FQ];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) gacc[u][j] = 0.f;
+#pragma unroll 4
+    for (int og = warp; og < ngroups; og += kGyWarps) {
+      const int r = og * 4 + rr;
+      const float4 gv = ld4(gs + swz128(r, tl));
+      const float4 wv = ld4(wpost + (size_t)r * FQ);
+      gacc[0][0] = fmaf(gv.x, wv.x, gacc[0][0]); gacc[0][1] = fmaf(gv.x, wv.y, gacc[0][1]);
+      gacc[0][2] = fmaf(gv.x, wv.z, gacc[0][2]); gacc[0][3] = fmaf(gv.x, wv.w, gacc[0][3]);
+      gacc[1][0] = fmaf(gv.y, wv.x, gacc[1][0]); gacc[1][1] = fmaf(gv.y, wv.y, gacc[1][1]);
+      gacc[1][2] = fmaf(gv.y, wv.z, gacc[1][2]); gacc[1][3] = fmaf(gv.y, wv.w, gacc[1][3]);
+      gacc[2][0] = fmaf(gv.z, wv.x, gacc[2][0]); gacc[2][1] = fmaf(gv.z, wv.y, gacc[2][1]);
+      gacc[2][2] = fmaf(gv.z, wv.z, gacc[2][2]); gacc[2][3] = fmaf(gv.z, wv.w, gacc[2][3]);
+      gacc[3][0] = fmaf(gv.w, wv.x, gacc[3][0]); gacc[3][1] = fmaf(gv.w, wv.y, gacc[3][1]);
+      gacc[3][2] = fmaf(gv.w, wv.z, gacc[3][2]); gacc[3][3] = fmaf(gv.w, wv.w, gacc[3][3]);
+    }
+    // ---- grad post_conv.{weight,bias}: lanes along output channels, accumulators live in registers
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) {
+      const int r = tid + m * kGyThreads;
+      if (r < a.O) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 gv = ld4(gs + swz128(r, c));
+          const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 ov = ld4(os + (size_t)(4 * c + u) * FQ);
+            wacc[m][0] = fmaf(g4[u], ov.x, wacc[m][0]);
+            wacc[m][1] = fmaf(g4[u], ov.y, wacc[m][1]);
+            wacc[m][2] = fmaf(g4[u], ov.z, wacc[m][2]);
+            wacc[m][3] = fmaf(g4[u], ov.w, wacc[m][3]);
+            wacc[m][4] += g4[u];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    // ---- finish gout: reduce the 4 row classes, then the warps
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) {
+        float v = gacc[u][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        gacc[u][j] = v;
+      }
+    float* gr = gred + (size_t)(n & 1) * kGyWarps * FTW * FQ;
+    if (rr == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        st4(gr + ((size_t)warp * FTW + 4 * tl + u) * FQ, make_float4(gacc[u][0], gacc[u][1], gacc[u][2], gacc[u][3]));
+    }
+    __syncthreads();
+    if (tid < FTW * FQ) {
+      const int t = tid >> 2;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGyWarps; ++w) sum += gr[(size_t)w * FTW * FQ + tid];
+      if (i0 + t < a.Lout) a.gout[((size_t)b * a.Lout + i0) * FQ + tid] = sum;
+    }
+  }
+  // ---- partial row of this CTA: [O*4 gw_post][O gb_post]
+  float* prow = a.part + (size_t)blockIdx.x * a.PA1;
+#pragma unroll
+  for (int m = 0; m < RPT; ++m) {
+    const int r = tid + m * kGyThreads;
+    if (r < a.O) {
+      st4(prow + (size_t)r * FQ, make_float4(wacc[m][0], wacc[m][1], wacc[m][2], wacc[m][3]));
+      prow[a.O * FQ + r] = wacc[m][4];
+    }
+  }
+  for (int e = a.O * (FQ + 1) + tid; e < a.PA1; e += kGyThreads) prow[e] = 0.f;
+}
+
+// =============================================================================================== backward: adjoint
+constexpr int kHaloL = 8;
+constexpr int kHaloR = 144;
+struct FastAdjArgs {
+  const float *pre_save, *gout, *qw;
+  float *gpre_pad, *part;  // gpre_pad: [B][LP][4]; part: [gridDim.x][PA2]
+  int B, Lout, LP, Lq, PA2;
+  long long W;
+};
+
+__global__ void __launch_bounds__(kThreads) fast_bwd_adj_kernel(const FastAdjArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_adj[];
+  constexpr int MS = kThreads + 1;
+  const int NE = FQ + a.Lq * FQ * 8;
+  float* gates = reinterpret_cast<float*>(smem_adj);         // [Lq][4][16]
+  float* macc = gates + (size_t)a.Lq * FQ * kGateStride;     // [NE][MS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  for (int idx = tid; idx < NE * MS; idx += kThreads) macc[idx] = 0.f;
+  // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
+  {
+    const int per = (kHaloL + kHaloR) * FQ;
+    for (long long idx = (long long)blockIdx.x * kThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kThreads) {
+      const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
+      const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
+      a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (long long w = (long long)blockIdx.x * kThreads + tid; w < a.W; w += (long long)gridDim.x * kThreads) {
+    const int b = (int)(w / a.Lout), i = (int)(w - (long long)b * a.Lout);
+    float pre[FQ], out[FQ], gout[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
+    ld_vec<float, FQ>(a.pre_save + w * FQ, pre);
+    ld_vec<float, FQ>(a.gout + w * FQ, gout);
+    const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+    SmemGateAcc<float, FQ> acc{macc + (size_t)FQ * MS + tid, MS, 0};
+    circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
+    st_vec<float, FQ>(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, gpre);
+#pragma unroll
+    for (int j = 0; j < FQ; ++j) macc[j * MS + tid] += gpre[j];
+  }
+  __syncthreads();
+  // partial row: [0..3] grad pre_conv.bias, [32 + g*8 + e] gate matrices
+  float* prow = a.part + (size_t)blockIdx.x * a.PA2;
+  for (int e = tid; e < a.PA2; e += kThreads) prow[e] = 0.f;
+  __syncthreads();
+  for (int e = warp; e < NE; e += kWarps) {
+    float s = 0.f;
+    for (int t = lane; t < kThreads; t += 32) s += macc[e * MS + t];
+    s = warp_sum(s);
+    if (lane == 0) prow[e < FQ ? e : 32 + (e - FQ)] = s;
+  }
+}
+
+// =============================================================================================== backward: pre_conv^T
+struct FastPreArgs {
+  const float *gpre_pad, *w_pre;
+  float* part;  // [gridDim.x][Cpad][12]
+  int B, C, L, P, Lout, LP, tiles_per_utt, num_tiles, Cpad;
+};
+constexpr int kPreSlots = 3;
+template <int S> __host__ __device__ constexpr int pre_gpn() { return S == 1 ? 136 : 72; }  // gpre rows staged per tile
+
+template <int S>
+__host__ __device__ constexpr size_t fast_pre_smem_bytes() {
+  return 1024 + (size_t)kPreSlots * 4096 * 4 + (size_t)kPreSlots * pre_gpn<S>() * FQ * 4 + kPreSlots * 8;
+}
+
+template <int S, int PAR, bool GX>
+__global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                const __grid_constant__ CUtensorMap tm_gx, const FastPreArgs a) {
+  constexpr int GPN = pre_gpn<S>();
+  constexpr int NWG = S == 1 ? 6 : 4;  // gpre rows touched by 4 consecutive positions
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = align1024(smem_dyn);
+  float* xs = reinterpret_cast<float*>(base);                  // [kPreSlots][4 boxes][32 rows][32] swizzled
+  float* gps = xs + (size_t)kPreSlots * 4096;                   // [kPreSlots][GPN][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(gps + (size_t)kPreSlots * GPN * FQ);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.y * 32, c = c0 + lane;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    if (GX) tma_prefetch_desc(&tm_gx);
+    for (int s = 0; s < kPreSlots; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  float w[FQ][3], gw[FQ][3];
+#pragma unroll
+  for (int j = 0; j < FQ; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      w[j][k] = (c < a.C) ? a.w_pre[(size_t)j * a.C * 3 + c * 3 + k] : 0.f;
+      gw[j][k] = 0.f;
+    }
+  __syncthreads();
+
+  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto issue = [&](int n) {
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int l0 = (tile - b * a.tiles_per_utt) * 128;
+    const int i_lo = floor_div(l0 + a.P - 2, S);
+    const int s = n % kPreSlots;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(4096 + GPN * FQ) * 4);
+    for (int bx = 0; bx < 4; ++bx) tma_load_3d(xs + (size_t)s * 4096 + bx * 1024, &tm_x, l0 + bx * 32, c0, b, &full[s]);
+    bulk_g2s(gps + (size_t)s * GPN * FQ, a.gpre_pad + ((size_t)b * a.LP + kHaloL + i_lo) * FQ, GPN * FQ * 4, &full[s]);
+  };
+  if (tid == 0)
+    for (int n = 0; n < kPreSlots - 1 && n < my_tiles; ++n) issue(n);
+
+  for (int n = 0; n < my_tiles; ++n) {
+    const int s = n % kPreSlots;
+    if (tid == 0 && n + kPreSlots - 1 < my_tiles) {
+      // slot (n-1) % kPreSlots: its grad_x stores were committed at the end of the previous iteration
+      if (GX) bulk_wait_read<0>();
+      issue(n + kPreSlots - 1);
+    }
+    mbar_wait(&full[s], (n / kPreSlots) & 1);
+    float* xb = xs + (size_t)s * 4096 + warp * 1024;  // this warp's 32-position box
+    const float* gp = gps + (size_t)s * GPN * FQ;
+#pragma unroll 2
+    for (int cc = 0; cc < 8; ++cc) {
+      const int off = swz128(lane, cc);
+      const float4 xv4 = ld4(xb + off);
+      const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+      const int wb = (S == 1) ? (warp * 32 + cc * 4) : (warp * 16 + cc * 2);
+      float4 g[NWG];
+#pragma unroll
+      for (int q = 0; q < NWG; ++q) g[q] = ld4(gp + (size_t)(wb + q) * FQ);
+      float gx[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          // window index relative to wb: stride 1: p - k + 2; stride 2: (p + PAR - k)/2 + 1 when even
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int num = p + PAR - k;
+          const bool valid = (S == 1) || ((num & 1) == 0);
+          if (valid) {
+            const int q = (S == 1) ? (p - k + 2) : (num / 2 + 1);
+            const float4 gq = g[q];
+            gw[0][k] = fmaf(gq.x, xv[p], gw[0][k]);
+            gw[1][k] = fmaf(gq.y, xv[p], gw[1][k]);
+            gw[2][k] = fmaf(gq.z, xv[p], gw[2][k]);
+            gw[3][k] = fmaf(gq.w, xv[p], gw[3][k]);
+            if (GX) acc = fmaf(gq.w, w[3][k], fmaf(gq.z, w[2][k], fmaf(gq.y, w[1][k], fmaf(gq.x, w[0][k], acc))));
+          }
+        }
+        gx[p] = acc;
+      }
+      if (GX) st4(xb + off, make_float4(gx[0], gx[1], gx[2], gx[3]));
+    }
+    if (GX) {
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        const int tile = blockIdx.x + n * gridDim.x;
+        const int b = tile / a.tiles_per_utt;
+        const int l0 = (tile - b * a.tiles_per_utt) * 128;
+        for (int bx = 0; bx < 4; ++bx) tma_store_3d(&tm_gx, l0 + bx * 32, c0, b, xs + (size_t)s * 4096 + bx * 1024);
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();  // slot reuse: every warp is done reading before thread 0 re-issues into it
+    }
+  }
+  if (GX && tid == 0) bulk_wait_all<0>();
+  __syncthreads();
+  // ---- cross-warp reduction of the weight-gradient partials (reuses the tile memory)
+  float* red = xs;  // [kWarps][32][12]
+#pragma unroll
+  for (int j = 0; j < FQ; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) red[((size_t)warp * 32 + lane) * 12 + j * 3 + k] = gw[j][k];
+  __syncthreads();
+  float* prow = a.part + ((size_t)blockIdx.x * a.Cpad + c0) * 12;
+  for (int e = tid; e < 32 * 12; e += kThreads) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kWarps; ++wq) sum += red[(size_t)wq * 32 * 12 + e];
+    prow[e] = sum;
+  }
+}
+
+// =============================================================================================== finalize
+struct FastFinArgs {
+  const float *part1, *part2, *part3, *qw;
+  float *gw_pre, *gb_pre, *gqw, *gw_post, *gb_post;
+  int G1, P1, G2, P2, G3, P3;
+  int C, O, Lq;
+};
+
+__global__ void __launch_bounds__(kFinThreads) fast_finalize_kernel(const FastFinArgs a) {
+  __shared__ double red[kFinWarps][33];
+  __shared__ double tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb1 = a.P1 / 32, nb2 = a.P2 / 32;
+  int seg, blk;
+  if ((int)blockIdx.x < nb1) { seg = 1; blk = blockIdx.x; }
+  else if ((int)blockIdx.x < nb1 + nb2) { seg = 2; blk = blockIdx.x - nb1; }
+  else { seg = 3; blk = blockIdx.x - nb1 - nb2; }
+  const int G = seg == 1 ? a.G1 : seg == 2 ? a.G2 : a.G3;
+  const int P = seg == 1 ? a.P1 : seg == 2 ? a.P2 : a.P3;
+  const float* __restrict__ part = seg == 1 ? a.part1 : seg == 2 ? a.part2 : a.part3;
+  const int blk0 = blk * 32, p = blk0 + lane;
+  double s = 0.0;
+  if (p < P) {
+    int g = warp;
+    for (; g + 3 * kFinWarps < G; g += 4 * kFinWarps) {
+      const float v0 = part[(size_t)g * P + p], v1 = part[(size_t)(g + kFinWarps) * P + p];
+      const float v2 = part[(size_t)(g + 2 * kFinWarps) * P + p], v3 = part[(size_t)(g + 3 * kFinWarps) * P + p];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; g < G; g += kFinWarps) s += (double)part[(size_t)g * P + p];
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp != 0) return;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kFinWarps; ++w) t += red[w][lane];
+  tot[lane] = t;
+  __syncwarp();
+  if (seg == 1) {
+    const int nW = a.O * FQ;
+    if (p < nW) a.gw_post[p] = (float)t;
+    else if (p < nW + a.O) a.gb_post[p - nW] = (float)t;
+  } else if (seg == 2) {
+    if (blk0 == 0) {
+      if (lane < FQ) a.gb_pre[lane] = (float)t;
+    } else if (lane < 4) {
+      const int gi = (blk0 - 32) / 8 + lane;
+      if (gi < a.Lq * FQ) {
+        double w3[3], g3[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) w3[e] = (double)a.qw[gi * 3 + e];
+        gate_grad_to_angles(w3, &tot[lane * 8], g3);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a.gqw[gi * 3 + e] = (float)g3[e];
+      }
+    }
+  } else {
+    const int cch = p / 12, r = p - cch * 12, j = r / 3, k = r - j * 3;
+    if (p < P && cch < a.C) a.gw_pre[(size_t)j * a.C * 3 + cch * 3 + k] = (float)t;
+  }
+}
+
+// =============================================================================================== host
+TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+
+int make_tmap_3d_f32(CUtensorMap* tm, const void* base, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                     unsigned box0, unsigned box1, bool swizzle128) {
+  TmapEncodeFn fn = tmap_encode_fn();
+  QW_CHECK_ARG(fn != nullptr, -2, "cuTensorMapEncodeTiled is not available from this driver");
+  // the driver API needs the primary context bound to THIS thread (autograd runs backward on its own threads)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    QW_CUDA_OK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
+  const cuuint64_t gdim[3] = {d0, d1, d2};
+  const cuuint64_t gstr[2] = {d0 * 4ull, d0 * d1 * 4ull};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QW_CHECK_ARG(r == CUDA_SUCCESS, -2, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static bool g_fast_enabled = true;
+void set_fast_path(bool on) { g_fast_enabled = on; }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd) {
+  return g_fast_enabled && (!fwd || d.P == 1) && d.Q == 4 && d.K == 3 && (d.S == 1 || d.S == 2) && d.emb == kEmbAmplitude && d.L % 4 == 0 &&
+         d.Lout % 4 == 0 && d.O % 4 == 0 && d.O <= 576 && d.C * 3 * FQ * 4 <= 96 * 1024 && aligned16(x) && aligned16(y_or_gy) &&
+         aligned16(gx) && tmap_encode_fn() != nullptr;
+}
+
+FastPlan make_fast_plan(const ConvDims& d) {
+  FastPlan p{};
+  const int sms = num_sms();
+  p.tiles_per_utt = (d.Lout + FTW - 1) / FTW;
+  p.num_tiles = d.B * p.tiles_per_utt;
+  p.rc = (d.C % 64 != 0 && d.C <= 128) ? 16 : 64;
+  p.chunks_per_tile = (d.C + p.rc - 1) / p.rc;
+  p.gridF = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
+  p.gridGy = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
+  p.PA1 = (int)align_up((size_t)d.O * 5, 32);
+  const long long W = (long long)d.B * d.Lout;
+  const long long need = (W + kThreads - 1) / kThreads;
+  p.gridAdj = (int)(need < 3LL * sms ? need : 3LL * sms);
+  p.PA2 = 32 + (int)align_up((size_t)d.Lq * FQ * 8, 32);
+  p.LP = kHaloL + d.Lout + kHaloR;
+  p.ptiles_per_utt = (d.L + 127) / 128;
+  p.num_ptiles = d.B * p.ptiles_per_utt;
+  p.nchunks = (d.C + 31) / 32;
+  p.Cpad = p.nchunks * 32;
+  int cap = 3 * sms / p.nchunks;
+  if (cap < 1) cap = 1;
+  p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
+  p.PB = p.Cpad * 12;
+  size_t o = 0;
+  p.off_gout = o; o = align_up(o + (size_t)W * FQ * 4, 256);
+  p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
+  p.off_p1 = o;   o = align_up(o + (size_t)p.gridGy * p.PA1 * 4, 256);
+  p.off_p2 = o;   o = align_up(o + (size_t)p.gridAdj * p.PA2 * 4, 256);
+  p.off_p3 = o;   o = align_up(o + (size_t)p.gridPx * p.PB * 4, 256);
+  p.ws_bytes = o;
+  return p;
+}
+
+template <int S, int RC>
+static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const FastPlan& p, cudaStream_t st) {
+  const size_t smem = fast_fwd_smem_bytes<S, RC>(a.C * 3, a.O, a.Lq);
+  QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast forward needs %zu bytes of shared memory", smem);
+  auto k = fast_fwd_kernel<S, RC>;
+  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelTimer kt(kKFwd, st);
+    k<<<p.gridF, kThreads, smem, st>>>(tm, a);
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fast_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
+                 const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st) {
+  const FastPlan p = make_fast_plan(d);
+  alignas(64) CUtensorMap tm;
+  const int xw = d.S == 1 ? fwd_xw<1>() : fwd_xw<2>();
+  if (int e = make_tmap_3d_f32(&tm, x, d.L, d.C, d.B, xw, p.rc, false)) return e;
+  const size_t W = (size_t)d.B * d.Lout;
+  FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
+                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile};
+  if (d.S == 1) return p.rc == 16 ? launch_fast_fwd<1, 16>(tm, a, p, st) : launch_fast_fwd<1, 64>(tm, a, p, st);
+  return p.rc == 16 ? launch_fast_fwd<2, 16>(tm, a, p, st) : launch_fast_fwd<2, 64>(tm, a, p, st);
+}
+
+template <int RPT>
+static int launch_fast_gy(const CUtensorMap& tg, const CUtensorMap& tq, const FastGyArgs& a, const FastPlan& p, cudaStream_t st) {
+  const size_t smem = fast_gy_smem_bytes(a.O);
+  QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
+  auto k = fast_bwd_gy_kernel<RPT>;
+  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelTimer kt(kKBwdPost, st);
+    k<<<p.gridGy, kGyThreads, smem, st>>>(tg, tq, a);
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int S, int PAR, bool GX>
+static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const FastPreArgs& a, const FastPlan& p, cudaStream_t st) {
+  const size_t smem = fast_pre_smem_bytes<S>();
+  auto k = fast_bwd_pre_kernel<S, PAR, GX>;
+  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelTimer kt(kKBwdPre, st);
+    k<<<dim3(p.gridPx, p.nchunks), kThreads, smem, st>>>(tx, tgx, a);
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
+                  const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st) {
+  const FastPlan p = make_fast_plan(d);
+  const size_t W = (size_t)d.B * d.Lout;
+  float* gout = reinterpret_cast<float*>(ws + p.off_gout);
+  float* gpre = reinterpret_cast<float*>(ws + p.off_gpre);
+  float* part1 = reinterpret_cast<float*>(ws + p.off_p1);
+  float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
+  float* part3 = reinterpret_cast<float*>(ws + p.off_p3);
+  alignas(64) CUtensorMap tm_gy, tm_qout, tm_x, tm_gx;
+  if (int e = make_tmap_3d_f32(&tm_gy, gy, d.Lout, d.O, d.B, 32, 64, true)) return e;
+  if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
+  if (int e = make_tmap_3d_f32(&tm_x, x, d.L, d.C, d.B, 32, 32, true)) return e;
+  if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
+  // 1) stream gy
+  {
+    FastGyArgs a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, (d.O + 63) / 64};
+    const int rpt = (d.O + kGyThreads - 1) / kGyThreads;
+    int e = rpt == 1 ? launch_fast_gy<1>(tm_gy, tm_qout, a, p, st)
+          : rpt == 2 ? launch_fast_gy<2>(tm_gy, tm_qout, a, p, st)
+                     : launch_fast_gy<3>(tm_gy, tm_qout, a, p, st);
+    if (e) return e;
+  }
+  // 2) adjoint circuit
+  {
+    FastAdjArgs a{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W};
+    const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)(FQ + d.Lq * FQ * 8) * (kThreads + 1)) * 4;
+    QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      KernelTimer kt(kKBwdAdj, st);
+      fast_bwd_adj_kernel<<<p.gridAdj, kThreads, smem, st>>>(a);
+    }
+    QW_CUDA_OK(cudaGetLastError());
+  }
+  // 3) pre_conv^T
+  {
+    FastPreArgs a{gpre, w_pre, part3, d.B, d.C, d.L, d.P, d.Lout, p.LP, p.ptiles_per_utt, p.num_ptiles, p.Cpad};
+    const int par = d.P & 1;
+    int e;
+    if (d.S == 1) e = gx ? launch_fast_pre<1, 0, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<1, 0, false>(tm_x, tm_gx, a, p, st);
+    else if (par) e = gx ? launch_fast_pre<2, 1, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<2, 1, false>(tm_x, tm_gx, a, p, st);
+    else          e = gx ? launch_fast_pre<2, 0, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<2, 0, false>(tm_x, tm_gx, a, p, st);
+    if (e) return e;
+  }
+  // 4) finalize
+  {
+    FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post,
+                  p.gridGy, p.PA1, p.gridAdj, p.PA2, p.gridPx, p.PB, d.C, d.O, d.Lq};
+    const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
+    {
+      KernelTimer kt(kKBwdFinalize, st);
+      fast_finalize_kernel<<<nblk, kFinThreads, 0, st>>>(a);
+    }
+    QW_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace qw

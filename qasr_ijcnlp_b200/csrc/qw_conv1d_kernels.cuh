@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) qconv_fwd_kernel(const FwdArgs<T> a)
         if (a.pre_save) st_vec<T, Q>(a.pre_save + ((size_t)b * d.Lout + i) * Q, pre);
         T re[1 << Q], im[1 << Q];
         circuit_forward_amp<T, Q>(pre, gates, d.Lq, re, im, out);
+        if (a.pre_save) st_vec<T, Q>(a.pre_save + ((size_t)(d.B + b) * d.Lout + i) * Q, out);  // plane 1: <Z_i>
       } else {
 #pragma unroll
         for (int j = 0; j < Q; ++j) out[j] = T(0);

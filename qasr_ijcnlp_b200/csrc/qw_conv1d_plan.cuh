@@ -35,6 +35,22 @@ inline WsLayout<T> ws_layout(const ConvDims& d, const Plan& p) {
 }
 
 
+// ---- fast path (qw_conv1d_fast.cu): fp32, q = 4, K = 3, stride 1|2, aligned shapes
+struct FastPlan {
+  int tiles_per_utt, num_tiles, rc, chunks_per_tile, gridF;
+  int gridGy, PA1, gridAdj, PA2, LP;
+  int ptiles_per_utt, num_ptiles, nchunks, Cpad, gridPx, PB;
+  size_t off_gout, off_gpre, off_p1, off_p2, off_p3, ws_bytes;
+};
+void set_fast_path(bool on);
+bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd);
+FastPlan make_fast_plan(const ConvDims& d);
+int fast_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
+                 const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st);
+int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
+                  const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st);
+
 // per-(T,Q) entry points, explicitly instantiated in qw_conv1d_inst.cu
 template <typename T, int Q>
 int fwd_tq(const FwdArgs<T>& a, const Plan& p, cudaStream_t st);

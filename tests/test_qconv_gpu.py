@@ -19,8 +19,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _mods():
-    from qasr_ijcnlp_b200 import _lib, quantum_conv1d as qc
-    return _lib, qc
+    import importlib
+
+    from qasr_ijcnlp_b200 import _lib
+    return _lib, importlib.import_module("qasr_ijcnlp_b200.quantum_conv1d")
 
 
 def _kat(golden_dir):
@@ -136,6 +138,57 @@ def test_layer_f64_validation_build(cuda, geom):
         assert _rel(got[k], ref[k]) <= 1e-10, k  # fp64 validation build: 1e-10 (relative to max(1,|ref|))
 
 
+FAST_GEOMS = [
+    # shapes that qualify for the TMA fast path (fp32, q=4, K=3, S in {1,2}, L%4==0, L_out%4==0, O%4==0)
+    (2, 80, 200, 3, 1, 1, 384, 4),
+    (2, 384, 208, 3, 2, 1, 384, 4),
+    (3, 80, 260, 3, 1, 1, 384, 4),
+    (2, 40, 136, 3, 2, 1, 64, 4),
+    (1, 100, 1028, 3, 1, 1, 8, 4),
+    (5, 33, 72, 3, 2, 1, 200, 4),
+    (2, 130, 392, 3, 2, 3, 512, 4),
+]
+
+
+@pytest.fixture(params=[True, False], ids=["fast", "generic"])
+def fast_path(request):
+    from qasr_ijcnlp_b200 import _lib
+    lib = _lib.load()
+    lib.qw_set_fast_path(1 if request.param else 0)
+    yield request.param
+    lib.qw_set_fast_path(1)
+
+
+@pytest.mark.parametrize("geom", FAST_GEOMS)
+@pytest.mark.parametrize("n_layers", [1, 2])
+def test_layer_f32_fast_and_generic(cuda, geom, n_layers, fast_path):
+    """Same tolerances as test_layer_f32, run once through the TMA fast path and once through the generic kernels."""
+    got, ref = _run_layer(cuda, geom, torch.float32, n_layers=n_layers, seed=5)
+    assert (got["y"] - ref["y"]).abs().max().item() <= 5e-5
+    for k in ("x", "w_pre", "b_pre", "qweights", "w_post", "b_post"):
+        assert _rel(got[k], ref[k]) <= 5e-5, k
+
+
+def test_fast_and_generic_agree_full_size(cuda):
+    """Whisper-Tiny stem shapes at batch 4: fast path vs generic kernels (both fp32) on identical inputs."""
+    _lib, qc = _mods()
+    lib = _lib.load()
+    for (C, S) in ((80, 1), (384, 2)):
+        torch.manual_seed(21)
+        m = qc.QuantumConv1d(C, 384, 3, stride=S, padding=1, n_qubits=4).to(cuda)
+        x = torch.randn(4, C, 3000, device=cuda, requires_grad=True)
+        res = []
+        for fast in (1, 0):
+            lib.qw_set_fast_path(fast)
+            y = m(x)
+            gy = torch.ones_like(y) * torch.linspace(-1, 1, y.shape[-1], device=cuda)
+            grads = torch.autograd.grad(y, [x] + list(m.parameters()), gy)
+            res.append([y.detach()] + [g for g in grads])
+        lib.qw_set_fast_path(1)
+        for a, b in zip(*res):
+            assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item())
+
+
 @pytest.mark.parametrize("geom", GEOMS)
 def test_layer_f32(cuda, geom):
     got, ref = _run_layer(cuda, geom, torch.float32)
@@ -173,12 +226,12 @@ def test_window_indexing_bit_exact(cuda, geom):
         dev = [t.to(cuda).contiguous() for t in (x, w_pre, torch.zeros(q), torch.randn(q, 3, generator=g),
                                                  torch.randn(O, q, generator=g), torch.zeros(O))]
         y = torch.empty(B, O, Lo, device=cuda)
-        pre_save = torch.empty(B * Lo, q, device=cuda)
+        pre_save = torch.empty(2, B * Lo, q, device=cuda)
         st = lib.qw_conv1d_forward(*[ctypes.c_void_p(t.data_ptr()) for t in dev], ctypes.c_void_p(y.data_ptr()),
                                    ctypes.c_void_p(pre_save.data_ptr()), B, C, L, K, S, P, O, q, 1, 0,
                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(st, "qw_conv1d_forward")
-        got = pre_save.cpu().reshape(B, Lo, q)
+        got = pre_save[0].cpu().reshape(B, Lo, q)
         want = ref_win[:, fsel, :].permute(0, 2, 1)
         assert torch.equal(got, want)
 
