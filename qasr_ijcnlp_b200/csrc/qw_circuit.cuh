@@ -271,26 +271,27 @@ __device__ __forceinline__ void circuit_backward_amp(const T (&pre)[Q], T inv, c
   for (int k = 0; k < Q; ++k) gpre[k] = (gv[k] - pre[k] * inv * dot) * inv;
 }
 
-// Gate matrices from quantum_weights (phi,theta,omega), computed in double.  out: 16 values (G then G^dagger).
+// Gate matrices from quantum_weights (phi,theta,omega), computed in the kernel's own precision (sincosf is
+// accurate to ~2 ulp; no fast-math).  out: 16 values (G then G^dagger).
 template <typename T>
 __device__ __forceinline__ void make_gate(const T* __restrict__ w3, T* __restrict__ out) {
-  const double phi = (double)w3[0], th = (double)w3[1], om = (double)w3[2];
-  double s, c, sp, cp, sm, cm;
-  sincos(0.5 * th, &s, &c);
-  sincos(0.5 * (phi + om), &sp, &cp);  // e^{-i(phi+om)/2} = cp - i sp
-  sincos(0.5 * (phi - om), &sm, &cm);  // e^{+i(phi-om)/2} = cm + i sm
-  const double g[8] = {cp * c, -sp * c, -cm * s, -sm * s, cm * s, -sm * s, cp * c, sp * c};
+  const T phi = w3[0], th = w3[1], om = w3[2];
+  T s, c, sp, cp, sm, cm;
+  sincos(T(0.5) * th, &s, &c);
+  sincos(T(0.5) * (phi + om), &sp, &cp);  // e^{-i(phi+om)/2} = cp - i sp
+  sincos(T(0.5) * (phi - om), &sm, &cm);  // e^{+i(phi-om)/2} = cm + i sm
+  const T g[8] = {cp * c, -sp * c, -cm * s, -sm * s, cm * s, -sm * s, cp * c, sp * c};
 #pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = (T)g[e];
+  for (int e = 0; e < 8; ++e) out[e] = g[e];
   // dagger: (G^dag)_ab = conj(G_ba)
-  out[8] = (T)g[0];
-  out[9] = (T)(-g[1]);
-  out[10] = (T)g[4];
-  out[11] = (T)(-g[5]);
-  out[12] = (T)g[2];
-  out[13] = (T)(-g[3]);
-  out[14] = (T)g[6];
-  out[15] = (T)(-g[7]);
+  out[8] = g[0];
+  out[9] = -g[1];
+  out[10] = g[4];
+  out[11] = -g[5];
+  out[12] = g[2];
+  out[13] = -g[3];
+  out[14] = g[6];
+  out[15] = -g[7];
 }
 
 // Chain rule from the summed gate-gradient matrix M_ab = sum conj(lambda_a) psi_b to (phi,theta,omega):

@@ -27,8 +27,10 @@ constexpr int FTW = 32;   // windows per tile (forward, gy streaming)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 1024-byte aligned start inside the dynamic shared-memory window.  Computed as an OFFSET from the
+// `extern __shared__` symbol so the compiler keeps the pointer in the shared address space (LDS/STS, not LD/ST).
 __device__ __forceinline__ unsigned char* align1024(unsigned char* p) {
-  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+  return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);
 }
 
 // =============================================================================================== forward
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constan
   constexpr int XW = fwd_xw<S>();
   constexpr int STAGE_ELEMS = RC * XW;
   constexpr int ITS = RC / 16;  // 4 warps x 4 rows per iteration
-  extern __shared__ unsigned char smem_dyn[];
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* base = align1024(smem_dyn);
   float* stage = reinterpret_cast<float*>(base);                    // [kFwdStages][RC][XW]
   float* wpre_t = stage + (size_t)kFwdStages * STAGE_ELEMS;         // [C*3][4]
@@ -252,7 +254,7 @@ __host__ __device__ constexpr size_t fast_gy_smem_bytes(int O) {
 template <int RPT>
 __global__ void __launch_bounds__(kGyThreads) fast_bwd_gy_kernel(const __grid_constant__ CUtensorMap tm_gy,
                                                                  const __grid_constant__ CUtensorMap tm_qout, const FastGyArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* base = align1024(smem_dyn);
   const int slot_elems = a.nbox * 64 * 32;
   float* slots = reinterpret_cast<float*>(base);                       // [kGySlots][nbox*64][32] swizzled
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tm_gx, const FastPreArgs a) {
   constexpr int GPN = pre_gpn<S>();
   constexpr int NWG = S == 1 ? 6 : 4;  // gpre rows touched by 4 consecutive positions
-  extern __shared__ unsigned char smem_dyn[];
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* base = align1024(smem_dyn);
   float* xs = reinterpret_cast<float*>(base);                  // [kPreSlots][4 boxes][32 rows][32] swizzled
   float* gps = xs + (size_t)kPreSlots * 4096;                   // [kPreSlots][GPN][4]
@@ -577,6 +579,8 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
 }
 
 // =============================================================================================== finalize
+constexpr int kFFThreads = 1024;  // 32 warps per 32-column block: short dependent chains over the partial rows
+constexpr int kFFWarps = kFFThreads / 32;
 struct FastFinArgs {
   const float *part1, *part2, *part3, *qw;
   float *gw_pre, *gb_pre, *gqw, *gw_post, *gb_post;
@@ -584,8 +588,8 @@ struct FastFinArgs {
   int C, O, Lq;
 };
 
-__global__ void __launch_bounds__(kFinThreads) fast_finalize_kernel(const FastFinArgs a) {
-  __shared__ double red[kFinWarps][33];
+__global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFinArgs a) {
+  __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb1 = a.P1 / 32, nb2 = a.P2 / 32;
@@ -600,19 +604,19 @@ __global__ void __launch_bounds__(kFinThreads) fast_finalize_kernel(const FastFi
   double s = 0.0;
   if (p < P) {
     int g = warp;
-    for (; g + 3 * kFinWarps < G; g += 4 * kFinWarps) {
-      const float v0 = part[(size_t)g * P + p], v1 = part[(size_t)(g + kFinWarps) * P + p];
-      const float v2 = part[(size_t)(g + 2 * kFinWarps) * P + p], v3 = part[(size_t)(g + 3 * kFinWarps) * P + p];
+    for (; g + 3 * kFFWarps < G; g += 4 * kFFWarps) {
+      const float v0 = part[(size_t)g * P + p], v1 = part[(size_t)(g + kFFWarps) * P + p];
+      const float v2 = part[(size_t)(g + 2 * kFFWarps) * P + p], v3 = part[(size_t)(g + 3 * kFFWarps) * P + p];
       s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
     }
-    for (; g < G; g += kFinWarps) s += (double)part[(size_t)g * P + p];
+    for (; g < G; g += kFFWarps) s += (double)part[(size_t)g * P + p];
   }
   red[warp][lane] = s;
   __syncthreads();
   if (warp != 0) return;
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < kFinWarps; ++w) t += red[w][lane];
+  for (int w = 0; w < kFFWarps; ++w) t += red[w][lane];
   tot[lane] = t;
   __syncwarp();
   if (seg == 1) {
@@ -696,7 +700,7 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.PA1 = (int)align_up((size_t)d.O * 5, 32);
   const long long W = (long long)d.B * d.Lout;
   const long long need = (W + kThreads - 1) / kThreads;
-  p.gridAdj = (int)(need < 3LL * sms ? need : 3LL * sms);
+  p.gridAdj = (int)(need < 1LL * sms ? need : 1LL * sms);
   p.PA2 = 32 + (int)align_up((size_t)d.Lq * FQ * 8, 32);
   p.LP = kHaloL + d.Lout + kHaloR;
   p.ptiles_per_utt = (d.L + 127) / 128;
@@ -823,7 +827,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
     {
       KernelTimer kt(kKBwdFinalize, st);
-      fast_finalize_kernel<<<nblk, kFinThreads, 0, st>>>(a);
+      fast_finalize_kernel<<<nblk, kFFThreads, 0, st>>>(a);
     }
     QW_CUDA_OK(cudaGetLastError());
   }
