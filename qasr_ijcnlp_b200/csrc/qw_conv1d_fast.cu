@@ -42,6 +42,8 @@ struct FastFwdArgs {
 };
 
 constexpr int kFwdStages = 4;
+constexpr int kFwdSW = 8;                         // streaming warps
+constexpr int kFwdThreads = (kFwdSW + 1) * 32;    // + 1 circuit warp
 // x tile columns: the TMA box must start on a 16-byte boundary, so it starts 4 columns before window i0 tap 0 + P
 // (P == 1 on the fast path: tap k of local window w sits in column 3 + w*S + k).
 template <int S> __host__ __device__ constexpr int fwd_xw() { return S == 1 ? 40 : 72; }
@@ -49,15 +51,21 @@ template <int S> __host__ __device__ constexpr int fwd_xw() { return S == 1 ? 40
 template <int S, int RC>
 __host__ __device__ constexpr size_t fast_fwd_smem_bytes(int CK, int O, int Lq) {
   return 1024 + (size_t)kFwdStages * RC * fwd_xw<S>() * 4 +
-         ((size_t)CK * FQ + (size_t)O * FQ + align_up(O, 4) + 4 + (size_t)Lq * FQ * kGateStride + kWarps * FTW * FQ + FTW * FQ) * 4 +
-         2 * kFwdStages * 8;
+         ((size_t)CK * FQ + (size_t)O * FQ + align_up(O, 4) + 4 + (size_t)Lq * FQ * kGateStride + 2 * kFwdSW * FTW * FQ +
+          2 * FTW * FQ) * 4 +
+         (2 * kFwdStages + 8) * 8;
 }
 
+// Warp-specialised, mbarrier-coupled pipeline over the tiles of a persistent CTA:
+//   warps 0-7 (streaming): pre_conv partial sums of tile n from the TMA ring -> part[n&1]; then post_conv of
+//                          tile n-1 (outs[(n-1)&1] -> y, 128-bit coalesced stores).
+//   warp  8   (circuit)  : tile n: part[n&1] -> bias, statevector circuit, <Z_i> -> outs[n&1] (+ pre_save/qout_save).
+// Hand-offs: pfull/pempty (part), ofull/oempty (outs).  No CTA-wide barrier inside the loop.
 template <int S, int RC>
-__global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const FastFwdArgs a) {
+__global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const FastFwdArgs a) {
   constexpr int XW = fwd_xw<S>();
   constexpr int STAGE_ELEMS = RC * XW;
-  constexpr int ITS = RC / 16;  // 4 warps x 4 rows per iteration
+  constexpr int ITS = RC / (4 * kFwdSW);  // kFwdSW warps x 4 rows per iteration
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* base = align1024(smem_dyn);
   float* stage = reinterpret_cast<float*>(base);                    // [kFwdStages][RC][XW]
@@ -67,10 +75,14 @@ __global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constan
   float* bpost = wpost + (size_t)a.O * FQ;                          // [O]
   float* bpre = bpost + align_up(a.O, 4);                           // [4]
   float* gates = bpre + 4;                                          // [Lq][4][16]
-  float* part = gates + (size_t)a.Lq * FQ * kGateStride;            // [kWarps][32][4]
-  float* outs = part + kWarps * FTW * FQ;                           // [32][4]
-  uint64_t* full = reinterpret_cast<uint64_t*>(outs + FTW * FQ);    // [kFwdStages]
+  float* part = gates + (size_t)a.Lq * FQ * kGateStride;            // [2][kFwdSW][32][4]
+  float* outs = part + 2 * kFwdSW * FTW * FQ;                       // [2][32][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(outs + 2 * FTW * FQ);  // [kFwdStages]
   uint64_t* empty = full + kFwdStages;                              // [kFwdStages]
+  uint64_t* pfull = empty + kFwdStages;                             // [2]
+  uint64_t* pempty = pfull + 2;                                     // [2]
+  uint64_t* ofull = pempty + 2;                                     // [2]
+  uint64_t* oempty = ofull + 2;                                     // [2]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 3, tl = lane & 7;
@@ -79,16 +91,34 @@ __global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constan
     tma_prefetch_desc(&tm_x);
     for (int s = 0; s < kFwdStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kWarps);
+      mbar_init(&empty[s], kFwdSW);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&pfull[s], kFwdSW);
+      mbar_init(&pempty[s], 1);
+      mbar_init(&ofull[s], 1);
+      mbar_init(&oempty[s], kFwdSW);
     }
     fence_mbar_init();
   }
-  for (int idx = tid; idx < CK * FQ; idx += kThreads) {
-    const int j = idx / CK, f = idx - j * CK;
-    wpre_t[f * FQ + j] = a.w_pre[idx];
+  // ---- stage parameters (vectorised: 4 features x 4 qubits per step, transposed in registers)
+  if ((CK & 3) == 0) {
+    for (int u = tid; u < CK / 4; u += kFwdThreads) {
+      const float4 r0 = ld4(a.w_pre + 0 * (size_t)CK + 4 * u), r1 = ld4(a.w_pre + 1 * (size_t)CK + 4 * u);
+      const float4 r2 = ld4(a.w_pre + 2 * (size_t)CK + 4 * u), r3 = ld4(a.w_pre + 3 * (size_t)CK + 4 * u);
+      st4(wpre_t + (size_t)(4 * u + 0) * FQ, make_float4(r0.x, r1.x, r2.x, r3.x));
+      st4(wpre_t + (size_t)(4 * u + 1) * FQ, make_float4(r0.y, r1.y, r2.y, r3.y));
+      st4(wpre_t + (size_t)(4 * u + 2) * FQ, make_float4(r0.z, r1.z, r2.z, r3.z));
+      st4(wpre_t + (size_t)(4 * u + 3) * FQ, make_float4(r0.w, r1.w, r2.w, r3.w));
+    }
+  } else {
+    for (int idx = tid; idx < CK * FQ; idx += kFwdThreads) {
+      const int j = idx / CK, f = idx - j * CK;
+      wpre_t[f * FQ + j] = a.w_pre[idx];
+    }
   }
-  for (int idx = tid; idx < a.O * FQ; idx += kThreads) wpost[idx] = a.w_post[idx];
-  for (int idx = tid; idx < a.O; idx += kThreads) bpost[idx] = a.b_post[idx];
+  for (int u = tid; u < a.O; u += kFwdThreads) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
+  for (int idx = tid; idx < a.O; idx += kFwdThreads) bpost[idx] = a.b_post[idx];
   if (tid < FQ) bpre[tid] = a.b_pre[tid];
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   __syncthreads();
@@ -96,6 +126,42 @@ __global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constan
   const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total_chunks = my_tiles * a.chunks_per_tile;
 
+  if (warp == kFwdSW) {
+    // ======================================================== circuit warp: one lane per window
+    for (int n = 0; n < my_tiles; ++n) {
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      const int pb = n & 1, ph = (n >> 1) & 1;
+      mbar_wait(&pfull[pb], ph);
+      const float* pp = part + (size_t)pb * kFwdSW * FTW * FQ;
+      float pre[FQ];
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) pre[j] = bpre[j];
+#pragma unroll
+      for (int w = 0; w < kFwdSW; ++w) {
+        const float4 pv = ld4(pp + ((size_t)w * FTW + lane) * FQ);
+        pre[0] += pv.x; pre[1] += pv.y; pre[2] += pv.z; pre[3] += pv.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pempty[pb]);
+      float out[FQ] = {0.f, 0.f, 0.f, 0.f};
+      if (i < a.Lout) {
+        float re[1 << FQ], im[1 << FQ];
+        circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+        const size_t wi = (size_t)b * a.Lout + i;
+        if (a.pre_save) st4(a.pre_save + wi * FQ, make_float4(pre[0], pre[1], pre[2], pre[3]));
+        if (a.qout_save) st4(a.qout_save + wi * FQ, make_float4(out[0], out[1], out[2], out[3]));
+      }
+      if (n >= 2) mbar_wait(&oempty[pb], ((n >> 1) - 1) & 1);
+      st4(outs + (size_t)pb * FTW * FQ + (size_t)lane * FQ, make_float4(out[0], out[1], out[2], out[3]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ofull[pb]);
+    }
+    return;
+  }
+
+  // ========================================================== streaming warps
   // producer (thread 0): chunk g of this CTA -> stage g % kFwdStages
   auto issue = [&](int g) {
     const int n = g / a.chunks_per_tile, ch = g - n * a.chunks_per_tile;
@@ -110,338 +176,364 @@ __global__ void __launch_bounds__(kThreads) fast_fwd_kernel(const __grid_constan
     for (int g = 0; g < kFwdStages - 1 && g < total_chunks; ++g) issue(g);
 
   int g = 0;  // running chunk counter
-  for (int n = 0; n < my_tiles; ++n) {
-    const int tile = blockIdx.x + n * gridDim.x;
-    const int b = tile / a.tiles_per_utt;
-    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
-
-    // ---- phase 1: pre_conv partial sums over the channel chunks of this tile
-    float acc[4][FQ];
+  for (int n = 0; n <= my_tiles; ++n) {
+    // ---- pre_conv partial sums of tile n
+    if (n < my_tiles) {
+      float acc[4][FQ];
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
+      for (int w = 0; w < 4; ++w)
 #pragma unroll
-      for (int j = 0; j < FQ; ++j) acc[w][j] = 0.f;
-
-    for (int ch = 0; ch < a.chunks_per_tile; ++ch, ++g) {
-      if (tid == 0) {
-        const int gn = g + kFwdStages - 1;
-        if (gn < total_chunks) {
-          if (gn >= kFwdStages) mbar_wait(&empty[gn % kFwdStages], ((gn / kFwdStages) - 1) & 1);
-          issue(gn);
+        for (int j = 0; j < FQ; ++j) acc[w][j] = 0.f;
+      for (int ch = 0; ch < a.chunks_per_tile; ++ch, ++g) {
+        if (tid == 0) {
+          const int gn = g + kFwdStages - 1;
+          if (gn < total_chunks) {
+            if (gn >= kFwdStages) mbar_wait(&empty[gn % kFwdStages], ((gn / kFwdStages) - 1) & 1);
+            issue(gn);
+          }
         }
-      }
-      const int s = g % kFwdStages;
-      mbar_wait(&full[s], (g / kFwdStages) & 1);
-      const float* st = stage + (size_t)s * STAGE_ELEMS;
+        const int s = g % kFwdStages;
+        mbar_wait(&full[s], (g / kFwdStages) & 1);
+        const float* st = stage + (size_t)s * STAGE_ELEMS;
 #pragma unroll
-      for (int it = 0; it < ITS; ++it) {
-        const int rl = it * 16 + warp * 4 + rr;  // row inside the chunk
-        const int c = ch * RC + rl;              // channel (rows >= C are zero-filled by TMA; weights masked)
-        const float* xr = st + rl * XW;
-        float xc[S == 1 ? 6 : 9];
-        if constexpr (S == 1) {
-          const float4 v0 = ld4(xr + 4 * tl + 4);
-          xc[0] = xr[4 * tl + 3];
-          xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
-          xc[5] = xr[4 * tl + 8];
-        } else {
-          const float4 v0 = ld4(xr + 8 * tl + 4), v1 = ld4(xr + 8 * tl + 8);
-          xc[0] = xr[8 * tl + 3];
-          xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
-          xc[5] = v1.x; xc[6] = v1.y; xc[7] = v1.z; xc[8] = v1.w;
-        }
-        if (c < a.C) {
+        for (int it = 0; it < ITS; ++it) {
+          const int rl = it * (4 * kFwdSW) + warp * 4 + rr;  // row inside the chunk
+          const int c = ch * RC + rl;              // channel (rows >= C are zero-filled by TMA; weights masked)
+          const float* xr = st + rl * XW;
+          float xc[S == 1 ? 6 : 9];
+          if constexpr (S == 1) {
+            const float4 v0 = ld4(xr + 4 * tl + 4);
+            xc[0] = xr[4 * tl + 3];
+            xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
+            xc[5] = xr[4 * tl + 8];
+          } else {
+            const float4 v0 = ld4(xr + 8 * tl + 4), v1 = ld4(xr + 8 * tl + 8);
+            xc[0] = xr[8 * tl + 3];
+            xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
+            xc[5] = v1.x; xc[6] = v1.y; xc[7] = v1.z; xc[8] = v1.w;
+          }
+          if (c < a.C) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float4 wv = ld4(wpre_t + (size_t)(c * 3 + k) * FQ);
+            for (int k = 0; k < 3; ++k) {
+              const float4 wv = ld4(wpre_t + (size_t)(c * 3 + k) * FQ);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const float xv = xc[w * S + k];
-              acc[w][0] = fmaf(wv.x, xv, acc[w][0]);
-              acc[w][1] = fmaf(wv.y, xv, acc[w][1]);
-              acc[w][2] = fmaf(wv.z, xv, acc[w][2]);
-              acc[w][3] = fmaf(wv.w, xv, acc[w][3]);
+              for (int w = 0; w < 4; ++w) {
+                const float xv = xc[w * S + k];
+                acc[w][0] = fmaf(wv.x, xv, acc[w][0]);
+                acc[w][1] = fmaf(wv.y, xv, acc[w][1]);
+                acc[w][2] = fmaf(wv.z, xv, acc[w][2]);
+                acc[w][3] = fmaf(wv.w, xv, acc[w][3]);
+              }
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-    }
-    // reduce over the 4 row classes of the warp, then across warps through shared memory
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int j = 0; j < FQ; ++j) {
-        float v = acc[w][j];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        acc[w][j] = v;
-      }
-    if (rr == 0) {
+      // reduce over the 4 row classes of the warp; the circuit warp sums the kFwdSW warps
 #pragma unroll
       for (int w = 0; w < 4; ++w)
-        st4(part + ((size_t)warp * FTW + 4 * tl + w) * FQ, make_float4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]));
-    }
-    __syncthreads();
-
-    // ---- phase 2: one thread per window: bias, circuit, <Z_i>
-    if (tid < FTW) {
-      const int i = i0 + tid;
-      float out[FQ] = {0.f, 0.f, 0.f, 0.f};
-      if (i < a.Lout) {
-        float pre[FQ];
 #pragma unroll
-        for (int j = 0; j < FQ; ++j) pre[j] = bpre[j];
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          const float4 pv = ld4(part + ((size_t)w * FTW + tid) * FQ);
-          pre[0] += pv.x; pre[1] += pv.y; pre[2] += pv.z; pre[3] += pv.w;
+        for (int j = 0; j < FQ; ++j) {
+          float v = acc[w][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          acc[w][j] = v;
         }
-        float re[1 << FQ], im[1 << FQ];
-        circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
-        const size_t wi = (size_t)b * a.Lout + i;
-        if (a.pre_save) st4(a.pre_save + wi * FQ, make_float4(pre[0], pre[1], pre[2], pre[3]));
-        if (a.qout_save) st4(a.qout_save + wi * FQ, make_float4(out[0], out[1], out[2], out[3]));
-      }
-      st4(outs + (size_t)tid * FQ, make_float4(out[0], out[1], out[2], out[3]));
-    }
-    __syncthreads();
-
-    // ---- phase 3: post_conv, 4 output rows x (8 lanes x 4 adjacent windows) per warp instruction
-    float ov[4][FQ];
+      const int pb = n & 1;
+      if (n >= 2) mbar_wait(&pempty[pb], ((n >> 1) - 1) & 1);
+      if (rr == 0) {
+        float* pp = part + (size_t)pb * kFwdSW * FTW * FQ;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float4 v = ld4(outs + (size_t)(4 * tl + w) * FQ);
-      ov[w][0] = v.x; ov[w][1] = v.y; ov[w][2] = v.z; ov[w][3] = v.w;
+        for (int w = 0; w < 4; ++w)
+          st4(pp + ((size_t)warp * FTW + 4 * tl + w) * FQ, make_float4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pfull[pb]);
     }
-    const bool store_ok = (i0 + 4 * tl) < a.Lout;  // Lout % 4 == 0: a lane's 4 windows are all valid or all invalid
-    float* __restrict__ yb = a.y + (size_t)b * a.O * a.Lout + i0 + 4 * tl;
-    const int ngroups = a.O >> 2;
+    // ---- post_conv of tile n-1
+    if (n >= 1) {
+      const int m = n - 1;
+      const int tile = blockIdx.x + m * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+      const int ob = m & 1;
+      mbar_wait(&ofull[ob], (m >> 1) & 1);
+      const float* oo = outs + (size_t)ob * FTW * FQ;
+      float ov[4][FQ];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float4 v = ld4(oo + (size_t)(4 * tl + w) * FQ);
+        ov[w][0] = v.x; ov[w][1] = v.y; ov[w][2] = v.z; ov[w][3] = v.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&oempty[ob]);
+      const bool store_ok = (i0 + 4 * tl) < a.Lout;  // Lout % 4 == 0: a lane's 4 windows are all valid or all invalid
+      float* __restrict__ yb = a.y + (size_t)b * a.O * a.Lout + i0 + 4 * tl;
+      const int ngroups = a.O >> 2;
 #pragma unroll 4
-    for (int og = warp; og < ngroups; og += kWarps) {
-      const int o = og * 4 + rr;
-      const float4 wv = ld4(wpost + (size_t)o * FQ);
-      const float bv = bpost[o];
-      float4 r;
-      r.x = fmaf(wv.w, ov[0][3], fmaf(wv.z, ov[0][2], fmaf(wv.y, ov[0][1], fmaf(wv.x, ov[0][0], bv))));
-      r.y = fmaf(wv.w, ov[1][3], fmaf(wv.z, ov[1][2], fmaf(wv.y, ov[1][1], fmaf(wv.x, ov[1][0], bv))));
-      r.z = fmaf(wv.w, ov[2][3], fmaf(wv.z, ov[2][2], fmaf(wv.y, ov[2][1], fmaf(wv.x, ov[2][0], bv))));
-      r.w = fmaf(wv.w, ov[3][3], fmaf(wv.z, ov[3][2], fmaf(wv.y, ov[3][1], fmaf(wv.x, ov[3][0], bv))));
-      if (store_ok) st4(yb + (size_t)o * a.Lout, r);
+      for (int og = warp; og < ngroups; og += kFwdSW) {
+        const int o = og * 4 + rr;
+        const float4 wv = ld4(wpost + (size_t)o * FQ);
+        const float bv = bpost[o];
+        float4 r;
+        r.x = fmaf(wv.w, ov[0][3], fmaf(wv.z, ov[0][2], fmaf(wv.y, ov[0][1], fmaf(wv.x, ov[0][0], bv))));
+        r.y = fmaf(wv.w, ov[1][3], fmaf(wv.z, ov[1][2], fmaf(wv.y, ov[1][1], fmaf(wv.x, ov[1][0], bv))));
+        r.z = fmaf(wv.w, ov[2][3], fmaf(wv.z, ov[2][2], fmaf(wv.y, ov[2][1], fmaf(wv.x, ov[2][0], bv))));
+        r.w = fmaf(wv.w, ov[3][3], fmaf(wv.z, ov[3][2], fmaf(wv.y, ov[3][1], fmaf(wv.x, ov[3][0], bv))));
+        if (store_ok) st4(yb + (size_t)o * a.Lout, r);
+      }
     }
-    // `part` / `outs` are rewritten only after the next tile's phase 1, which every warp enters after this point;
-    // the __syncthreads() before phase 2 of the next tile orders those writes against these reads of `outs`.
-    __syncthreads();
   }
 }
 
-// =============================================================================================== backward: gy streaming
+// =============================================================================================== backward: gy streaming + adjoint
+constexpr int kHaloL = 8;
+constexpr int kHaloR = 144;
 struct FastGyArgs {
-  const float* w_post;
-  float *gout, *part;  // gout: [W][4]; part: [gridDim.x][PA1]
-  int B, O, Lout, tiles_per_utt, num_tiles, PA1, nbox;  // nbox = ceil(O/64) row boxes per tile
+  const float *w_post, *pre_save, *qw;
+  float *gpre_pad, *part;  // gpre_pad: [B][LP][4]; part: [gridDim.x][PA1]
+  int B, O, Lout, LP, Lq, tiles_per_utt, num_tiles, PA1;
 };
-constexpr int kGyThreads = 192;
-constexpr int kGyWarps = kGyThreads / 32;
-constexpr int kGySlots = 2;
+constexpr int kGySW = 6;                          // streaming warps (192 threads = one stage row each)
+constexpr int kGyAW = 2;                          // adjoint warps (alternate tiles)
+constexpr int kGyThreads = (kGySW + kGyAW) * 32;
+constexpr int kGyStream = kGySW * 32;
+constexpr int kGyStages = 3;                      // ring of 192-row x 32-window stages (3 TMA boxes of 64 rows)
+constexpr int kGyStageRows = 192;
+constexpr int kGyStageElems = kGyStageRows * 32;
+constexpr int kGyMS = 33;                         // per-lane accumulator column stride
+// partial-row layout: [O*4 gw_post][O gb_post][pad to 32][gb_pre 4 + pad 28][Lq*32 gate matrices][pad to 32]
+__host__ __device__ inline int gy_moff(int O) { return (int)align_up((size_t)O * 5, 32); }
+__host__ __device__ inline int gy_plen(int O, int Lq) { return gy_moff(O) + 32 + (int)align_up((size_t)Lq * 32, 32); }
 
-__host__ __device__ constexpr size_t fast_gy_smem_bytes(int O) {
-  return 1024 + (size_t)kGySlots * ((O + 63) / 64) * 64 * 128 + (size_t)kGySlots * FTW * FQ * 4 + (size_t)O * FQ * 4 +
-         (size_t)2 * kGyWarps * FTW * FQ * 4 + 2 * kGySlots * 8;
+__host__ __device__ constexpr size_t fast_gy_smem_bytes(int O, int Lq) {
+  return 1024 + (size_t)kGyStages * kGyStageElems * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)O * FQ * 4 +
+         (size_t)3 * kGySW * FTW * FQ * 4 + (size_t)Lq * FQ * kGateStride * 4 + (size_t)kGyAW * (FQ + Lq * 32) * kGyMS * 4 +
+         (2 * kGyStages + 6) * 8;
 }
 
-template <int RPT>
-__global__ void __launch_bounds__(kGyThreads) fast_bwd_gy_kernel(const __grid_constant__ CUtensorMap tm_gy,
-                                                                 const __grid_constant__ CUtensorMap tm_qout, const FastGyArgs a) {
+// Warp-specialised, mbarrier-coupled:
+//   warps 0-5 (streaming): per tile, NHALF stages of 192 output channels: gout partials (time-major lanes) and
+//                          grad post_conv.{weight,bias} (channel-major lanes, register accumulators); gout partials of
+//                          tile n -> gred[n%3].
+//   warps 6-7 (adjoint)  : tile n (n%2 == warp-6): gred[n%3] -> adjoint circuit -> gpre (halo-padded), gate-gradient
+//                          and grad pre_conv.bias sums in per-lane shared-memory columns.
+template <int NHALF>
+__global__ void __launch_bounds__(kGyThreads, 2) fast_bwd_gy_kernel(const __grid_constant__ CUtensorMap tm_gy,
+                                                                    const __grid_constant__ CUtensorMap tm_qout, const FastGyArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* base = align1024(smem_dyn);
-  const int slot_elems = a.nbox * 64 * 32;
-  float* slots = reinterpret_cast<float*>(base);                       // [kGySlots][nbox*64][32] swizzled
-  float* outs = slots + (size_t)kGySlots * slot_elems;                 // [kGySlots][32][4]
-  float* wpost = outs + kGySlots * FTW * FQ;                           // [O][4]
-  float* gred = wpost + (size_t)a.O * FQ;                              // [2][kGyWarps][32][4]
-  uint64_t* full = reinterpret_cast<uint64_t*>(gred + 2 * kGyWarps * FTW * FQ);
-  uint64_t* empty = full + kGySlots;
+  const int NE = FQ + a.Lq * 32;
+  float* stages = reinterpret_cast<float*>(base);                      // [kGyStages][192][32] swizzled
+  float* outs = stages + (size_t)kGyStages * kGyStageElems;            // [3][32][4]
+  float* wpost = outs + 3 * FTW * FQ;                                  // [O][4]
+  float* gred = wpost + (size_t)a.O * FQ;                              // [3][kGySW][32][4]
+  float* gates = gred + 3 * kGySW * FTW * FQ;                          // [Lq][4][16]
+  float* macc = gates + (size_t)a.Lq * FQ * kGateStride;               // [kGyAW][NE][kGyMS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(macc + (size_t)kGyAW * NE * kGyMS);
+  uint64_t* empty = full + kGyStages;
+  uint64_t* gfull = empty + kGyStages;   // [3]
+  uint64_t* gempty = gfull + 3;          // [3]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 3, tl = lane & 7;
   if (tid == 0) {
     tma_prefetch_desc(&tm_gy);
     tma_prefetch_desc(&tm_qout);
-    for (int s = 0; s < kGySlots; ++s) {
+    for (int s = 0; s < kGyStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kGyWarps);
+      mbar_init(&empty[s], kGySW);
+    }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&gfull[s], kGySW);
+      mbar_init(&gempty[s], 1);
     }
     fence_mbar_init();
   }
-  for (int idx = tid; idx < a.O * FQ; idx += kGyThreads) wpost[idx] = a.w_post[idx];
-  __syncthreads();
-
-  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto issue = [&](int n) {
-    const int tile = blockIdx.x + n * gridDim.x;
-    const int b = tile / a.tiles_per_utt;
-    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
-    const int s = n % kGySlots;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(slot_elems + FTW * FQ) * 4);
-    for (int bx = 0; bx < a.nbox; ++bx) tma_load_3d(slots + (size_t)s * slot_elems + bx * 64 * 32, &tm_gy, i0, bx * 64, b, &full[s]);
-    tma_load_3d(outs + s * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
-  };
-  if (tid == 0 && my_tiles > 0) issue(0);
-
-  float wacc[RPT][FQ + 1];
-#pragma unroll
-  for (int m = 0; m < RPT; ++m)
-#pragma unroll
-    for (int j = 0; j <= FQ; ++j) wacc[m][j] = 0.f;
-
-  const int ngroups = a.O >> 2;
-  for (int n = 0; n < my_tiles; ++n) {
-    if (tid == 0 && n + 1 < my_tiles) {
-      if (n + 1 >= kGySlots) mbar_wait(&empty[(n + 1) % kGySlots], (((n + 1) / kGySlots) - 1) & 1);
-      issue(n + 1);
-    }
-    const int tile = blockIdx.x + n * gridDim.x;
-    const int b = tile / a.tiles_per_utt;
-    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
-    const int s = n % kGySlots;
-    mbar_wait(&full[s], (n / kGySlots) & 1);
-    const float* gs = slots + (size_t)s * slot_elems;
-    const float* os = outs + s * FTW * FQ;
-
-    // ---- gout = post_conv^T gy : lanes (4 rows x 8 chunks of 4 windows)
-    float gacc[4][FQ];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int j = 0; j < FQ; ++j) gacc[u][j] = 0.f;
-#pragma unroll 4
-    for (int og = warp; og < ngroups; og += kGyWarps) {
-      const int r = og * 4 + rr;
-      const float4 gv = ld4(gs + swz128(r, tl));
-      const float4 wv = ld4(wpost + (size_t)r * FQ);
-      gacc[0][0] = fmaf(gv.x, wv.x, gacc[0][0]); gacc[0][1] = fmaf(gv.x, wv.y, gacc[0][1]);
-      gacc[0][2] = fmaf(gv.x, wv.z, gacc[0][2]); gacc[0][3] = fmaf(gv.x, wv.w, gacc[0][3]);
-      gacc[1][0] = fmaf(gv.y, wv.x, gacc[1][0]); gacc[1][1] = fmaf(gv.y, wv.y, gacc[1][1]);
-      gacc[1][2] = fmaf(gv.y, wv.z, gacc[1][2]); gacc[1][3] = fmaf(gv.y, wv.w, gacc[1][3]);
-      gacc[2][0] = fmaf(gv.z, wv.x, gacc[2][0]); gacc[2][1] = fmaf(gv.z, wv.y, gacc[2][1]);
-      gacc[2][2] = fmaf(gv.z, wv.z, gacc[2][2]); gacc[2][3] = fmaf(gv.z, wv.w, gacc[2][3]);
-      gacc[3][0] = fmaf(gv.w, wv.x, gacc[3][0]); gacc[3][1] = fmaf(gv.w, wv.y, gacc[3][1]);
-      gacc[3][2] = fmaf(gv.w, wv.z, gacc[3][2]); gacc[3][3] = fmaf(gv.w, wv.w, gacc[3][3]);
-    }
-    // ---- grad post_conv.{weight,bias}: lanes along output channels, accumulators live in registers
-#pragma unroll
-    for (int m = 0; m < RPT; ++m) {
-      const int r = tid + m * kGyThreads;
-      if (r < a.O) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 gv = ld4(gs + swz128(r, c));
-          const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 ov = ld4(os + (size_t)(4 * c + u) * FQ);
-            wacc[m][0] = fmaf(g4[u], ov.x, wacc[m][0]);
-            wacc[m][1] = fmaf(g4[u], ov.y, wacc[m][1]);
-            wacc[m][2] = fmaf(g4[u], ov.z, wacc[m][2]);
-            wacc[m][3] = fmaf(g4[u], ov.w, wacc[m][3]);
-            wacc[m][4] += g4[u];
-          }
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-    // ---- finish gout: reduce the 4 row classes, then the warps
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int j = 0; j < FQ; ++j) {
-        float v = gacc[u][j];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        gacc[u][j] = v;
-      }
-    float* gr = gred + (size_t)(n & 1) * kGyWarps * FTW * FQ;
-    if (rr == 0) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        st4(gr + ((size_t)warp * FTW + 4 * tl + u) * FQ, make_float4(gacc[u][0], gacc[u][1], gacc[u][2], gacc[u][3]));
-    }
-    __syncthreads();
-    if (tid < FTW * FQ) {
-      const int t = tid >> 2;
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < kGyWarps; ++w) sum += gr[(size_t)w * FTW * FQ + tid];
-      if (i0 + t < a.Lout) a.gout[((size_t)b * a.Lout + i0) * FQ + tid] = sum;
-    }
-  }
-  // ---- partial row of this CTA: [O*4 gw_post][O gb_post]
-  float* prow = a.part + (size_t)blockIdx.x * a.PA1;
-#pragma unroll
-  for (int m = 0; m < RPT; ++m) {
-    const int r = tid + m * kGyThreads;
-    if (r < a.O) {
-      st4(prow + (size_t)r * FQ, make_float4(wacc[m][0], wacc[m][1], wacc[m][2], wacc[m][3]));
-      prow[a.O * FQ + r] = wacc[m][4];
-    }
-  }
-  for (int e = a.O * (FQ + 1) + tid; e < a.PA1; e += kGyThreads) prow[e] = 0.f;
-}
-
-// =============================================================================================== backward: adjoint
-constexpr int kHaloL = 8;
-constexpr int kHaloR = 144;
-struct FastAdjArgs {
-  const float *pre_save, *gout, *qw;
-  float *gpre_pad, *part;  // gpre_pad: [B][LP][4]; part: [gridDim.x][PA2]
-  int B, Lout, LP, Lq, PA2;
-  long long W;
-};
-
-__global__ void __launch_bounds__(kThreads) fast_bwd_adj_kernel(const FastAdjArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_adj[];
-  constexpr int MS = kThreads + 1;
-  const int NE = FQ + a.Lq * FQ * 8;
-  float* gates = reinterpret_cast<float*>(smem_adj);         // [Lq][4][16]
-  float* macc = gates + (size_t)a.Lq * FQ * kGateStride;     // [NE][MS]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int u = tid; u < a.O; u += kGyThreads) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
-  for (int idx = tid; idx < NE * MS; idx += kThreads) macc[idx] = 0.f;
+  for (int e = tid; e < kGyAW * NE * kGyMS; e += kGyThreads) macc[e] = 0.f;
   // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
   {
     const int per = (kHaloL + kHaloR) * FQ;
-    for (long long idx = (long long)blockIdx.x * kThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kThreads) {
+    for (long long idx = (long long)blockIdx.x * kGyThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kGyThreads) {
       const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
       const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
       a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
     }
   }
   __syncthreads();
-  for (long long w = (long long)blockIdx.x * kThreads + tid; w < a.W; w += (long long)gridDim.x * kThreads) {
-    const int b = (int)(w / a.Lout), i = (int)(w - (long long)b * a.Lout);
-    float pre[FQ], out[FQ], gout[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
-    ld_vec<float, FQ>(a.pre_save + w * FQ, pre);
-    ld_vec<float, FQ>(a.gout + w * FQ, gout);
-    const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
-    SmemGateAcc<float, FQ> acc{macc + (size_t)FQ * MS + tid, MS, 0};
-    circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
-    st_vec<float, FQ>(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, gpre);
+
+  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_stages = my_tiles * NHALF;
+  float wacc[NHALF][FQ + 1];
 #pragma unroll
-    for (int j = 0; j < FQ; ++j) macc[j * MS + tid] += gpre[j];
+  for (int m = 0; m < NHALF; ++m)
+#pragma unroll
+    for (int j = 0; j <= FQ; ++j) wacc[m][j] = 0.f;
+
+  if (warp >= kGySW) {
+    // ======================================================== adjoint warps
+    const int aw = warp - kGySW;
+    float* mymacc = macc + (size_t)aw * NE * kGyMS;
+    auto load_pre = [&](int n) {
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      return (i < a.Lout) ? ld4(a.pre_save + ((size_t)b * a.Lout + i) * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+    };
+    float4 pre_cur = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (aw < my_tiles) pre_cur = load_pre(aw);
+    for (int n = aw; n < my_tiles; n += kGyAW) {
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      const bool valid = i < a.Lout;
+      const int gb = n % 3;
+      mbar_wait(&gfull[gb], (n / 3) & 1);
+      const float* gr = gred + (size_t)gb * kGySW * FTW * FQ;
+      float gout[FQ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int w = 0; w < kGySW; ++w) {
+        const float4 pv = ld4(gr + ((size_t)w * FTW + lane) * FQ);
+        gout[0] += pv.x; gout[1] += pv.y; gout[2] += pv.z; gout[3] += pv.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gempty[gb]);
+      if (!valid) gout[0] = gout[1] = gout[2] = gout[3] = 0.f;
+      const float pre[FQ] = {pre_cur.x, pre_cur.y, pre_cur.z, pre_cur.w};
+      if (n + kGyAW < my_tiles) pre_cur = load_pre(n + kGyAW);  // prefetch for this warp's next tile
+      float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
+      const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+      SmemGateAcc<float, FQ> acc{mymacc + (size_t)FQ * kGyMS + lane, kGyMS, 0};
+      circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
+      if (valid) st4(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
+    }
+  } else {
+    // ======================================================== streaming warps
+    auto issue = [&](int gs) {
+      const int n = gs / NHALF, h = gs - n * NHALF;
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+      const int s = gs % kGyStages;
+      mbar_arrive_expect_tx(&full[s], (uint32_t)(kGyStageElems + (h == 0 ? FTW * FQ : 0)) * 4);
+#pragma unroll
+      for (int bx = 0; bx < 3; ++bx)
+        tma_load_3d(stages + (size_t)s * kGyStageElems + bx * 64 * 32, &tm_gy, i0, h * kGyStageRows + bx * 64, b, &full[s]);
+      if (h == 0) tma_load_3d(outs + (n % 3) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
+    };
+    if (tid == 0)
+      for (int gs = 0; gs < kGyStages - 1 && gs < total_stages; ++gs) issue(gs);
+
+    int gs = 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      float gacc[4][FQ];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < FQ; ++j) gacc[u][j] = 0.f;
+      const float* os = outs + (n % 3) * FTW * FQ;
+#pragma unroll
+      for (int h = 0; h < NHALF; ++h, ++gs) {
+        if (tid == 0) {
+          const int gn = gs + kGyStages - 1;
+          if (gn < total_stages) {
+            if (gn >= kGyStages) mbar_wait(&empty[gn % kGyStages], ((gn / kGyStages) - 1) & 1);
+            issue(gn);
+          }
+        }
+        const int s = gs % kGyStages;
+        mbar_wait(&full[s], (gs / kGyStages) & 1);
+        const float* gsm = stages + (size_t)s * kGyStageElems;
+        const int row0 = h * kGyStageRows;
+        // ---- gout partials: lanes (4 rows x 8 chunks of 4 windows); 48 row groups per stage, 8 per warp
+#pragma unroll 4
+        for (int og = warp; og < kGyStageRows / 4; og += kGySW) {
+          const int rl = og * 4 + rr;
+          const int r = row0 + rl;
+          const float4 gv = ld4(gsm + swz128(rl, tl));
+          const float4 wv = (r < a.O) ? ld4(wpost + (size_t)r * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gacc[0][0] = fmaf(gv.x, wv.x, gacc[0][0]); gacc[0][1] = fmaf(gv.x, wv.y, gacc[0][1]);
+          gacc[0][2] = fmaf(gv.x, wv.z, gacc[0][2]); gacc[0][3] = fmaf(gv.x, wv.w, gacc[0][3]);
+          gacc[1][0] = fmaf(gv.y, wv.x, gacc[1][0]); gacc[1][1] = fmaf(gv.y, wv.y, gacc[1][1]);
+          gacc[1][2] = fmaf(gv.y, wv.z, gacc[1][2]); gacc[1][3] = fmaf(gv.y, wv.w, gacc[1][3]);
+          gacc[2][0] = fmaf(gv.z, wv.x, gacc[2][0]); gacc[2][1] = fmaf(gv.z, wv.y, gacc[2][1]);
+          gacc[2][2] = fmaf(gv.z, wv.z, gacc[2][2]); gacc[2][3] = fmaf(gv.z, wv.w, gacc[2][3]);
+          gacc[3][0] = fmaf(gv.w, wv.x, gacc[3][0]); gacc[3][1] = fmaf(gv.w, wv.y, gacc[3][1]);
+          gacc[3][2] = fmaf(gv.w, wv.z, gacc[3][2]); gacc[3][3] = fmaf(gv.w, wv.w, gacc[3][3]);
+        }
+        // ---- grad post_conv.{weight,bias}: thread <-> stage row, accumulators live in registers
+        {
+          const int rl = tid;  // 0..191
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 gv = ld4(gsm + swz128(rl, c));
+            const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 ov = ld4(os + (size_t)(4 * c + u) * FQ);
+              wacc[h][0] = fmaf(g4[u], ov.x, wacc[h][0]);
+              wacc[h][1] = fmaf(g4[u], ov.y, wacc[h][1]);
+              wacc[h][2] = fmaf(g4[u], ov.z, wacc[h][2]);
+              wacc[h][3] = fmaf(g4[u], ov.w, wacc[h][3]);
+              wacc[h][4] += g4[u];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      // ---- reduce the 4 row classes and hand the warp partial to the adjoint warps
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < FQ; ++j) {
+          float v = gacc[u][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          gacc[u][j] = v;
+        }
+      const int gb = n % 3;
+      if (n >= 3) mbar_wait(&gempty[gb], ((n / 3) - 1) & 1);
+      if (rr == 0) {
+        float* gr = gred + (size_t)gb * kGySW * FTW * FQ;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          st4(gr + ((size_t)warp * FTW + 4 * tl + u) * FQ, make_float4(gacc[u][0], gacc[u][1], gacc[u][2], gacc[u][3]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gfull[gb]);
+    }
   }
   __syncthreads();
-  // partial row: [0..3] grad pre_conv.bias, [32 + g*8 + e] gate matrices
-  float* prow = a.part + (size_t)blockIdx.x * a.PA2;
-  for (int e = tid; e < a.PA2; e += kThreads) prow[e] = 0.f;
-  __syncthreads();
-  for (int e = warp; e < NE; e += kWarps) {
-    float s = 0.f;
-    for (int t = lane; t < kThreads; t += 32) s += macc[e * MS + t];
-    s = warp_sum(s);
-    if (lane == 0) prow[e < FQ ? e : 32 + (e - FQ)] = s;
+  // ---- partial row of this CTA
+  float* prow = a.part + (size_t)blockIdx.x * a.PA1;
+  if (warp < kGySW) {
+#pragma unroll
+    for (int m = 0; m < NHALF; ++m) {
+      const int r = m * kGyStageRows + tid;
+      if (r < a.O) {
+        st4(prow + (size_t)r * FQ, make_float4(wacc[m][0], wacc[m][1], wacc[m][2], wacc[m][3]));
+        prow[a.O * FQ + r] = wacc[m][4];
+      }
+    }
+  }
+  const int moff = gy_moff(a.O);
+  for (int e = a.O * (FQ + 1) + tid; e < moff; e += kGyThreads) prow[e] = 0.f;
+  for (int e = warp; e < a.PA1 - moff; e += kGyThreads / 32) {
+    // e in [0,4): grad pre_conv.bias; [32, 32+Lq*32): gate matrices; everything else padding
+    float v = 0.f;
+    const int src = e < FQ ? e : (e >= 32 && e < 32 + a.Lq * 32) ? FQ + (e - 32) : -1;
+    if (src >= 0) {
+#pragma unroll
+      for (int w = 0; w < kGyAW; ++w) v += macc[((size_t)w * NE + src) * kGyMS + lane];
+      v = warp_sum(v);
+    }
+    if (lane == 0) prow[moff + e] = v;
   }
 }
 
@@ -582,9 +674,9 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
 constexpr int kFFThreads = 1024;  // 32 warps per 32-column block: short dependent chains over the partial rows
 constexpr int kFFWarps = kFFThreads / 32;
 struct FastFinArgs {
-  const float *part1, *part2, *part3, *qw;
+  const float *part1, *part3, *qw;
   float *gw_pre, *gb_pre, *gqw, *gw_post, *gb_post;
-  int G1, P1, G2, P2, G3, P3;
+  int G1, P1, G3, P3;
   int C, O, Lq;
 };
 
@@ -592,14 +684,12 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb1 = a.P1 / 32, nb2 = a.P2 / 32;
-  int seg, blk;
-  if ((int)blockIdx.x < nb1) { seg = 1; blk = blockIdx.x; }
-  else if ((int)blockIdx.x < nb1 + nb2) { seg = 2; blk = blockIdx.x - nb1; }
-  else { seg = 3; blk = blockIdx.x - nb1 - nb2; }
-  const int G = seg == 1 ? a.G1 : seg == 2 ? a.G2 : a.G3;
-  const int P = seg == 1 ? a.P1 : seg == 2 ? a.P2 : a.P3;
-  const float* __restrict__ part = seg == 1 ? a.part1 : seg == 2 ? a.part2 : a.part3;
+  const int nb1 = a.P1 / 32;
+  const bool seg1 = (int)blockIdx.x < nb1;
+  const int blk = seg1 ? blockIdx.x : blockIdx.x - nb1;
+  const int G = seg1 ? a.G1 : a.G3;
+  const int P = seg1 ? a.P1 : a.P3;
+  const float* __restrict__ part = seg1 ? a.part1 : a.part3;
   const int blk0 = blk * 32, p = blk0 + lane;
   double s = 0.0;
   if (p < P) {
@@ -619,15 +709,14 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   for (int w = 0; w < kFFWarps; ++w) t += red[w][lane];
   tot[lane] = t;
   __syncwarp();
-  if (seg == 1) {
-    const int nW = a.O * FQ;
+  if (seg1) {
+    const int nW = a.O * FQ, moff = gy_moff(a.O);
     if (p < nW) a.gw_post[p] = (float)t;
     else if (p < nW + a.O) a.gb_post[p - nW] = (float)t;
-  } else if (seg == 2) {
-    if (blk0 == 0) {
+    else if (blk0 == moff) {
       if (lane < FQ) a.gb_pre[lane] = (float)t;
-    } else if (lane < 4) {
-      const int gi = (blk0 - 32) / 8 + lane;
+    } else if (blk0 > moff && lane < 4) {
+      const int gi = (blk0 - moff - 32) / 8 + lane;
       if (gi < a.Lq * FQ) {
         double w3[3], g3[3];
 #pragma unroll
@@ -684,7 +773,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd) {
   return g_fast_enabled && (!fwd || d.P == 1) && d.Q == 4 && d.K == 3 && (d.S == 1 || d.S == 2) && d.emb == kEmbAmplitude && d.L % 4 == 0 &&
-         d.Lout % 4 == 0 && d.O % 4 == 0 && d.O <= 576 && d.C * 3 * FQ * 4 <= 96 * 1024 && aligned16(x) && aligned16(y_or_gy) &&
+         d.Lout % 4 == 0 && d.O % 4 == 0 && d.O <= 576 && d.Lq <= 4 && d.C * 3 * FQ * 4 <= 96 * 1024 && aligned16(x) && aligned16(y_or_gy) &&
          aligned16(gx) && tmap_encode_fn() != nullptr;
 }
 
@@ -693,15 +782,20 @@ FastPlan make_fast_plan(const ConvDims& d) {
   const int sms = num_sms();
   p.tiles_per_utt = (d.Lout + FTW - 1) / FTW;
   p.num_tiles = d.B * p.tiles_per_utt;
-  p.rc = (d.C % 64 != 0 && d.C <= 128) ? 16 : 64;
+  p.rc = d.C <= 128 ? (int)align_up(d.C, 32) : 64;  // small C: the whole channel range is one TMA box per tile
   p.chunks_per_tile = (d.C + p.rc - 1) / p.rc;
-  p.gridF = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
+  {
+    const size_t smem = 1024 + (size_t)kFwdStages * p.rc * (d.S == 1 ? 40 : 72) * 4 +
+                        ((size_t)d.C * 3 * FQ + (size_t)d.O * 5 + 2 * kFwdSW * FTW * FQ + 512) * 4;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;  // 288 threads x 96 registers: two CTAs per SM
+    p.gridF = p.num_tiles < per_sm * sms ? p.num_tiles : per_sm * sms;
+  }
   p.gridGy = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
-  p.PA1 = (int)align_up((size_t)d.O * 5, 32);
+  p.PA1 = gy_plen(d.O, d.Lq);
   const long long W = (long long)d.B * d.Lout;
-  const long long need = (W + kThreads - 1) / kThreads;
-  p.gridAdj = (int)(need < 1LL * sms ? need : 1LL * sms);
-  p.PA2 = 32 + (int)align_up((size_t)d.Lq * FQ * 8, 32);
+  p.gridAdj = 0;
+  p.PA2 = 0;
   p.LP = kHaloL + d.Lout + kHaloR;
   p.ptiles_per_utt = (d.L + 127) / 128;
   p.num_ptiles = d.B * p.ptiles_per_utt;
@@ -712,10 +806,10 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
   p.PB = p.Cpad * 12;
   size_t o = 0;
-  p.off_gout = o; o = align_up(o + (size_t)W * FQ * 4, 256);
+  p.off_gout = o;
   p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
   p.off_p1 = o;   o = align_up(o + (size_t)p.gridGy * p.PA1 * 4, 256);
-  p.off_p2 = o;   o = align_up(o + (size_t)p.gridAdj * p.PA2 * 4, 256);
+  p.off_p2 = o;
   p.off_p3 = o;   o = align_up(o + (size_t)p.gridPx * p.PB * 4, 256);
   p.ws_bytes = o;
   return p;
@@ -729,7 +823,7 @@ static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const Fa
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKFwd, st);
-    k<<<p.gridF, kThreads, smem, st>>>(tm, a);
+    k<<<p.gridF, kFwdThreads, smem, st>>>(tm, a);
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -744,15 +838,27 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
   const size_t W = (size_t)d.B * d.Lout;
   FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
                 d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile};
-  if (d.S == 1) return p.rc == 16 ? launch_fast_fwd<1, 16>(tm, a, p, st) : launch_fast_fwd<1, 64>(tm, a, p, st);
-  return p.rc == 16 ? launch_fast_fwd<2, 16>(tm, a, p, st) : launch_fast_fwd<2, 64>(tm, a, p, st);
+  if (d.S == 1) {
+    switch (p.rc) {
+      case 32: return launch_fast_fwd<1, 32>(tm, a, p, st);
+      case 96: return launch_fast_fwd<1, 96>(tm, a, p, st);
+      case 128: return launch_fast_fwd<1, 128>(tm, a, p, st);
+      default: return launch_fast_fwd<1, 64>(tm, a, p, st);
+    }
+  }
+  switch (p.rc) {
+    case 32: return launch_fast_fwd<2, 32>(tm, a, p, st);
+    case 96: return launch_fast_fwd<2, 96>(tm, a, p, st);
+    case 128: return launch_fast_fwd<2, 128>(tm, a, p, st);
+    default: return launch_fast_fwd<2, 64>(tm, a, p, st);
+  }
 }
 
-template <int RPT>
+template <int NHALF>
 static int launch_fast_gy(const CUtensorMap& tg, const CUtensorMap& tq, const FastGyArgs& a, const FastPlan& p, cudaStream_t st) {
-  const size_t smem = fast_gy_smem_bytes(a.O);
+  const size_t smem = fast_gy_smem_bytes(a.O, a.Lq);
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
-  auto k = fast_bwd_gy_kernel<RPT>;
+  auto k = fast_bwd_gy_kernel<NHALF>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKBwdPost, st);
@@ -780,35 +886,22 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
                   unsigned char* ws, const ConvDims& d, cudaStream_t st) {
   const FastPlan p = make_fast_plan(d);
   const size_t W = (size_t)d.B * d.Lout;
-  float* gout = reinterpret_cast<float*>(ws + p.off_gout);
   float* gpre = reinterpret_cast<float*>(ws + p.off_gpre);
   float* part1 = reinterpret_cast<float*>(ws + p.off_p1);
-  float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
   float* part3 = reinterpret_cast<float*>(ws + p.off_p3);
   alignas(64) CUtensorMap tm_gy, tm_qout, tm_x, tm_gx;
   if (int e = make_tmap_3d_f32(&tm_gy, gy, d.Lout, d.O, d.B, 32, 64, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
   if (int e = make_tmap_3d_f32(&tm_x, x, d.L, d.C, d.B, 32, 32, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
-  // 1) stream gy
+  // 1) stream gy (+ adjoint circuit on a dedicated warp)
   {
-    FastGyArgs a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, (d.O + 63) / 64};
-    const int rpt = (d.O + kGyThreads - 1) / kGyThreads;
-    int e = rpt == 1 ? launch_fast_gy<1>(tm_gy, tm_qout, a, p, st)
-          : rpt == 2 ? launch_fast_gy<2>(tm_gy, tm_qout, a, p, st)
-                     : launch_fast_gy<3>(tm_gy, tm_qout, a, p, st);
+    FastGyArgs a{w_post, pre_save, qwts, gpre, part1, d.B, d.O, d.Lout, p.LP, d.Lq, p.tiles_per_utt, p.num_tiles, p.PA1};
+    const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
+    int e = nhalf == 1 ? launch_fast_gy<1>(tm_gy, tm_qout, a, p, st)
+          : nhalf == 2 ? launch_fast_gy<2>(tm_gy, tm_qout, a, p, st)
+                       : launch_fast_gy<3>(tm_gy, tm_qout, a, p, st);
     if (e) return e;
-  }
-  // 2) adjoint circuit
-  {
-    FastAdjArgs a{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W};
-    const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)(FQ + d.Lq * FQ * 8) * (kThreads + 1)) * 4;
-    QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-      KernelTimer kt(kKBwdAdj, st);
-      fast_bwd_adj_kernel<<<p.gridAdj, kThreads, smem, st>>>(a);
-    }
-    QW_CUDA_OK(cudaGetLastError());
   }
   // 3) pre_conv^T
   {
@@ -822,9 +915,8 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   }
   // 4) finalize
   {
-    FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post,
-                  p.gridGy, p.PA1, p.gridAdj, p.PA2, p.gridPx, p.PB, d.C, d.O, d.Lq};
-    const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
+    FastFinArgs a{part1, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridPx, p.PB, d.C, d.O, d.Lq};
+    const int nblk = p.PA1 / 32 + p.PB / 32;
     {
       KernelTimer kt(kKBwdFinalize, st);
       fast_finalize_kernel<<<nblk, kFFThreads, 0, st>>>(a);
