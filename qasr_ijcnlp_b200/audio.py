@@ -1,0 +1,133 @@
+"""Log-mel front end on the GPU (host mirror of /root/reference/whisper/whisper/audio.py:65-157).
+
+Same public names and argument meaning as the vendored whisper module for this path:
+``pad_or_trim``, ``mel_filters``, ``log_mel_spectrogram`` and the hyper-parameter constants; the computation is
+one fused sm_100a kernel (+ a small in-place finish pass) behind ``qw_log_mel`` in ``include/qw.h``.  There is
+no CPU path and no torch.stft fallback.
+
+Differences that are deliberate and documented:
+  * a 2-D input ``(B, n_samples)`` is a BATCH: the ``max`` of audio.py:155 is taken per utterance (the reference
+    only ever passes one utterance);
+  * the mel filterbank is generated (``librosa.filters.mel`` defaults, as audio.py:96-103 says the asset was made)
+    rather than loaded from ``assets/mel_filters.npz``; it matches the asset to <= 1e-7 (tests/golden);
+  * file-path input (ffmpeg, audio.py:25-62) is out of scope: tensors / arrays only.
+"""
+from __future__ import annotations
+
+import ctypes
+from functools import lru_cache
+from typing import Optional, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+# audio.py:12-22
+SAMPLE_RATE = 16000
+N_FFT = 400
+HOP_LENGTH = 160
+CHUNK_LENGTH = 30
+N_SAMPLES = CHUNK_LENGTH * SAMPLE_RATE  # 480000
+N_FRAMES = N_SAMPLES // HOP_LENGTH  # 3000
+N_SAMPLES_PER_TOKEN = HOP_LENGTH * 2
+FRAMES_PER_SECOND = SAMPLE_RATE // HOP_LENGTH
+TOKENS_PER_SECOND = SAMPLE_RATE // N_SAMPLES_PER_TOKEN
+
+
+def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
+    """Right zero-pad or trim `axis` to `length` samples (audio.py:65-88); tensors stay on their device."""
+    if torch.is_tensor(array):
+        if array.shape[axis] > length:
+            array = array.index_select(dim=axis, index=torch.arange(length, device=array.device))
+        if array.shape[axis] < length:
+            pad = [(0, 0)] * array.ndim
+            pad[axis] = (0, length - array.shape[axis])
+            array = F.pad(array, [p for sizes in pad[::-1] for p in sizes])
+        return array
+    array = np.asarray(array)
+    if array.shape[axis] > length:
+        array = array.take(indices=range(length), axis=axis)
+    if array.shape[axis] < length:
+        pad = [(0, 0)] * array.ndim
+        pad[axis] = (0, length - array.shape[axis])
+        array = np.pad(array, pad)
+    return array
+
+
+def _slaney_hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    lin = 3.0 * f / 200.0
+    log_region = 15.0 + 27.0 * np.log(np.maximum(f, 1e-300) / 1000.0) / np.log(6.4)
+    return np.where(f >= 1000.0, log_region, lin)
+
+
+def _slaney_mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    return np.where(m >= 15.0, 1000.0 * np.exp(np.log(6.4) * (m - 15.0) / 27.0), 200.0 * m / 3.0)
+
+
+@lru_cache(maxsize=None)
+def _mel_filterbank_np(n_mels: int) -> np.ndarray:
+    """Slaney-scale, area-normalised triangular filters over the 201 rFFT bins of a 400-point frame at 16 kHz."""
+    centres_hz = np.linspace(0.0, SAMPLE_RATE / 2.0, N_FFT // 2 + 1)
+    edges_hz = _slaney_mel_to_hz(np.linspace(_slaney_hz_to_mel(0.0), _slaney_hz_to_mel(SAMPLE_RATE / 2.0), n_mels + 2))
+    widths = np.diff(edges_hz)
+    rising = (centres_hz[None, :] - edges_hz[:-2, None]) / widths[:-1, None]
+    falling = (edges_hz[2:, None] - centres_hz[None, :]) / widths[1:, None]
+    tri = np.clip(np.minimum(rising, falling), 0.0, None)
+    tri *= (2.0 / (edges_hz[2:] - edges_hz[:-2]))[:, None]
+    return tri.astype(np.float32)
+
+
+_FILTER_CACHE = {}
+
+
+def mel_filters(device, n_mels: int) -> torch.Tensor:
+    """(n_mels, 201) float32 filterbank on `device` (audio.py:91-107); cached per (device, n_mels)."""
+    if n_mels not in (80, 128):
+        raise AssertionError(f"Unsupported n_mels: {n_mels}")  # audio.py:103
+    key = (str(device), n_mels)
+    if key not in _FILTER_CACHE:
+        _FILTER_CACHE[key] = torch.from_numpy(_mel_filterbank_np(n_mels)).to(device).contiguous()
+    return _FILTER_CACHE[key]
+
+
+def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80, padding: int = 0,
+                        device: Optional[Union[str, torch.device]] = None) -> torch.Tensor:
+    """audio (n_samples,) or (B, n_samples) -> (n_mels, n_frames) or (B, n_mels, n_frames), n_frames = n_samples // 160.
+
+    Signature of audio.py:110-115 (minus the file-path form).  The tensor must end up on a CUDA device."""
+    if isinstance(audio, str):
+        raise TypeError("file-path input (ffmpeg) is outside this package's scope: pass samples")
+    if not torch.is_tensor(audio):
+        audio = torch.from_numpy(np.asarray(audio))
+    if device is not None:
+        audio = audio.to(device)
+    if padding > 0:
+        audio = F.pad(audio, (0, padding))
+    if not audio.is_cuda:
+        raise RuntimeError("log_mel_spectrogram (B200 build) has no CPU path: pass a CUDA tensor or device='cuda'")
+    if audio.dim() not in (1, 2):
+        raise ValueError(f"expected (n_samples,) or (batch, n_samples), got {tuple(audio.shape)}")
+    single = audio.dim() == 1
+    a = audio.reshape(1, -1) if single else audio
+    a = a.to(torch.float32).contiguous()
+    B, n = a.shape
+    if n % HOP_LENGTH:
+        # torch.stft yields 1 + n // 160 frames and the reference drops the last: the tail samples beyond the last
+        # full hop only ever feed frames through reflect padding.  Keep exact framing by handling whole hops only.
+        raise ValueError(f"n_samples={n} must be a multiple of {HOP_LENGTH} (use pad_or_trim)")
+    lib = _lib.load()
+    T = n // HOP_LENGTH
+    filt = mel_filters(a.device, n_mels)
+    mel = torch.empty(B, n_mels, T, device=a.device, dtype=torch.float32)
+    nbytes = lib.qw_log_mel_workspace_bytes(B, n, n_mels)
+    ws = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
+    with torch.cuda.device(a.device):
+        st = lib.qw_log_mel(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(filt.data_ptr()), ctypes.c_void_p(mel.data_ptr()),
+                            ctypes.c_void_p(ws.data_ptr()), nbytes, B, n, n_mels,
+                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "qw_log_mel")
+    return mel[0] if single else mel

@@ -1,0 +1,105 @@
+"""Batch-sharded data parallelism for the quantum stem.
+
+The reference has no distributed code at all (single process, `train_quantum_whisper.py:195-214`); `north_star`
+asks for the batch of utterances to be partitioned across the GPUs of one box: windows and utterances are
+independent, so forward / inference need NO collective, and a training step needs exactly one gradient
+all-reduce (NCCL over NVLink/NVSwitch; `gloo` in the CPU tests) over the trainable parameters
+(`freeze_non_quantum_layers` regime: 2 x QuantumConv1d = 9 440 floats + the task head).
+
+One process per GPU; this module only holds the plumbing (shard arithmetic, one flat gradient bucket,
+parameter broadcast).  The gradient partials of the quantum layers are already reduced to their final
+per-GPU value inside the backward kernels' finalize step, so the bucket is ready as soon as autograd returns.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of the utterances rank `rank` owns: contiguous, sizes differ by at most one, the first
+    `n_items % world` ranks get the extra item.  Integer arithmetic only."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Make every rank start from rank `src`'s parameters and buffers (one flat broadcast per dtype)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault((t.dtype, t.device), []).append(t)
+    for (_, _), ts in by_dtype.items():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for t in ts:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+
+class GradBucket:
+    """One flat fp32 buffer holding the gradients of the trainable parameters, all-reduced once per step.
+
+    `allreduce_mean()` packs `p.grad` (zeros for parameters that received none), issues a single
+    `all_reduce(SUM)`, scales by 1/world and points every `p.grad` at its slice of the bucket (so the optimizer
+    reads the reduced values with no copy back)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        for p in self.params:
+            if p.device != dev or p.dtype != dt:
+                raise ValueError("GradBucket needs all trainable parameters on one device with one dtype")
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    @property
+    def nbytes(self) -> int:
+        return self.numel * self.flat.element_size()
+
+    def pack(self, grads: Optional[Iterable[Optional[torch.Tensor]]] = None) -> None:
+        src = [p.grad for p in self.params] if grads is None else list(grads)
+        for v, g in zip(self.views, src):
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+
+    def allreduce_mean(self, grads: Optional[Iterable[Optional[torch.Tensor]]] = None, async_op: bool = False):
+        self.pack(grads)
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        work = None
+        if world > 1:
+            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+            if not async_op:
+                self.flat.mul_(1.0 / world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        if async_op and work is not None:
+            return _Pending(work, self.flat, world)
+        return None
+
+
+class _Pending:
+    def __init__(self, work, flat, world):
+        self.work, self.flat, self.world = work, flat, world
+
+    def wait(self):
+        self.work.wait()
+        self.flat.mul_(1.0 / self.world)

@@ -1,0 +1,119 @@
+"""Parity of the fused log-mel kernel (qw_log_mel through the C ABI / qasr_ijcnlp_b200.audio) with the fp64 oracle and
+with the golden outputs of the vendored whisper.log_mel_spectrogram (tests/golden/logmel_*.npz).
+
+Tolerance: the reference pins nothing tighter than `mel.max()-mel.min() <= 2` (whisper/tests/test_audio.py:8-19);
+SURVEY.md 8d asks <= 1e-4 abs on the (x+4)/4 scale.  Near the 1e-10 power floor a bin is the difference of large
+fp32 FFT terms, so a few bins of a loud frame move more; the bound used is 1e-4 on >= 99.9 % of the entries and
+2e-3 on all of them against the fp64 oracle (the vendored fp32 implementation itself differs from fp64 by that much),
+and the frame / sample indexing checks are exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, tight=1e-4, loose=2e-3, frac=0.999):
+    err = np.abs(np.asarray(got, dtype=np.float64) - ref)
+    assert err.max() <= loose, err.max()
+    assert (err <= tight).mean() >= frac, (err <= tight).mean()
+
+
+def test_short_clips_vs_golden_and_oracle(cuda, golden_dir):
+    from qasr_ijcnlp_b200 import audio as qa
+    g = np.load(os.path.join(golden_dir, "logmel_short.npz"))
+    for a, m, n in ((g["a1"], g["m1"], 80), (g["a2"], g["m2"], 80), (g["a1"], g["m1_128"], 128)):
+        got = qa.log_mel_spectrogram(torch.from_numpy(a), n_mels=n, device=cuda).cpu().numpy()
+        assert got.shape == m.shape and got.dtype == np.float32
+        _close(got, m.astype(np.float64))                      # vendored whisper output
+        _close(got, lo.log_mel_spectrogram(a, n_mels=n))       # fp64 oracle
+        assert got.max() - got.min() <= 2.0                    # whisper/tests/test_audio.py:17
+
+
+def test_30s_full_size_vs_golden(cuda, golden_dir):
+    from qasr_ijcnlp_b200 import audio as qa
+    g = np.load(os.path.join(golden_dir, "logmel_30s.npz"))
+    rs = np.random.RandomState(int(g["seed"]))
+    full = (0.1 * rs.standard_normal(480000)).astype(np.float32)
+    stride = int(g["stride"])
+    sc = qa.pad_or_trim(torch.from_numpy(full[:16000]))        # Speech-Commands-shaped: 1 s + zero padding
+    batch = torch.stack([torch.from_numpy(full), sc]).to(cuda)
+    mel = qa.log_mel_spectrogram(batch).cpu().numpy()
+    assert mel.shape == (2, 80, 3000)
+    _close(mel[0][:, ::stride], g["full_sub"].astype(np.float64))
+    _close(np.concatenate([mel[0][:, :4], mel[0][:, -4:]], axis=1), g["full_edges"].astype(np.float64))  # reflect edges
+    _close(mel[1][:, ::stride], g["sc_sub"].astype(np.float64))
+    for k, st in ((0, g["full_stats"]), (1, g["sc_stats"])):
+        assert abs(mel[k].min() - st[0]) <= 2e-4 and abs(mel[k].max() - st[1]) <= 2e-4 and abs(mel[k].mean() - st[2]) <= 2e-5
+    # batched call == per-utterance calls, bit for bit (max taken per utterance)
+    for k in range(2):
+        assert np.array_equal(mel[k], qa.log_mel_spectrogram(batch[k]).cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [1600, 5920, 16000, 160 * 33])
+def test_random_lengths_vs_oracle(cuda, n):
+    from qasr_ijcnlp_b200 import audio as qa
+    rs = np.random.RandomState(n)
+    a = (rs.standard_normal((3, n)) * np.array([[1.0], [0.01], [5.0]])).astype(np.float32)
+    got = qa.log_mel_spectrogram(torch.from_numpy(a).to(cuda)).cpu().numpy()
+    assert got.shape == (3, 80, n // 160)
+    _close(got, lo.log_mel_spectrogram(a))
+
+
+def test_frame_indexing_exact(cuda):
+    """A single unit impulse at sample p lights exactly the frames whose 400-tap window (after reflect padding) contains
+    p with a non-zero Hann weight: integer frame map == oracle's frame_sample_indices, incl. both reflected edges and
+    the dropped last frame (audio.py:149)."""
+    from qasr_ijcnlp_b200 import audio as qa
+    n = 160 * 70
+    T = n // 160
+    idx = lo.frame_sample_indices(n, T)              # (T, 400)
+    win = lo.hann_periodic()
+    ps = [0, 1, 37, 199, 200, 201, 5000, n - 201, n - 200, n - 41, n - 40, n - 2, n - 1]
+    a = np.zeros((len(ps), n), np.float32)
+    for r, p in enumerate(ps):
+        a[r, p] = 1.0
+    got = qa.log_mel_spectrogram(torch.from_numpy(a).to(cuda)).cpu().numpy()
+    for r, p in enumerate(ps):
+        hit = ((idx == p) & (win[None, :] > 1e-6)).any(axis=1)      # frames that see the impulse
+        floor = got[r].min()
+        lit = (got[r] > floor + 1e-6).any(axis=0)
+        # a frame seeing the impulse only through a ~0 Hann weight may sit on the floor; a frame not seeing it must
+        assert not (lit & ~((idx == p).any(axis=1))).any()
+        assert (lit | ~hit).all()
+    _close(got, lo.log_mel_spectrogram(a), tight=2e-4)
+
+
+def test_errors(cuda):
+    from qasr_ijcnlp_b200 import audio as qa
+    with pytest.raises(ValueError):
+        qa.log_mel_spectrogram(torch.zeros(1000, device=cuda))       # not a multiple of the hop
+    with pytest.raises(ValueError):
+        qa.log_mel_spectrogram(torch.zeros(1, 2, 1600, device=cuda))
+    with pytest.raises(RuntimeError):
+        qa.log_mel_spectrogram(torch.zeros(1600))                    # CPU tensor, no device: no CPU path
+    with pytest.raises(Exception):
+        qa.log_mel_spectrogram(torch.zeros(160, device=cuda))        # <= 200 samples: reflect padding undefined
+    # all-zero audio: every bin on the 1e-10 floor -> (-10 + 4) / 4 = -1.5 everywhere, like the reference
+    z = qa.log_mel_spectrogram(torch.zeros(3200, device=cuda))
+    assert torch.all(z == -1.5)
+
+
+def test_encoder_forward_config2_shape(cuda):
+    """BASELINE configs[1] shape: Speech-Commands clips -> log-mel -> quantum encoder -> 35-class head, on the GPU."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200 import _lib
+    from qasr_ijcnlp_b200 import audio as qa
+    torch.manual_seed(1)
+    model = qw.QuantumWhisperClassifier(qw.QuantumWhisper(qw.get_whisper_tiny_dims(), n_qubits=4), 35).to(cuda).eval()
+    audio = qa.pad_or_trim(0.1 * torch.randn(2, 16000), qa.N_SAMPLES).to(cuda)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        mel = qa.log_mel_spectrogram(audio)
+        logits = model(mel)
+    assert mel.shape == (2, 80, 3000) and logits.shape == (2, 35) and torch.isfinite(logits).all()
+    assert _lib.launch_count() - n0 == 2 + 2  # stft + finish, conv1 fwd, conv2 fwd

@@ -1,0 +1,248 @@
+"""The CPU oracle against every golden vector / known answer / identity available for the path.
+
+The reference holds NO test or golden vector for QuantumConv1d (its arithmetic lives in the un-vendored
+PennyLane), so the qconv restatement is pinned by: the KATs of SURVEY.md 8c, a second independently written
+dense-unitary oracle, the literal single-window loop, finite differences and the algebraic identities.
+The log-mel restatement and the encoder mirror ARE pinned by outputs of the vendored whisper package run in
+the build container (tests/golden/*.npz, generator tests/golden/make_golden.py).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_oracle as lo
+from oracle import qconv_oracle as qo
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "qconv_kat.json")) as fh:
+        return json.load(fh)
+
+
+# ------------------------------------------------------------------------------------------ circuit KATs
+def test_kat0_zero_weights(kat):
+    pre = torch.tensor([kat["pre"]], dtype=torch.float64)
+    out = qo.circuit_expvals(pre, torch.zeros(4, 3, dtype=torch.float64))[0].numpy()
+    assert np.abs(out - np.array(kat["kat0"]["out"])).max() <= 1e-14
+    p = np.array(kat["pre"]) ** 2
+    p /= p.sum()
+    assert abs(out[2] - (p[0] + p[1] - p[2] - p[3])) <= 1e-15
+    assert abs(out[3] - (p[0] - p[1] - p[2] + p[3])) <= 1e-15
+
+
+def test_kat1_forward_and_gradients(kat):
+    k = kat["kat1"]
+    pre = torch.tensor([kat["pre"]], dtype=torch.float64, requires_grad=True)
+    w = torch.tensor(k["quantum_weights"], dtype=torch.float64, requires_grad=True)
+    out = qo.circuit_expvals(pre, w)
+    assert np.abs(out.detach().numpy()[0] - np.array(k["out"])).max() <= 1e-11  # KAT printed to 12 digits
+    gp, gw = torch.autograd.grad(out, [pre, w], torch.tensor([k["cotangent"]], dtype=torch.float64))
+    assert np.abs(gp.numpy()[0] - np.array(k["grad_pre"])).max() <= 1e-11
+    assert np.abs(gw.numpy() - np.array(k["grad_quantum_weights"])).max() <= 1e-11
+    # the structural zeros are exact to rounding: d/d omega == 0, d/d phi == 0 on wires < q - ceil(log2 q)
+    assert np.abs(gw.numpy()[:, 2]).max() <= 1e-15
+    assert np.abs(gw.numpy()[:2, 0]).max() <= 1e-15
+    assert abs(out[0, 0].item() - np.cos(0.2)) <= 1e-15
+    assert abs(out[0, 1].item() - np.cos(0.2) * np.cos(0.5)) <= 1e-15
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("n_layers", [1, 2, 3])
+def test_dense_unitary_second_oracle(q, n_layers):
+    """Statevector restatement == x^T M_i x with the dense 2^q x 2^q unitary built by Kronecker products."""
+    g = torch.Generator().manual_seed(10 * q + n_layers)
+    pre = torch.randn(37, q, generator=g, dtype=torch.float64)
+    w = torch.randn(n_layers, q, 3, generator=g, dtype=torch.float64)
+    a = qo.circuit_expvals(pre, w).numpy()
+    b = qo.dense_unitary_expvals(pre.numpy(), w.numpy())
+    assert np.abs(a - b).max() <= 1e-14
+
+
+@pytest.mark.parametrize("q", [2, 4, 5])
+def test_single_window_literal_matches_vectorised(q):
+    g = torch.Generator().manual_seed(q)
+    pre = torch.randn(9, q, generator=g, dtype=torch.float64)
+    w = torch.randn(q, 3, generator=g, dtype=torch.float64)
+    vec = qo.circuit_expvals(pre, w)
+    for j in range(pre.shape[0]):
+        assert (qo.circuit_single_window(pre[j], w) - vec[j]).abs().max().item() <= 1e-14
+
+
+@pytest.mark.parametrize("q", [4, 6, 8])
+def test_identities(q):
+    """omega invariance, phi invariance on the product-state wires, scale invariance, prod-cos channels."""
+    g = torch.Generator().manual_seed(q)
+    pre = torch.randn(21, q, generator=g, dtype=torch.float64)
+    w = torch.randn(q, 3, generator=g, dtype=torch.float64)
+    out = qo.circuit_expvals(pre, w)
+    m = int(np.ceil(np.log2(q)))
+    w2 = w.clone()
+    w2[:, 2] += torch.randn(q, generator=g, dtype=torch.float64)
+    w2[: q - m, 0] += torch.randn(q - m, generator=g, dtype=torch.float64)
+    assert (qo.circuit_expvals(pre, w2) - out).abs().max().item() <= 1e-14
+    assert (qo.circuit_expvals(-2.5 * pre, w) - out).abs().max().item() <= 1e-14
+    prod = torch.cumprod(torch.cos(w[:, 1]), 0)
+    for i in range(q - m):
+        assert (out[:, i] - prod[i]).abs().max().item() <= 1e-14
+    # x . d out / d x == 0 (scale invariance of the normalised embedding)
+    p = pre.clone().requires_grad_(True)
+    gp, = torch.autograd.grad(qo.circuit_expvals(p, w), [p], torch.randn(21, q, generator=g, dtype=torch.float64))
+    assert (gp * pre).sum(dim=1).abs().max().item() <= 1e-13
+
+
+@pytest.mark.parametrize("embedding", [qo.EMB_AMPLITUDE, qo.EMB_ANGLE])
+def test_gradients_by_finite_differences(embedding):
+    g = torch.Generator().manual_seed(3)
+    pre = torch.randn(3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(2, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: qo.circuit_expvals(a, b, embedding), (pre, w), eps=1e-6, atol=1e-7)
+
+
+def test_angle_embedding_closed_form():
+    """Angle mode, zero trainable weights, 1 wire: RZ(a) RY(a)|0> -> <Z> = cos(a)."""
+    a = torch.linspace(-3, 3, 13, dtype=torch.float64)[:, None]
+    out = qo.circuit_expvals(a, torch.zeros(1, 3, dtype=torch.float64), qo.EMB_ANGLE)
+    assert (out - torch.cos(a)).abs().max().item() <= 1e-15
+
+
+# ------------------------------------------------------------------------------------------ windowing (integer)
+@pytest.mark.parametrize("L,K,S,P", [(3000, 3, 1, 1), (3000, 3, 2, 1), (100, 5, 3, 2), (7, 7, 1, 0), (10, 4, 2, 3), (5, 1, 1, 0)])
+def test_window_indexing_equals_unfold(L, K, S, P):
+    C = 3
+    x = torch.arange(1, 2 * C * L + 1, dtype=torch.float64).reshape(2, C, L)  # every entry distinct and non-zero
+    win = qo.extract_windows(x, K, S, P)
+    ref = torch.nn.functional.unfold(x[:, :, None, :], (1, K), padding=(0, P), stride=(1, S)).permute(0, 2, 1)
+    assert torch.equal(win, ref)
+    Lo = qo.out_length(L, K, S, P)
+    assert win.shape == (2, Lo, C * K)
+    idx = qo.window_indices(L, K, S, P)
+    assert idx.shape == (Lo, K)
+    for i in (0, Lo // 2, Lo - 1):
+        for k in range(K):
+            col = i * S - P + k
+            want = x[0, 1, col].item() if 0 <= col < L else 0.0
+            assert win[0, i, 1 * K + k].item() == want  # feature index f = c*K + k
+            assert idx[i, k] == (col if 0 <= col < L else -1)
+
+
+def test_out_length_matches_reference_formula():
+    for L in (1, 2, 3, 10, 3000):
+        for K in (1, 2, 3, 5):
+            for S in (1, 2, 3):
+                for P in (0, 1, 2):
+                    if L + 2 * P >= K:
+                        assert qo.out_length(L, K, S, P) == (L + 2 * P - K) // S + 1
+                        assert qo.out_length(L, K, S, P) == torch.nn.functional.conv1d(
+                            torch.zeros(1, 1, L), torch.zeros(1, 1, K), stride=S, padding=P).shape[-1]
+
+
+# ------------------------------------------------------------------------------------------ the layer
+def test_pre_conv_is_a_conv1d():
+    """pre_conv over flattened windows == Conv1d with weight.view(q, C, K)."""
+    C, O, K, S, P, q = 6, 10, 3, 2, 1, 4
+    params = qo.make_params(C, O, K, q, seed=4)
+    x = torch.randn(2, C, 41, dtype=torch.float64)
+    _, pre, _ = qo.qconv1d_forward(x, *params, K=K, S=S, P=P, return_intermediates=True)
+    ref = torch.nn.functional.conv1d(x, params[0].view(q, C, K), params[1], stride=S, padding=P).permute(0, 2, 1)
+    assert (pre - ref).abs().max().item() <= 1e-14
+
+
+@pytest.mark.parametrize("geom", [(2, 5, 23, 3, 1, 1, 7, 4), (1, 4, 20, 3, 2, 1, 6, 4), (2, 3, 17, 5, 3, 2, 4, 2)])
+def test_literal_loop_equals_vectorised(geom):
+    B, C, L, K, S, P, O, q = geom
+    params = qo.make_params(C, O, K, q, seed=1)
+    x = torch.randn(B, C, L, dtype=torch.float64)
+    a = qo.qconv1d_forward(x, *params, K=K, S=S, P=P)
+    b = qo.qconv1d_literal(x, *params, K=K, S=S, P=P)
+    assert a.shape == (B, O, qo.out_length(L, K, S, P))
+    assert (a - b).abs().max().item() <= 1e-13
+
+
+def test_layer_gradcheck():
+    C, O, K, S, P, q = 3, 4, 3, 2, 1, 3
+    params = [p.requires_grad_(True) for p in qo.make_params(C, O, K, q, seed=2)]
+    x = torch.randn(1, C, 9, dtype=torch.float64, requires_grad=True)
+    f = lambda x_, *ps: qo.qconv1d_forward(x_, *ps, K=K, S=S, P=P)
+    assert torch.autograd.gradcheck(f, (x, *params), eps=1e-6, atol=1e-7)
+
+
+def test_fp32_cast_point():
+    """cast_fp32 rounds the readout exactly where quantum_whisper.py:122 calls .float()."""
+    params = qo.make_params(4, 5, 3, 4, seed=0)
+    x = torch.randn(1, 4, 12, dtype=torch.float64)
+    y, _, qout = qo.qconv1d_forward(x, *params, K=3, S=1, P=1, return_intermediates=True)
+    y32 = qo.qconv1d_forward(x, *params, K=3, S=1, P=1, cast_fp32=True)
+    want = (qout.float().double() @ params[3].T + params[4]).permute(0, 2, 1)
+    assert torch.equal(y32, want)
+    assert (y - y32).abs().max().item() <= 1e-6
+
+
+def test_zero_window_is_nan_like_the_reference():
+    """quantum_whisper.py:74 normalises without a guard: an all-zero pre vector gives NaN."""
+    out = qo.circuit_expvals(torch.zeros(1, 4, dtype=torch.float64), torch.zeros(4, 3, dtype=torch.float64))
+    assert torch.isnan(out).all()
+
+
+# ------------------------------------------------------------------------------------------ log-mel (pinned by vendored whisper)
+def test_mel_filterbank_matches_reference_asset(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "mel_filters_ref.npz"))
+    for n in (80, 128):
+        fb = lo.mel_filterbank(n)
+        assert fb.shape == (n, 201) and fb.dtype == np.float32
+        dense = np.zeros((n, 201), dtype=np.float32)
+        dense[ref[f"rows_{n}"].astype(int), ref[f"cols_{n}"].astype(int)] = ref[f"vals_{n}"]
+        assert np.abs(fb - dense).max() <= 1e-7
+        assert np.count_nonzero(dense) == len(ref[f"vals_{n}"])
+
+
+def test_logmel_short_clips_match_vendored_whisper(golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_short.npz"))
+    for a, m, n in ((g["a1"], g["m1"], 80), (g["a2"], g["m2"], 80), (g["a1"], g["m1_128"], 128)):
+        out = lo.log_mel_spectrogram(a, n_mels=n)
+        assert out.shape == m.shape == (n, len(a) // 160)
+        # the vendored implementation computes in fp32 (torch.stft); on the (x+4)/4 scale a power of 1e-10 moves
+        # by 0.1 per decade, so fp32 rounding of near-floor bins dominates: 2e-4 abs, and 1e-5 on the mean
+        assert np.abs(out - m).max() <= 2e-4
+        assert abs(out.mean() - m.mean()) <= 1e-5
+
+
+def test_logmel_30s_matches_vendored_whisper(golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_30s.npz"))
+    rs = np.random.RandomState(int(g["seed"]))
+    full = (0.1 * rs.standard_normal(480000)).astype(np.float32)
+    stride = int(g["stride"])
+    mf = lo.log_mel_spectrogram(full)
+    assert mf.shape == (80, 3000)
+    assert np.abs(mf[:, ::stride] - g["full_sub"]).max() <= 2e-4
+    assert np.abs(np.concatenate([mf[:, :4], mf[:, -4:]], axis=1) - g["full_edges"]).max() <= 2e-4  # reflect padding
+    st = g["full_stats"]
+    assert abs(mf.min() - st[0]) <= 2e-4 and abs(mf.max() - st[1]) <= 2e-4 and abs(mf.mean() - st[2]) <= 1e-5
+    # Speech-Commands-shaped: 1 s of signal zero-padded by pad_or_trim; the silent tail sits on the max-8 floor
+    sc = lo.pad_or_trim(full[:16000])
+    assert sc.shape == (480000,) and not sc[16000:].any()
+    ms = lo.log_mel_spectrogram(sc)
+    assert np.abs(ms[:, ::stride] - g["sc_sub"]).max() <= 2e-4
+    assert abs(ms.min() - g["sc_stats"][0]) <= 2e-4 and abs(ms.max() - g["sc_stats"][1]) <= 2e-4
+
+
+def test_logmel_frame_indexing_is_reflect_padding():
+    """Integer map frame/tap -> sample == torch.stft(center=True, pad_mode='reflect') framing, last frame dropped."""
+    n = 1600
+    idx = lo.frame_sample_indices(n, n // 160)
+    x = torch.arange(n, dtype=torch.float64)
+    padded = torch.nn.functional.pad(x[None, None], (200, 200), mode="reflect")[0, 0]
+    frames = padded.unfold(0, 400, 160)  # n//160 + 1 frames
+    assert frames.shape[0] == n // 160 + 1
+    assert np.array_equal(idx, frames[: n // 160].numpy().astype(np.int64))
+
+
+def test_logmel_batched_max_is_per_utterance():
+    rs = np.random.RandomState(0)
+    a = np.stack([0.5 * rs.standard_normal(3200), 1e-3 * rs.standard_normal(3200)])
+    both = lo.log_mel_spectrogram(a)
+    assert np.array_equal(both[0], lo.log_mel_spectrogram(a[0]))
+    assert np.array_equal(both[1], lo.log_mel_spectrogram(a[1]))
