@@ -37,12 +37,14 @@ def _nvcc() -> str:
 def _units():
     """(object name, source, extra flags)"""
     units = [("qw_api.o", "qw_api.cu", []), ("qw_conv1d.o", "qw_conv1d.cu", []), ("qw_logmel.o", "qw_logmel.cu", []),
-             ("qw_conv1d_fast.o", "qw_conv1d_fast.cu", [])]
+             ("qw_conv1d_fast.o", "qw_conv1d_fast.cu", []), ("qw_conv1d_general.o", "qw_conv1d_general.cu", [])]
     for tname, t in (("f32", "float"), ("f64", "double")):
         for q in (1, 2, 3, 4):
             units.append((f"qw_conv1d_inst_{tname}_q{q}.o", "qw_conv1d_inst.cu", [f"-DQW_T={t}", f"-DQW_Q={q}"]))
-    if os.path.exists(os.path.join(CSRC, "qw_circuit_warp.cu")):
-        units.append(("qw_circuit_warp.o", "qw_circuit_warp.cu", []))
+    units.append(("qw_circuit_warp.o", "qw_circuit_warp.cu", []))
+    for tname, t in (("f32", "float"), ("f64", "double")):
+        for q in range(1, 13):
+            units.append((f"qw_circuit_warp_inst_{tname}_q{q}.o", "qw_circuit_warp_inst.cu", [f"-DQW_T={t}", f"-DQW_Q={q}"]))
     return units
 
 

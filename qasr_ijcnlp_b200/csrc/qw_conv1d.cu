@@ -3,8 +3,20 @@
 
 #include "../../include/qw.h"
 #include "qw_conv1d_plan.cuh"
+#include "qw_circuit_warp_host.h"
 
 namespace qw {
+
+namespace gen {  // qw_conv1d_general.cu: n_qubits > 4 and / or angle embedding
+size_t general_workspace_bytes(const ConvDims& d, int elem);
+template <typename T>
+int general_forward(const T* x, const T* w_pre, const T* b_pre, const T* qwts, const T* w_post, const T* b_post, T* y, T* pre_save,
+                    const ConvDims& d, cudaStream_t st);
+template <typename T>
+int general_backward(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* qwts, const T* w_post, T* gx, T* gw_pre,
+                     T* gb_pre, T* gqw, T* gw_post, T* gb_post, unsigned char* ws, size_t ws_bytes, const ConvDims& d, cudaStream_t st);
+}  // namespace gen
+static bool is_general(const ConvDims& d) { return d.Q > 4 || d.emb != kEmbAmplitude; }
 
 static std::mutex g_mu;
 static int g_num_sms = 0;
@@ -60,9 +72,9 @@ static int check_dims(ConvDims& d) {
   QW_CHECK_ARG(d.L + 2 * d.P >= d.K, -1, "kernel_size %d larger than padded length %d", d.K, d.L + 2 * d.P);
   d.Lout = (d.L + 2 * d.P - d.K) / d.S + 1;
   QW_CHECK_ARG(d.Q >= 1 && d.Q <= (long long)d.C * d.K, -1, "n_qubits=%d must be in [1, C*K=%d]", d.Q, d.C * d.K);
-  QW_CHECK_ARG(d.Q <= 4, -2, "fused QuantumConv1d kernels support n_qubits <= 4 (got %d)", d.Q);
+  QW_CHECK_ARG(d.Q <= 12, -2, "QuantumConv1d supports n_qubits <= 12 (got %d)", d.Q);
   QW_CHECK_ARG(d.Lq >= 1 && d.Lq <= 8, -2, "n_layers=%d must be in [1,8]", d.Lq);
-  QW_CHECK_ARG(d.emb == kEmbAmplitude, -2, "embedding=%d not supported by the fused kernels (amplitude only)", d.emb);
+  QW_CHECK_ARG(d.emb == kEmbAmplitude || d.emb == kEmbAngle, -2, "embedding=%d is neither amplitude (0) nor angle (1)", d.emb);
   QW_CHECK_ARG((long long)d.B * d.C * d.L < (1LL << 40) && (long long)d.B * d.O * d.Lout < (1LL << 40), -1, "tensor too large");
   return 0;
 }
@@ -73,6 +85,7 @@ static int conv1d_forward_impl(const T* x, const T* w_pre, const T* b_pre, const
   QW_CHECK_ARG(x && w_pre && b_pre && qwts && w_post && b_post && y, -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  if (is_general(d)) return gen::general_forward<T>(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, st);
   if constexpr (sizeof(T) == 4) {
     if (fast_eligible(d, x, y, pre_save, true)) return fast_forward(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, st);
   }
@@ -93,10 +106,12 @@ static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, cons
   QW_CHECK_ARG(gy && x && pre_save && w_pre && qwts && w_post && gw_pre && gb_pre && gqw && gw_post && gb_post && workspace,
                -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
-  QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
   QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = (unsigned char*)workspace;
+  if (is_general(d))
+    return gen::general_backward<T>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, ws_bytes, d, st);
+  QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
   if constexpr (sizeof(T) == 4) {
     if (fast_eligible(d, x, gy, gx, false) && (((uintptr_t)pre_save) & 15) == 0) {
       const FastPlan fp = make_fast_plan(d);
@@ -125,11 +140,12 @@ static int circ_PA(int q, int Lq) { return (int)align_up((size_t)Lq * q * 8, 32)
 template <typename T>
 static int circuit_forward_impl(const T* pre, const T* qwts, T* out, long long W, int q, int Lq, int emb, void* stream) {
   QW_CHECK_ARG(pre && qwts && out && W > 0, -1, "null pointer or empty batch");
-  QW_CHECK_ARG(q >= 1 && q <= 4, -2, "circuit kernels support n_qubits in [1,4] (got %d)", q);
+  QW_CHECK_ARG(q >= 1 && q <= 12, -2, "circuit kernels support n_qubits in [1,12] (got %d)", q);
   QW_CHECK_ARG(Lq >= 1 && Lq <= 8, -2, "n_layers=%d must be in [1,8]", Lq);
-  QW_CHECK_ARG(emb == kEmbAmplitude, -2, "embedding=%d not supported", emb);
-  CircArgs<T> a{pre, qwts, nullptr, out, nullptr, nullptr, W, q, Lq, 0};
+  QW_CHECK_ARG(emb == kEmbAmplitude || emb == kEmbAngle, -2, "embedding=%d not supported", emb);
   cudaStream_t st = (cudaStream_t)stream;
+  if (q > 4 || emb != kEmbAmplitude) return wc::wcirc_forward<T>(pre, qwts, out, W, q, Lq, emb, st);
+  CircArgs<T> a{pre, qwts, nullptr, out, nullptr, nullptr, W, q, Lq, 0};
   const int grid = circ_grid(W);
   switch (q) {
     case 1: return circ_fwd_tq<T, 1>(a, grid, st);
@@ -143,13 +159,17 @@ template <typename T>
 static int circuit_backward_impl(const T* pre, const T* qwts, const T* gout, T* gpre, T* gqw, void* workspace, size_t ws_bytes,
                                  long long W, int q, int Lq, int emb, void* stream) {
   QW_CHECK_ARG(pre && qwts && gout && gpre && gqw && workspace && W > 0, -1, "null pointer or empty batch");
-  QW_CHECK_ARG(q >= 1 && q <= 4, -2, "circuit kernels support n_qubits in [1,4] (got %d)", q);
+  QW_CHECK_ARG(q >= 1 && q <= 12, -2, "circuit kernels support n_qubits in [1,12] (got %d)", q);
   QW_CHECK_ARG(Lq >= 1 && Lq <= 8, -2, "n_layers=%d must be in [1,8]", Lq);
-  QW_CHECK_ARG(emb == kEmbAmplitude, -2, "embedding=%d not supported", emb);
+  QW_CHECK_ARG(emb == kEmbAmplitude || emb == kEmbAngle, -2, "embedding=%d not supported", emb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q > 4 || emb != kEmbAmplitude) {
+    QW_CHECK_ARG(ws_bytes >= wc::wcirc_workspace_bytes(W, q, Lq, (int)sizeof(T)), -3, "workspace too small");
+    return wc::wcirc_backward<T>(pre, qwts, gout, gpre, gqw, workspace, W, q, Lq, emb, st);
+  }
   const int grid = circ_grid(W), PA = circ_PA(q, Lq);
   QW_CHECK_ARG(ws_bytes >= (size_t)grid * PA * sizeof(T), -3, "workspace too small");
   CircArgs<T> a{pre, qwts, gout, nullptr, gpre, (T*)workspace, W, q, Lq, PA};
-  cudaStream_t st = (cudaStream_t)stream;
   int e = 0;
   switch (q) {
     case 1: e = circ_bwd_tq<T, 1>(a, grid, st); break;
@@ -191,11 +211,17 @@ int qw_conv1d_forward_f64(const double* x, const double* w_pre, const double* b_
 size_t qw_conv1d_workspace_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int elem_size) {
   ConvDims d{B, C, L, K, S, P, O, q, n_layers, 0, 0};
   if (qw::check_dims(d)) return 0;
+  if (d.Q > 4) return qw::gen::general_workspace_bytes(d, elem_size == 8 ? 8 : 4);
+  const size_t general = qw::gen::general_workspace_bytes(d, elem_size == 8 ? 8 : 4);  // angle embedding is chosen per call
   const qw::Plan p = qw::make_plan(d);
-  if (elem_size == 8) return qw::ws_layout<double>(d, p).total;
+  if (elem_size == 8) {
+    const size_t g64 = qw::ws_layout<double>(d, p).total;
+    return g64 > general ? g64 : general;
+  }
   const size_t generic = qw::ws_layout<float>(d, p).total;
   const size_t fast = qw::make_fast_plan(d).ws_bytes;
-  return generic > fast ? generic : fast;
+  const size_t m = generic > fast ? generic : fast;
+  return m > general ? m : general;
 }
 
 int qw_conv1d_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
@@ -216,8 +242,11 @@ int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_
 }
 
 size_t qw_circuit_workspace_bytes(long long W, int q, int n_layers, int elem_size) {
-  if (W <= 0 || q < 1 || n_layers < 1) return 0;
-  return (size_t)qw::circ_grid(W) * qw::circ_PA(q, n_layers) * (size_t)(elem_size == 8 ? 8 : 4);
+  if (W <= 0 || q < 1 || q > 12 || n_layers < 1) return 0;
+  const int es = elem_size == 8 ? 8 : 4;
+  const size_t warp = qw::wc::wcirc_workspace_bytes(W, q, n_layers, es);
+  const size_t thread = q <= 4 ? (size_t)qw::circ_grid(W) * qw::circ_PA(q, n_layers) * (size_t)es : 0;
+  return warp > thread ? warp : thread;
 }
 int qw_circuit_forward(const float* pre, const float* qwts, float* out, long long W, int q, int n_layers, int embedding,
                        void* stream) {

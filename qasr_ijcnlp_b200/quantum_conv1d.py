@@ -47,7 +47,8 @@ class _QuantumConv1dFn(torch.autograd.Function):
         params = [t.contiguous() for t in (w_pre, b_pre, qw, w_post, b_post)]
         y = torch.empty(B, O, Lout, device=x.device, dtype=x.dtype)
         need_bwd = any(ctx.needs_input_grad[:6])
-        pre_save = torch.empty(2, B * Lout, q, device=x.device, dtype=x.dtype) if need_bwd else None
+        general = q > 4 or emb != 0  # composed path: pre_save doubles as the scratch between its kernels
+        pre_save = torch.empty(2, B * Lout, q, device=x.device, dtype=x.dtype) if (need_bwd or general) else None
         fn = lib.qw_conv1d_forward_f64 if f64 else lib.qw_conv1d_forward
         with torch.cuda.device(x.device):
             st = fn(_ptr(x), *[_ptr(p) for p in params], _ptr(y), _ptr(pre_save),
