@@ -1,16 +1,21 @@
 // Fused log-mel front end: replaces whisper.log_mel_spectrogram (/root/reference/whisper/whisper/audio.py:110-157),
 // batched, with the max of :155 taken per utterance (the reference always passes one utterance).
 //
+//   logmel_prep_kernel   one CTA: support [lo, hi) of every mel row + the non-zero filter values compacted (whisper's
+//                        80 x 201 bank has 391 non-zeros) into the workspace, so the streaming CTAs stage ~3 KB instead
+//                        of scanning 64 KB each.
 //   logmel_stft_kernel   reflect-padded framing (bit-exact torch.stft(center=True) frame map) -> Hann -> 400-point
 //                        real FFT -> power -> mel filterbank -> log10(max(., 1e-10)) -> mel (B, n_mels, T) + per-
 //                        utterance running max (one atomic per warp per tile).
 //   logmel_finish_kernel max(., max_b - 8) ; (. + 4) / 4, in place (the tensor was just written: L2-resident).
 //
-// Layout: one STFT frame per LANE, a tile = 32 consecutive frames of one utterance per CTA iteration, the G warps
-// of the CTA split the butterflies / mel rows of those 32 frames.  Shared memory per CTA: the tile's audio span
-// (34 hops at pitch 161 floats -> conflict-free frame-strided reads) + a 400 x 32 float work array indexed
-// [slot][lane] (every access is one 128-byte row) = 73 KB -> 3 CTAs per SM.  HBM traffic is the algorithmic
-// minimum: audio read once (hop overlap is served from shared memory), mel written once by 128-byte rows.
+// Layout: one STFT frame per LANE, a tile = 32 consecutive frames of one utterance per CTA iteration, the G warps of
+// the CTA split the butterflies / mel rows of those 32 frames.  Shared memory per CTA: the tile's audio span (5 360
+// samples, skewed by one float per 32 so frame-strided reads are conflict-free) + a 400 x 32 float work array indexed
+// [slot][lane] (every access is one 128-byte row) = 76 KB.  The NEXT tile's audio is fetched with cp.async right
+// after pass A has consumed the current one, so its HBM latency hides under pass B / untangle / mel.  HBM traffic is
+// the algorithmic minimum: audio read once (hop overlap served from shared memory), mel written once by 128-byte rows.
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/qw.h"
@@ -22,26 +27,74 @@ namespace lm {
 
 constexpr int kFrames = 32;                                   // frames per tile == lanes
 constexpr int kSpan = (kFrames - 1) * kHop + kNfft;           // 5360 samples feed one tile
-constexpr int kHops = (kSpan + kHop - 1) / kHop;              // 34
-constexpr int kAudFloats = kHops * kHopPitch;                 // 5474
+constexpr int kAudFloats = ((kSpan + (kSpan >> 5) + 3) / 4) * 4;  // 5528 (skewed)
 constexpr int kWorkFloats = kNfft * kFrames;                  // 12800
 constexpr int kMaxMels = 256;
+constexpr int kMaxNnz = 1024;                                 // compact filter values staged in shared memory
+
+// workspace: [umax: B floats, 256-aligned][meta: lo[256] hi[256] off[256] total pad -> 4 KB][vals: n_mels * 201 floats]
+struct Meta {
+  int lo[kMaxMels], hi[kMaxMels], off[kMaxMels];
+  int total, pad[255];
+};
 
 struct Args {
   const float* audio;    // (B, n)
   const float* filters;  // (n_mels, 201)
   float* mel;            // (B, n_mels, T)
   float* umax;           // (B) running max, initialised to 0xffffffff ("-inf" for the mixed int/uint atomics)
+  const Meta* meta;
+  const float* vals;
   int B, n, T, n_mels, tiles_per_utt, num_tiles;
 };
+
+__global__ void __launch_bounds__(1024) logmel_prep_kernel(const float* __restrict__ filters, int n_mels, Meta* meta, float* vals) {
+  __shared__ int slo[kMaxMels], shi[kMaxMels], soff[kMaxMels + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m = warp; m < n_mels; m += 32) {
+    int lo = kNfreq, hi = 0;
+    for (int k0 = 0; k0 < kNfreq; k0 += 32) {
+      const int k = k0 + lane;
+      const bool nz = k < kNfreq && filters[m * kNfreq + k] != 0.f;
+      const unsigned bal = __ballot_sync(0xffffffffu, nz);
+      if (bal) {
+        const int first = k0 + __ffs(bal) - 1, last = k0 + 32 - __clz(bal);
+        lo = first < lo ? first : lo;
+        hi = last > hi ? last : hi;
+      }
+    }
+    if (lane == 0) {
+      slo[m] = lo < hi ? lo : 0;
+      shi[m] = lo < hi ? hi : 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int m = 0; m < n_mels; ++m) {
+      soff[m] = o;
+      o += shi[m] - slo[m];
+    }
+    soff[n_mels] = o;
+    meta->total = o;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    meta->lo[m] = slo[m];
+    meta->hi[m] = shi[m];
+    meta->off[m] = soff[m];
+  }
+  for (int m = warp; m < n_mels; m += 32)
+    for (int k = slo[m] + lane; k < shi[m]; k += 32) vals[soff[m] + k - slo[m]] = filters[m * kNfreq + k];
+}
 
 struct SmemCol {
   float* base;  // &work[lane]
   __device__ __forceinline__ float& at(int e) { return base[e * kFrames]; }
 };
 struct SmemAud {
-  const float* base;  // &aud[lane * 161]: hop h of the tile starts at aud[h * 161]
-  __device__ __forceinline__ float tap(int j) const { return base[(j / kHop) * kHopPitch + (j % kHop)]; }
+  const float* base;  // &aud[165 * lane]
+  __device__ __forceinline__ float tap(int j) const { return base[j + (j >> 5)]; }
 };
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
@@ -51,52 +104,64 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 template <int G>
 __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
   extern __shared__ __align__(16) float smem[];
-  float* aud = smem;
-  float* work = smem + kAudFloats + 2;  // +2 keeps `work` 16-byte aligned (5476 floats)
-  int* mlo = reinterpret_cast<int*>(work + kWorkFloats);
+  float* aud = smem;                       // [kAudFloats] skewed tile samples
+  float* work = smem + kAudFloats;         // [400][32]
+  float* fvals = work + kWorkFloats;       // [kMaxNnz]
+  int* mlo = reinterpret_cast<int*>(fvals + kMaxNnz);
   int* mhi = mlo + kMaxMels;
+  int* moff = mhi + kMaxMels;
   const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  constexpr int NT = 32 * G;
 
-  // support [lo, hi) of every mel row (first / last non-zero), found once per CTA: warp per row, ballot scan
-  for (int m = g; m < a.n_mels; m += G) {
-    int lo = kNfreq, hi = 0;
-    for (int k0 = 0; k0 < kNfreq; k0 += 32) {
-      const int k = k0 + lane;
-      const bool nz = k < kNfreq && a.filters[m * kNfreq + k] != 0.f;
-      const unsigned bal = __ballot_sync(0xffffffffu, nz);
-      if (bal) {
-        const int first = k0 + __ffs(bal) - 1, last = k0 + 32 - __clz(bal);
-        lo = first < lo ? first : lo;
-        hi = last > hi ? last : hi;
-      }
-    }
-    if (lane == 0) {
-      mlo[m] = lo < hi ? lo : 0;
-      mhi[m] = lo < hi ? hi : 0;
-    }
-  }
-
-  SmemCol col{work + lane};
-  SmemAud au{aud + lane * kHopPitch};
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  // asynchronous fill of the audio staging buffer for one tile (reflect padding resolved per sample)
+  auto fill = [&](int tile) {
     const int b = tile / a.tiles_per_utt;
     const int t0 = (tile - b * a.tiles_per_utt) * kFrames;
     const float* src = a.audio + (size_t)b * a.n;
     const int p0 = t0 * kHop - kNfft / 2;  // original index of the tile's first sample (before reflection)
-    __syncthreads();                       // previous tile's readers are done with aud / work
-    for (int s = tid; s < kSpan; s += 32 * G) {
+#pragma unroll 4
+    for (int s = tid; s < kSpan; s += NT) {
       int p = p0 + s;
-      p = p < 0 ? -p : p;                          // reflect (no edge repeat), torch.stft center=True
+      p = p < 0 ? -p : p;                     // reflect (no edge repeat), torch.stft center=True
       p = p >= a.n ? 2 * (a.n - 1) - p : p;
-      const float v = (p >= 0 && p < a.n) ? __ldg(src + p) : 0.f;  // frames >= T of a ragged last tile read zeros
-      aud[s + s / kHop] = v;                       // hop-major, pitch 161
+      float* dst = aud + s + (s >> 5);
+      if (p >= 0 && p < a.n) cp_async4(dst, src + p);
+      else *dst = 0.f;                        // frames >= T of a ragged last tile read zeros
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+
+  if ((int)blockIdx.x < a.num_tiles) fill(blockIdx.x);
+  const int nnz = a.meta->total;
+  const bool cached = nnz <= kMaxNnz;
+  for (int m = tid; m < a.n_mels; m += NT) {
+    mlo[m] = a.meta->lo[m];
+    mhi[m] = a.meta->hi[m];
+    moff[m] = a.meta->off[m];
+  }
+  if (cached)
+    for (int e = tid; e < nnz; e += NT) fvals[e] = a.vals[e];
+
+  SmemCol col{work + lane};
+  SmemAud au{aud + kLanePitch * lane};
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int b = tile / a.tiles_per_utt;
+    const int t0 = (tile - b * a.tiles_per_utt) * kFrames;
+    cp_async_wait_all();
+    __syncthreads();  // audio of this tile visible; previous tile's mel readers are done with `work`
     pass_a(g, G, au, col);
     __syncthreads();
+    if (tile + (int)gridDim.x < a.num_tiles) fill(tile + gridDim.x);  // overlaps pass B / untangle / mel
     pass_b(g, G, col);
     __syncthreads();
     untangle_power(g, G, col);
@@ -105,10 +170,19 @@ __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
     float vmax = -INFINITY;
     for (int m = g; m < a.n_mels; m += G) {
       const int lo = mlo[m], hi = mhi[m];
-      const float* frow = a.filters + m * kNfreq;
-      float acc = 0.f;
-      for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(frow + k), work[pslot(k) * kFrames + lane], acc);
-      const float v = log10f(fmaxf(acc, 1e-10f));  // audio.py:154
+      const float* fv = (cached ? fvals : a.vals) + moff[m];
+      const bool top = hi == kNfreq;          // P[200] lives at float slot 1, everything else at float 2k
+      const int n = (top ? 200 : hi) - lo;
+      const float* pw = work + lane + 2 * kFrames * lo;
+      float acc0 = 0.f, acc1 = 0.f;
+      int e = 0;
+      for (; e + 1 < n; e += 2) {
+        acc0 = fmaf(fv[e], pw[e * 2 * kFrames], acc0);
+        acc1 = fmaf(fv[e + 1], pw[(e + 1) * 2 * kFrames], acc1);
+      }
+      if (e < n) acc0 = fmaf(fv[e], pw[e * 2 * kFrames], acc0);
+      if (top) acc1 = fmaf(fv[200 - lo], work[kFrames + lane], acc1);
+      const float v = 0.30102999566398120f * __log2f(fmaxf(acc0 + acc1, 1e-10f));  // audio.py:154
       if (t < a.T) {
         a.mel[((size_t)b * a.n_mels + m) * a.T + t] = v;
         vmax = fmaxf(vmax, v);
@@ -145,8 +219,23 @@ __global__ void __launch_bounds__(256) logmel_finish_kernel(float* __restrict__ 
   }
 }
 
-constexpr int kG = 4;
-constexpr size_t kSmemBytes = (size_t)(kAudFloats + 2 + kWorkFloats) * sizeof(float) + 2 * kMaxMels * sizeof(int);
+constexpr size_t smem_bytes() { return (size_t)(kAudFloats + kWorkFloats + kMaxNnz) * sizeof(float) + 3 * kMaxMels * sizeof(int); }
+static int g_warps = 0;  // 0 = default; tools may override through QW_LOGMEL_WARPS (4 or 8)
+
+template <int G>
+static int launch_stft(const Args& a, cudaStream_t st) {
+  auto k = logmel_stft_kernel<G>;
+  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  const int per_sm = (int)((227 * 1024) / (smem_bytes() + 1024));
+  const int cap = num_sms() * per_sm;
+  const int grid = a.num_tiles < cap ? a.num_tiles : cap;
+  {
+    KernelTimer kt(kKLogMelStft, st);
+    k<<<grid, 32 * G, smem_bytes(), st>>>(a);
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace lm
 }  // namespace qw
@@ -155,7 +244,8 @@ extern "C" {
 
 size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels) {
   if (B <= 0 || n_samples <= 0 || n_mels <= 0) return 0;
-  return qw::align_up((size_t)B * sizeof(float), 256);
+  return qw::align_up((size_t)B * sizeof(float), 256) + sizeof(qw::lm::Meta) +
+         qw::align_up((size_t)n_mels * qw::lm::kNfreq * sizeof(float), 256);
 }
 
 int qw_log_mel(const float* audio, const float* filters, float* mel, void* workspace, size_t ws_bytes, int B, int n_samples,
@@ -167,14 +257,20 @@ int qw_log_mel(const float* audio, const float* filters, float* mel, void* works
                kMaxMels);
   QW_CHECK_ARG(n_samples > kNfft / 2 && n_samples % kHop == 0, -1,
                "qw_log_mel: n_samples=%d must be a multiple of %d and > %d (reflect padding)", n_samples, kHop, kNfft / 2);
-  QW_CHECK_ARG(ws_bytes >= (size_t)B * sizeof(float), -3, "qw_log_mel: workspace too small");
+  QW_CHECK_ARG(ws_bytes >= qw_log_mel_workspace_bytes(B, n_samples, n_mels), -3, "qw_log_mel: workspace too small");
+  QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "qw_log_mel: workspace must be 256-byte aligned");
   QW_CHECK_ARG((long long)B * n_samples < (1LL << 40), -1, "qw_log_mel: tensor too large");
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
   Args a{};
   a.audio = audio;
   a.filters = filters;
   a.mel = mel;
-  a.umax = (float*)workspace;
+  a.umax = (float*)ws;
+  Meta* meta = (Meta*)(ws + align_up((size_t)B * sizeof(float), 256));
+  float* vals = (float*)((unsigned char*)meta + sizeof(Meta));
+  a.meta = meta;
+  a.vals = vals;
   a.B = B;
   a.n = n_samples;
   a.T = n_samples / kHop;  // frame T (the 3001st for 30 s) is dropped, audio.py:149
@@ -182,23 +278,24 @@ int qw_log_mel(const float* audio, const float* filters, float* mel, void* works
   a.tiles_per_utt = (a.T + kFrames - 1) / kFrames;
   a.num_tiles = B * a.tiles_per_utt;
   QW_CUDA_OK(cudaMemsetAsync(a.umax, 0xff, (size_t)B * sizeof(float), st));
-  auto k = logmel_stft_kernel<kG>;
-  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  const int cap = num_sms() * 3;
-  const int grid = a.num_tiles < cap ? a.num_tiles : cap;
   {
-    KernelTimer kt(kKLogMelStft, st);
-    k<<<grid, 32 * kG, kSmemBytes, st>>>(a);
+    KernelTimer kt(kKLogMelPrep, st);
+    logmel_prep_kernel<<<1, 1024, 0, st>>>(filters, n_mels, meta, vals);
   }
   QW_CUDA_OK(cudaGetLastError());
+  if (g_warps == 0) {
+    const char* e = getenv("QW_LOGMEL_WARPS");
+    g_warps = (e && atoi(e) == 4) ? 4 : 8;
+  }
+  if (int e = (g_warps == 4 ? launch_stft<4>(a, st) : launch_stft<8>(a, st))) return e;
   {
     const long long per_utt = (long long)n_mels * a.T;
     const long long work = ((long long)B * per_utt + 3) / 4;
     long long blocks = (work + 255) / 256;
     const long long capf = (long long)num_sms() * 8;
     if (blocks > capf) blocks = capf;
-    KernelTimer kt(kKLogMelFinish, st);
     const int vec4 = ((per_utt & 3) == 0 && ((uintptr_t)mel & 15) == 0) ? 1 : 0;
+    KernelTimer kt(kKLogMelFinish, st);
     logmel_finish_kernel<<<(int)blocks, 256, 0, st>>>(mel, a.umax, B, per_utt, vec4);
   }
   QW_CUDA_OK(cudaGetLastError());

@@ -9,9 +9,10 @@
 // 200 = 8 x 25 Cooley-Tukey:  n = 25 n1 + n2,  k = k1 + 8 k2:
 //    pass A (per n2):  Y[k1] = sum_n1 z[25 n1 + n2] W8^(n1 k1);  A[k1][n2] = Y[k1] W200^(n2 k1)
 //    pass B (per k1):  Z[k1 + 8 k2] = sum_n2 A[k1][n2] W25^(n2 k2)          (25 = 5 x 5 in registers)
-// Work-column layout (floats): complex slot s = k1*25 + j holds re at 2s, im at 2s+1.  After pass B slot
-// k1*25 + k2 holds Z[k1 + 8 k2].  The untangle pass overwrites re-slots with the power spectrum:
-//    P[k] at 2*zslot(k) for k < 200, P[200] at 1 (the im part of Z[0]'s slot).
+// Work-column layout (floats): complex slot s holds re at 2s, im at 2s+1.  Pass A stores A[k1][n2] at slot
+// n2*8 + k1; pass B reads slots {n2*8 + k1} and writes Z[k1 + 8 k2] to slot k2*8 + k1 -- the same set, so it is in
+// place per k1 and leaves the spectrum in NATURAL order (slot k = Z[k]).  The untangle pass overwrites re-slots with
+// the power spectrum: P[k] at float 2k for k < 200, P[200] at float 1 (the im part of Z[0]'s slot).
 // The G warps of a CTA split every pass by index (n2, k1, k, mel row = g, g+G, ...); a __syncthreads()
 // separates the passes.  Every table index is uniform across a warp -> constant-cache broadcasts.
 #pragma once
@@ -29,7 +30,9 @@ namespace lm {
 constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kNfreq = 201;
-constexpr int kHopPitch = 161;  // shared-memory pitch of one hop of audio: odd -> lanes (frames) hit distinct banks
+// audio staging skew: sample s of the tile sits at float s + (s >> 5).  Frames are 160 samples apart, so lane f reads
+// 165 f + j + (j >> 5): 165 is odd -> the 32 lanes hit 32 distinct banks for every tap j.
+constexpr int kLanePitch = 165;
 
 #if defined(__CUDACC__)
 __constant__ float c_win[400] = QW_TBL_WIN;
@@ -54,11 +57,10 @@ static const float h_un_im[101] = QW_TBL_UN_IM;
 #define QW_TBL(name, i) (h_##name[i])
 #endif
 
-QW_HD int zslot(int k) { return (k & 7) * 25 + (k >> 3); }      // complex slot of Z[k], k < 200
-QW_HD int pslot(int k) { return k < 200 ? 2 * zslot(k) : 1; }   // float slot of P[k], k <= 200
-
-// smem float index of tap j of the frame that starts at hop h (audio stored hop-major with pitch 161)
-QW_HD int tap_index(int h, int j) { return (h + j / kHop) * kHopPitch + (j % kHop); }
+QW_HD int pslot(int k) { return k < 200 ? 2 * k : 1; }  // float slot of P[k], k <= 200
+QW_HD int skew(int s) { return s + (s >> 5); }           // staging index of tile sample s
+// staging index of tap j of the tile's frame f (frame f starts at tile sample 160 f)
+QW_HD int tap_index(int f, int j) { return kLanePitch * f + j + (j >> 5); }
 
 // ---- forward 8-point DFT (e^{-2 pi i nk/8}), natural order in and out
 QW_HD void dft8(float (&r)[8], float (&i)[8]) {
@@ -178,8 +180,8 @@ QW_HD void pass_a(int g, int G, const Aud& aud, Col& col) {
         yi = yr * wi + yi * wr;
         yr = tr;
       }
-      col.at(2 * (k1 * 25 + n2)) = yr;
-      col.at(2 * (k1 * 25 + n2) + 1) = yi;
+      col.at(2 * (n2 * 8 + k1)) = yr;
+      col.at(2 * (n2 * 8 + k1) + 1) = yi;
     }
   }
 }
@@ -190,8 +192,8 @@ QW_HD void pass_b(int g, int G, Col& col) {
     float r[25], i[25];
 #pragma unroll
     for (int n2 = 0; n2 < 25; ++n2) {
-      r[n2] = col.at(2 * (k1 * 25 + n2));
-      i[n2] = col.at(2 * (k1 * 25 + n2) + 1);
+      r[n2] = col.at(2 * (n2 * 8 + k1));
+      i[n2] = col.at(2 * (n2 * 8 + k1) + 1);
     }
     dft25(r, i);
 #pragma unroll
@@ -199,8 +201,8 @@ QW_HD void pass_b(int g, int G, Col& col) {
 #pragma unroll
       for (int d = 0; d < 5; ++d) {
         const int k2 = c + 5 * d;
-        col.at(2 * (k1 * 25 + k2)) = r[5 * c + d];
-        col.at(2 * (k1 * 25 + k2) + 1) = i[5 * c + d];
+        col.at(2 * (k2 * 8 + k1)) = r[5 * c + d];
+        col.at(2 * (k2 * 8 + k1) + 1) = i[5 * c + d];
       }
     }
   }
@@ -216,7 +218,7 @@ QW_HD void untangle_power(int g, int G, Col& col) {
       col.at(0) = a * a;
       col.at(1) = b * b;
     } else {
-      const int s0 = 2 * zslot(k), s1 = 2 * zslot(200 - k);
+      const int s0 = 2 * k, s1 = 2 * (200 - k);
       const float ar = col.at(s0), ai = col.at(s0 + 1), br = col.at(s1), bi = col.at(s1 + 1);
       const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);   // (Z[k] + conj Z[200-k]) / 2
       const float orr = 0.5f * (ai + bi), oi = -0.5f * (ar - br);  // (Z[k] - conj Z[200-k]) / (2i)

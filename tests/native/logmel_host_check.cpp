@@ -26,7 +26,8 @@ void lm_host_power(const float* frames, float* power, int n, int G) {
     for (int k = 0; k <= 200; ++k) power[201 * f + k] = col.v[qw::lm::pslot(k)];
   }
 }
-int lm_tap_index(int h, int j) { return qw::lm::tap_index(h, j); }
+int lm_tap_index(int f, int j) { return qw::lm::tap_index(f, j); }
+int lm_skew(int s) { return qw::lm::skew(s); }
 void lm_dft25(float* r, float* i) {
   float rr[25], ii[25];
   for (int k = 0; k < 25; ++k) { rr[k] = r[k]; ii[k] = i[k]; }

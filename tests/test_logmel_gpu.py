@@ -116,4 +116,4 @@ def test_encoder_forward_config2_shape(cuda):
         mel = qa.log_mel_spectrogram(audio)
         logits = model(mel)
     assert mel.shape == (2, 80, 3000) and logits.shape == (2, 35) and torch.isfinite(logits).all()
-    assert _lib.launch_count() - n0 == 2 + 2  # stft + finish, conv1 fwd, conv2 fwd
+    assert _lib.launch_count() - n0 == 3 + 2  # prep + stft + finish, conv1 fwd, conv2 fwd

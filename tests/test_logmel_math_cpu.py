@@ -46,8 +46,10 @@ def test_frame_power_spectrum(lm, G):
 
 
 def test_tap_map_is_conflict_free_and_exact(lm):
-    """smem index of (hop h, tap j) = (h + j // 160) * 161 + j % 160; frames (lanes) h = 0..31 hit 32 distinct banks."""
-    for j in (0, 1, 159, 160, 161, 319, 320, 399):
-        idx = [lm.lm_tap_index(h, j) for h in range(32)]
-        assert idx == [(h + j // 160) * 161 + j % 160 for h in range(32)]
+    """staging index of tile sample s is s + (s >> 5); frame f (lane f) tap j reads sample 160 f + j, i.e. index
+    165 f + j + (j >> 5): the two formulas agree and the 32 lanes hit 32 distinct banks for every tap."""
+    for j in (0, 1, 31, 32, 159, 160, 161, 319, 320, 398, 399):
+        idx = [lm.lm_tap_index(f, j) for f in range(32)]
+        assert idx == [lm.lm_skew(160 * f + j) for f in range(32)]
         assert len({i % 32 for i in idx}) == 32
+    assert lm.lm_skew(5359) < 5528

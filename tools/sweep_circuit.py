@@ -1,0 +1,59 @@
+"""BASELINE.json config 4: n_qubits x n_layers sweep of the circuit alone (forward + adjoint backward), windows/s vs the
+min(FMA, HBM) roofline.  Input pre = randn(W, q) (seed 3), weights randn(Lq, q, 3).  One JSON line per point.
+
+    python tools/sweep_circuit.py [--embedding amplitude|angle] [--out profiles/r1_config4_sweep.jsonl]
+"""
+import argparse, ctypes, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from qasr_ijcnlp_b200 import _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--embedding", default="amplitude")
+ap.add_argument("--out", default=None)
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+lib = _lib.load()
+dev = torch.device("cuda:0")
+emb = {"amplitude": 0, "angle": 1}[a.embedding]
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}
+HBM = peaks["hbm_gbs"] * 1e9
+FMA = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6  # fp32 flop/s at max clock (not measured by the driver)
+p = lambda t: ctypes.c_void_p(t.data_ptr())
+st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+rows = []
+for q in (4, 6, 8, 10, 12):
+    for Lq in (1, 2, 4):
+        W = (1 << 20) if q <= 8 else (1 << 18) if q == 10 else (1 << 16)
+        g = torch.Generator(device=dev).manual_seed(3)
+        pre = torch.randn(W, q, device=dev, generator=g)
+        w = torch.randn(Lq, q, 3, device=dev, generator=g)
+        gout = torch.randn(W, q, device=dev, generator=g)
+        out, gpre, gw = torch.empty_like(pre), torch.empty_like(pre), torch.empty_like(w)
+        n = lib.qw_circuit_workspace_bytes(W, q, Lq, 4)
+        ws = torch.empty(n, device=dev, dtype=torch.uint8)
+        def fwd(): _lib.check(lib.qw_circuit_forward(p(pre), p(w), p(out), W, q, Lq, emb, st()), "f")
+        def bwd(): _lib.check(lib.qw_circuit_backward(p(pre), p(w), p(gout), p(gpre), p(gw), p(ws), n, W, q, Lq, emb, st()), "b")
+        fwd(); bwd(); torch.cuda.synchronize()
+        _lib.profile_read(True); _lib.profile_enable(True)
+        for _ in range(a.iters): fwd(); bwd()
+        _lib.profile_enable(False)
+        prof = _lib.profile_read(True)
+        ms = {k: v[0] / v[1] for k, v in prof.items()}
+        t_f, t_b = ms["circuit_fwd_kernel"], ms["circuit_bwd_kernel"] + ms.get("circuit_finalize_kernel", 0.0)
+        N = 1 << q
+        flop_f = 14.0 * q * N * Lq + (3 + q) * N
+        flop_fb = flop_f * 4.0                             # fwd + (recompute + 2 adjoint sweeps + products) ~ 3x
+        bytes_fb = 4.0 * q * (2 + 3)                       # fwd: pre in, out out; bwd: pre, gout in, gpre out
+        ceil = min(FMA / flop_fb, HBM / bytes_fb)
+        wps = W / ((t_f + t_b) * 1e-3)
+        row = {"config": 4, "embedding": a.embedding, "n_qubits": q, "n_layers": Lq, "windows": W, "fwd_ms": round(t_f, 4),
+               "bwd_ms": round(t_b, 4), "windows_per_s_fwd_bwd": round(wps, 1), "roofline_windows_per_s": round(ceil, 1),
+               "bound": "fma" if FMA / flop_fb < HBM / bytes_fb else "hbm", "frac": round(wps / ceil, 4),
+               "fwd_windows_per_s": round(W / (t_f * 1e-3), 1)}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+if a.out:
+    with open(a.out, "a") as fh:
+        for r in rows: fh.write(json.dumps(r) + "\n")
