@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--nsets", type=int, default=4, help="rotating buffer sets (L2 defeat)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="gradient all-reduce at N > 1")
     return ap.parse_args()
 
 
@@ -175,7 +176,15 @@ class StemParams:
         for name, m in self.mods.items():
             ps = [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias]
             self.p[name] = [t.detach().contiguous() for t in ps]
-            self.g[name] = [torch.empty_like(t) for t in self.p[name]]
+        # one flat gradient bucket (9 440 floats, padded per tensor to 16 B): the backward kernels write straight into it and the
+        # data-parallel all-reduce runs on it in place
+        sizes = [(name, i, (t.numel() + 3) // 4 * 4) for name in self.mods for i, t in enumerate(self.p[name])]
+        self.flat_grads = torch.zeros(sum(n for _, _, n in sizes), device=dev)
+        off = 0
+        for name, i, n in sizes:
+            t = self.p[name][i]
+            self.g.setdefault(name, []).append(self.flat_grads[off:off + t.numel()].view_as(t))
+            off += n
 
 
 class StemRunner:
@@ -210,11 +219,16 @@ class StemRunner:
         self._lib.check(st, "qw_conv1d_backward")
 
     def step(self, s):
-        for name in ("conv1", "conv2"):
-            self.fwd(name, s)
-            self.bwd(name, s)
+        # training order of the stem: conv1 fwd, conv2 fwd, [rest of the model], conv2 bwd, conv1 bwd, gradient all-reduce
+        self.fwd("conv1", s)
+        self.fwd("conv2", s)
+        self.bwd("conv2", s)
+        self.bwd("conv1", s)
+        if self.allreduce is not None:
+            self.allreduce(self.params.flat_grads)
 
-    LAUNCHES_PER_STEP = 2 * (1 + 3)  # per layer: fwd kernel + bwd_post + bwd_pre + finalize
+    allreduce = None                 # set by run_b200 when world > 1
+    LAUNCHES_PER_STEP = 2 * (1 + 3)  # per layer: fwd kernel + bwd_gy + bwd_pre + finalize (+1: P2P all-reduce kernel at N > 1)
 
 
 def algorithmic_bytes(kernel, layer, B):
@@ -269,32 +283,65 @@ def run_b200(args):
     B, K, Wm, nsets = args.batch, args.steps, max(args.warmup, 3), args.nsets
     runner = StemRunner(B, dev, nsets)
     windows_per_step = B * WINDOWS_PER_UTT
+    collective = "none (single GPU)"
+    if world > 1:
+        from qasr_ijcnlp_b200 import dp
+        n = runner.params.flat_grads.numel()
+        try:
+            if args.collective == "nccl":
+                raise RuntimeError("forced")
+            runner.allreduce = dp.P2PGradAllReduce(n, dev)
+            collective = f"own one-shot NVLink peer-memory all-reduce kernel ({4 * n} B bucket, fused 1/N scale, in the step's CUDA graph)"
+        except Exception as e:  # symmetric memory unavailable -> NCCL
+            flat = runner.params.flat_grads
+            runner.allreduce = lambda t: torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG)
+            collective = f"NCCL all_reduce(AVG) of the {4 * n} B bucket, in the step's CUDA graph ({type(e).__name__}: {str(e)[:80]})"
 
     # ---- warm up eagerly (also sets function attributes), then capture one CUDA graph per buffer set
     for i in range(2):
         runner.step(i % nsets)
     torch.cuda.synchronize()
-    graphs = []
     side = torch.cuda.Stream()
-    for s in range(nsets):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
-            runner.step(s)
-        graphs.append(g)
+
+    def capture():
+        gs = []
+        for s_ in range(nsets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                runner.step(s_)
+            gs.append(g)
+        return gs
+
+    post = None
+    try:
+        graphs = capture()
+    except Exception as e:  # a collective that cannot be captured: keep it eager, right behind the graph
+        if runner.allreduce is None:
+            raise
+        post, runner.allreduce = runner.allreduce, None
+        collective += f" [not capturable: {type(e).__name__}; issued eagerly after the graph]"
+        torch.cuda.synchronize()
+        graphs = capture()
     torch.cuda.synchronize()
+
+    def replay(i):
+        graphs[i % nsets].replay()
+        if post is not None:
+            post(runner.params.flat_grads)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
     for i in range(Wm):
-        graphs[i % nsets].replay()
+        replay(i)
     barrier(world)
-    ms = time_events(lambda i: graphs[i % nsets].replay(), K)
+    ms = time_events(replay, K)
     barrier(world)
     ms = max_over_ranks(ms, world, dev)
     value = world * windows_per_step * K / (ms * 1e-3)
-    gpu_launches = K * StemRunner.LAUNCHES_PER_STEP
+    own_per_step = StemRunner.LAUNCHES_PER_STEP + (1 if (world > 1 and "own" in collective) else 0)
+    gpu_launches = K * own_per_step
 
     # ---- per-kernel durations (CUDA events inside the library, eager launches, same rotating buffers)
     kern = {}
@@ -345,16 +392,20 @@ def run_b200(args):
         except Exception as e:  # keep the headline line alive
             enc = {"error": repr(e)[:200]}
 
+    enc_train = None
+    if not args.no_encoder:
+        try:
+            enc_train = run_encoder_train(B, max(3, min(K, 10)), dev, world, rank)
+        except Exception as e:
+            enc_train = {"error": repr(e)[:200]}
+
     # ---- clocks: make sure the sampler saw the workload for >= 1.5 s
-    if rank == 0:
-        t0 = time.time()
-        i = 0
-        while time.time() - t0 < 1.5:
-            graphs[i % nsets].replay()
-            i += 1
-            if i % 64 == 0:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
+    n_extra = min(200000, int(1.5 / max(1e-6, ms / K * 1e-3)))  # same count on every rank (ms is the max over ranks)
+    for i in range(n_extra):
+        replay(i)
+        if i % 64 == 63:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else {}
     barrier(world)
 
@@ -372,12 +423,13 @@ def run_b200(args):
                             f"fwd+bwd, n_qubits=4, batch {B}/GPU x 80 mel x 3000 frames (BASELINE configs[1]/[2] shape)",
                 "windows_per_step_per_gpu": windows_per_step, "batch_per_gpu": B, "n_qubits": Q, "n_layers": 1,
                 "l2": f"{nsets} rotating buffer sets ({nsets} x {runner_bytes(B) / 1e6:.0f} MB > 126 MB L2)",
-                "launch": "one CUDA graph per step (8 kernels)", "parallelism": f"dp{world} (batch shard, no collective)",
+                "launch": f"one CUDA graph per step ({own_per_step} kernels)",
+                "parallelism": f"dp{world} (batch shard; forward: no collective; gradients: {collective})",
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "step_roofline_frac": round(step_frac, 4), "kernels": kernels,
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
-            "encoder_fwd": enc, "launch_count_check": _lib.launch_count() - launches0,
+            "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
         }
         print(json.dumps(line))
     if world > 1:
@@ -423,7 +475,9 @@ def run_e2e(runner, B, K, Wm, world, dev):
         grads = torch.autograd.grad(loss, params)
         ev_free[slot].record(main)
         flat = torch.cat([loss.reshape(1)] + [gr.reshape(-1) for gr in grads])
-        host_out[i % nhost].copy_(flat, non_blocking=True)
+        if world > 1:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.AVG)
+        host_out[i % nhost].copy_(flat.detach(), non_blocking=True)
 
     def loop(n):
         for s in range(2):
@@ -447,7 +501,8 @@ def run_e2e(runner, B, K, Wm, world, dev):
     return {"value": round(val, 1), "unit": UNIT, "h2d_bytes_per_step": B * N_MELS * N_FRAMES * 4,
             "d2h_bytes_per_step": 4 * (1 + n_grad), "ms_per_step": round(ms / K, 5),
             "api": "QuantumConv1d nn.Module x2 + GELU + MSE-style loss, torch.autograd, pinned host in/out, "
-                   "H2D double-buffered on a copy stream", "loss": float(host_out[(K - 1) % nhost][0])}
+                   "H2D double-buffered on a copy stream" + ("; NCCL all_reduce(AVG) of loss + gradients" if world > 1 else ""),
+            "loss": float(host_out[(K - 1) % nhost][0])}
 
 
 def run_encoder_fwd(B, K, dev, world):
@@ -472,6 +527,53 @@ def run_encoder_fwd(B, K, dev, world):
     ms = max_over_ranks(time_events(step, K), world, dev)
     return {"value": round(world * B * K / (ms * 1e-3), 2), "unit": "utt/s", "ms_per_step": round(ms / K, 4),
             "workload": f"log-mel + QuantumWhisper-Tiny encoder fwd + Linear(384,35), batch {B}, host audio in"}
+
+
+def run_encoder_train(B, K, dev, world, rank):
+    """BASELINE.json configs[2]: Quantum Whisper-Tiny + LSTM char decoder ASR training step on LibriSpeech-shaped synthetic
+    30 s audio, batch B per GPU: host audio -> H2D -> log-mel (qw_log_mel) -> encoder (quantum stem + 4 blocks) -> char
+    decoder -> CE(ignore 0) -> backward -> gradient all-reduce (NCCL, one flat bucket) -> clip 1.0 -> AdamW.
+    Trainables as freeze_non_quantum_layers selects them (quantum_whisper.py:325-333): conv1, conv2, asr_head."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200 import audio as qa
+    from qasr_ijcnlp_b200 import dp
+
+    torch.manual_seed(0)
+    model = qw.QuantumWhisperASR(qw.QuantumWhisper(qw.get_whisper_tiny_dims(), n_qubits=Q)).to(dev)
+    qw.freeze_non_quantum_layers(model)
+    dp.broadcast_parameters(model)
+    train = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(train, lr=1e-3, weight_decay=0.01)
+    bucket = dp.GradBucket(train)
+    g = torch.Generator().manual_seed(2 + rank)
+    audio = (0.1 * torch.randn(B, 480000, generator=g)).pin_memory()
+    V = len(qw.CHAR_VOCAB)
+    tokens = torch.randint(4, V, (B, 100), generator=g)
+    tokens[:, 0] = 2
+    tokens = tokens.to(dev)
+    lossf = torch.nn.CrossEntropyLoss(ignore_index=0)
+
+    def step(_):
+        mel = qa.log_mel_spectrogram(audio.to(dev, non_blocking=True))
+        logits = model(mel, tokens[:, :-1])
+        loss = lossf(logits.reshape(-1, V), tokens[:, 1:].reshape(-1))
+        loss.backward()
+        bucket.allreduce_mean()
+        torch.nn.utils.clip_grad_norm_(train, 1.0)
+        opt.step()
+        for p in train:
+            p.grad = None
+        return loss
+
+    for i in range(3):
+        step(i)
+    barrier(world)
+    ms = max_over_ranks(time_events(step, K), world, dev)
+    barrier(world)
+    return {"value": round(world * B * K / (ms * 1e-3), 2), "unit": "utt/s", "ms_per_step": round(ms / K, 3),
+            "trainable_floats": bucket.numel,
+            "workload": f"ASR training step (30 s synthetic audio, batch {B}/GPU, quantum stem + 4 frozen blocks + LSTM char decoder), "
+                        f"fwd+bwd+allreduce+clip+AdamW, host audio in"}
 
 
 # --------------------------------------------------------------------------------------------- CPU legs

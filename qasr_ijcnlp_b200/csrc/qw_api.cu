@@ -82,7 +82,7 @@ int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset
 const char* qw_kernel_name(int kernel_id) {
   static const char* names[] = {"qconv_fwd_kernel", "qconv_bwd_post_kernel", "qconv_bwd_pre_kernel", "qconv_bwd_finalize_kernel",
                                 "circuit_fwd_kernel", "circuit_bwd_kernel", "circuit_finalize_kernel", "logmel_stft_kernel",
-                                "logmel_finish_kernel", "qconv_bwd_adj_kernel", "logmel_prep_kernel"};
+                                "logmel_finish_kernel", "qconv_bwd_adj_kernel", "logmel_prep_kernel", "grads_allreduce_p2p_kernel"};
   return (kernel_id >= 0 && kernel_id < qw::kKCount) ? names[kernel_id] : "";
 }
 }

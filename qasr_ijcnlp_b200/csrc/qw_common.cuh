@@ -13,7 +13,7 @@ void count_launch(int n = 1);
 int num_sms();
 
 // Optional per-kernel CUDA-event timing (qw_profile_enable): KernelTimer brackets one launch on `st`.
-enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKCount };
+enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKGradAllReduce, kKCount };
 bool profiling_enabled();
 void profile_begin(int id, cudaStream_t st);
 void profile_end(int id, cudaStream_t st);

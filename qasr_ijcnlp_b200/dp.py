@@ -103,3 +103,62 @@ class _Pending:
     def wait(self):
         self.work.wait()
         self.flat.mul_(1.0 / self.world)
+
+
+class P2PGradAllReduce:
+    """One-shot NVLink peer-memory all-reduce (mean) of a small flat fp32 gradient bucket: `qw_grads_allreduce_p2p`.
+
+    torch symmetric memory does the rendezvous (it maps every rank's buffer into every process); the data movement and
+    the reduction are the library's own kernel -- no NCCL call on the step's critical path, and the launch is CUDA-graph
+    capturable.  world == 1 works with plain device tensors (used by the single-GPU test).  Raises if symmetric memory is
+    unavailable; callers then fall back to `GradBucket` (NCCL)."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import ctypes
+
+        from . import _lib
+
+        self._ctypes, self._lib_mod = ctypes, _lib
+        self.lib = _lib.load()
+        self.numel = int(numel)
+        self.device = torch.device(device)
+        inited = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if inited else 1
+        self.rank = dist.get_rank(group) if inited else 0
+        nbuf = self.lib.qw_grads_allreduce_p2p_buffer_bytes(self.numel) // 4
+        nflag = self.lib.qw_grads_allreduce_p2p_flag_bytes(self.world) // 4
+        if self.world == 1:
+            self.buf = torch.zeros(nbuf, device=self.device, dtype=torch.float32)
+            self.flags = torch.zeros(nflag, device=self.device, dtype=torch.int32)
+            buf_ptrs, flag_ptrs = [self.buf.data_ptr()], [self.flags.data_ptr()]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            grp = group if group is not None else dist.group.WORLD
+            self.buf = symm_mem.empty(nbuf, dtype=torch.float32, device=self.device)
+            self.flags = symm_mem.empty(max(nflag, 64), dtype=torch.int32, device=self.device)
+            self.buf.zero_()
+            self.flags.zero_()
+            self._hb = symm_mem.rendezvous(self.buf, grp)
+            self._hf = symm_mem.rendezvous(self.flags, grp)
+            buf_ptrs, flag_ptrs = list(self._hb.buffer_ptrs), list(self._hf.buffer_ptrs)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)  # every rank's flags are zero before anybody signals
+        P = ctypes.c_void_p
+        self._bufs = (P * self.world)(*[P(p) for p in buf_ptrs])
+        self._flags = (P * self.world)(*[P(p) for p in flag_ptrs])
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        """In-place mean over ranks of `flat` (contiguous fp32, numel == self.numel) on the current stream."""
+        if flat.numel() != self.numel or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("bucket must be a contiguous fp32 tensor of the size given at construction")
+        P = self._ctypes.c_void_p
+        with torch.cuda.device(self.device):
+            st = self.lib.qw_grads_allreduce_p2p(P(flat.data_ptr()), self.numel, self._bufs, self._flags, self.rank, self.world,
+                                                 1.0 / self.world, P(torch.cuda.current_stream().cuda_stream))
+        self._lib_mod.check(st, "qw_grads_allreduce_p2p")
+        return flat
+
+    def status(self) -> int:
+        """0 ok; 1 if some call timed out waiting for a peer (synchronises)."""
+        return int(self.flags[2 * self.world + 1].item())

@@ -1,0 +1,102 @@
+"""GPU tests of the data-parallel gradient collective (qw_grads_allreduce_p2p).  The single-GPU case exercises the
+kernel's epoch / double-buffer logic; the 2-GPU case (skipped on a 1-GPU box) spawns one process per GPU and checks the
+NVLink peer-memory all-reduce against NCCL, eagerly and from a replayed CUDA graph."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_world1_is_identity_and_graph_capturable(cuda):
+    from qasr_ijcnlp_b200 import dp
+    ar = dp.P2PGradAllReduce(9440, cuda)
+    g = torch.randn(9440, device=cuda)
+    want = g.clone()
+    for _ in range(3):  # epochs 1..3, both slots
+        ar(g)
+    assert torch.equal(g, want) and ar.status() == 0
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.graph(graph, stream=s):
+        ar(g)
+    for _ in range(4):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g, want) and ar.status() == 0
+    assert int(ar.flags[2].item()) == 3 + 4 + 0 or int(ar.flags[2].item()) >= 7  # epoch advanced once per launch
+    with pytest.raises(ValueError):
+        ar(torch.zeros(5, device=cuda))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from qasr_ijcnlp_b200 import dp
+        n = 9440 + 35 * 385
+        ar = dp.P2PGradAllReduce(n, dev)
+        ok = True
+        for it in range(5):
+            g = torch.Generator(device=dev).manual_seed(100 * it + rank)
+            x = torch.randn(n, device=dev, generator=g)
+            ref = x.clone()
+            dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+            ref /= world
+            ar(x)
+            ok = ok and (x - ref).abs().max().item() <= 1e-6
+        # ranks must end bit-identical (fixed summation order)
+        gathered = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(gathered, x)
+        ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+        # graph replay
+        y = torch.full((n,), float(rank + 1), device=dev)
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.graph(graph, stream=s):
+            ar(y)
+        torch.cuda.synchronize()
+        dist.barrier()
+        want = float(sum(range(1, world + 1))) / world
+        for _ in range(3):
+            y.fill_(float(rank + 1))
+            torch.cuda.synchronize()
+            dist.barrier()
+            graph.replay()
+            torch.cuda.synchronize()
+            ok = ok and bool((y - want).abs().max().item() <= 1e-6)
+        ok = ok and ar.status() == 0
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_p2p_allreduce_matches_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
