@@ -37,6 +37,15 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "qconv_windows_per_sec_fwd_bwd"
 UNIT = "windows/s"
 N_MELS, N_STATE, N_FRAMES, Q = 80, 384, 3000, 4
@@ -228,7 +237,6 @@ class StemRunner:
             self.allreduce(self.params.flat_grads)
 
     allreduce = None                 # set by run_b200 when world > 1
-    LAUNCHES_PER_STEP = 2 * (1 + 3)  # per layer: fwd kernel + bwd_gy + bwd_pre + finalize (+1: P2P all-reduce kernel at N > 1)
 
 
 def algorithmic_bytes(kernel, layer, B):
@@ -299,7 +307,9 @@ def run_b200(args):
 
     # ---- warm up eagerly (also sets function attributes), then capture one CUDA graph per buffer set
     for i in range(2):
+        n_before = _lib.launch_count()
         runner.step(i % nsets)
+        launches_per_step = _lib.launch_count() - n_before  # counted, not assumed: every kernel of the step is the library's own
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
 
@@ -340,7 +350,7 @@ def run_b200(args):
     barrier(world)
     ms = max_over_ranks(ms, world, dev)
     value = world * windows_per_step * K / (ms * 1e-3)
-    own_per_step = StemRunner.LAUNCHES_PER_STEP + (1 if (world > 1 and "own" in collective) else 0)
+    own_per_step = launches_per_step
     gpu_launches = K * own_per_step
 
     # ---- per-kernel durations (CUDA events inside the library, eager launches, same rotating buffers)
@@ -431,7 +441,7 @@ def run_b200(args):
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
             "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -661,11 +671,17 @@ def run_reference(args):
         "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
     args = parse_args()
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner) write to fd 1 too, so point fd 1 at
+    # stderr for the duration of the run and emit the line through a private duplicate of the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

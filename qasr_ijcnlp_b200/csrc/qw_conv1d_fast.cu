@@ -16,6 +16,8 @@
 //   fast_bwd_pre_kernel<S,PAR,GX>  x tile ring in, grad_x written in place and stored back by TMA; lanes along
 //                           channels hold pre_conv weights and their gradient accumulators in registers.
 //   fast_finalize_kernel    deterministic reduction of the per-CTA partial rows.
+#include <cstdlib>
+
 #include "../../include/qw.h"
 #include "qw_conv1d_plan.cuh"
 #include "qw_tma.cuh"
@@ -288,8 +290,6 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
 }
 
 // =============================================================================================== backward: gy streaming + adjoint
-constexpr int kHaloL = 8;
-constexpr int kHaloR = 144;
 struct FastGyArgs {
   const float *w_post, *pre_save, *qw;
   float *gpre_pad, *part;  // gpre_pad: [B][LP][4]; part: [gridDim.x][PA1]
@@ -537,6 +537,225 @@ __global__ void __launch_bounds__(kGyThreads, 2) fast_bwd_gy_kernel(const __grid
   }
 }
 
+// =============================================================================================== backward: gy streaming (lean) + adjoint kernel
+// Split form of the kernel above (default; QW_GY_FUSED=1 selects the fused one): ncu showed the fused kernel bound by its two
+// adjoint warps (a 3 000-instruction dependent chain per tile on one warp) and by instruction-cache misses (98 KB of code
+// shared by two roles).  Here the streaming kernel only streams (small code, every warp the same role) and writes
+// gout (16 B / window); the adjoint runs as its own kernel with one window per thread across all SMs.
+struct FastGy2Args {
+  const float* w_post;
+  float *gout, *part;  // gout: [B*Lout][4]; part: [gridDim.x][PA1]
+  int B, O, Lout, tiles_per_utt, num_tiles, PA1;
+};
+__host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O) {
+  return 1024 + (size_t)kGyStages * kGyStageElems * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)O * FQ * 4 +
+         (size_t)2 * kGySW * FTW * FQ * 4 + (2 * kGyStages) * 8;
+}
+
+template <int NHALF>
+__global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid_constant__ CUtensorMap tm_gy,
+                                                                    const __grid_constant__ CUtensorMap tm_qout, const FastGy2Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* base = align1024(smem_dyn);
+  float* stages = reinterpret_cast<float*>(base);                      // [kGyStages][192][32] swizzled
+  float* outs = stages + (size_t)kGyStages * kGyStageElems;            // [3][32][4]
+  float* wpost = outs + 3 * FTW * FQ;                                  // [O][4]
+  float* gred = wpost + (size_t)a.O * FQ;                              // [2][kGySW][32][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(gred + 2 * kGySW * FTW * FQ);
+  uint64_t* empty = full + kGyStages;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rr = lane >> 3, tl = lane & 7;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_gy);
+    tma_prefetch_desc(&tm_qout);
+    for (int s = 0; s < kGyStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGySW);
+    }
+    fence_mbar_init();
+  }
+  for (int u = tid; u < a.O; u += kGyStream) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
+  __syncthreads();
+
+  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_stages = my_tiles * NHALF;
+  float wacc[NHALF][FQ + 1];
+#pragma unroll
+  for (int m = 0; m < NHALF; ++m)
+#pragma unroll
+    for (int j = 0; j <= FQ; ++j) wacc[m][j] = 0.f;
+
+  auto issue = [&](int gs) {
+    const int n = gs / NHALF, h = gs - n * NHALF;
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int s = gs % kGyStages;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(kGyStageElems + (h == 0 ? FTW * FQ : 0)) * 4);
+#pragma unroll
+    for (int bx = 0; bx < 3; ++bx)
+      tma_load_3d(stages + (size_t)s * kGyStageElems + bx * 64 * 32, &tm_gy, i0, h * kGyStageRows + bx * 64, b, &full[s]);
+    if (h == 0) tma_load_3d(outs + (n % 3) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
+  };
+  if (tid == 0)
+    for (int gs = 0; gs < kGyStages - 1 && gs < total_stages; ++gs) issue(gs);
+
+  int gs = 0;
+  for (int n = 0; n < my_tiles; ++n) {
+    float gacc[4][FQ];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) gacc[u][j] = 0.f;
+    const float* os = outs + (n % 3) * FTW * FQ;
+#pragma unroll
+    for (int h = 0; h < NHALF; ++h, ++gs) {
+      if (tid == 0) {
+        const int gn = gs + kGyStages - 1;
+        if (gn < total_stages) {
+          if (gn >= kGyStages) mbar_wait(&empty[gn % kGyStages], ((gn / kGyStages) - 1) & 1);
+          issue(gn);
+        }
+      }
+      const int s = gs % kGyStages;
+      mbar_wait(&full[s], (gs / kGyStages) & 1);
+      const float* gsm = stages + (size_t)s * kGyStageElems;
+      const int row0 = h * kGyStageRows;
+      // ---- gout partials: lanes (4 rows x 8 chunks of 4 windows); 48 row groups per stage, 8 per warp
+#pragma unroll 2
+      for (int og = warp; og < kGyStageRows / 4; og += kGySW) {
+        const int rl = og * 4 + rr;
+        const int r = row0 + rl;
+        const float4 gv = ld4(gsm + swz128(rl, tl));
+        const float4 wv = (r < a.O) ? ld4(wpost + (size_t)r * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gacc[0][0] = fmaf(gv.x, wv.x, gacc[0][0]); gacc[0][1] = fmaf(gv.x, wv.y, gacc[0][1]);
+        gacc[0][2] = fmaf(gv.x, wv.z, gacc[0][2]); gacc[0][3] = fmaf(gv.x, wv.w, gacc[0][3]);
+        gacc[1][0] = fmaf(gv.y, wv.x, gacc[1][0]); gacc[1][1] = fmaf(gv.y, wv.y, gacc[1][1]);
+        gacc[1][2] = fmaf(gv.y, wv.z, gacc[1][2]); gacc[1][3] = fmaf(gv.y, wv.w, gacc[1][3]);
+        gacc[2][0] = fmaf(gv.z, wv.x, gacc[2][0]); gacc[2][1] = fmaf(gv.z, wv.y, gacc[2][1]);
+        gacc[2][2] = fmaf(gv.z, wv.z, gacc[2][2]); gacc[2][3] = fmaf(gv.z, wv.w, gacc[2][3]);
+        gacc[3][0] = fmaf(gv.w, wv.x, gacc[3][0]); gacc[3][1] = fmaf(gv.w, wv.y, gacc[3][1]);
+        gacc[3][2] = fmaf(gv.w, wv.z, gacc[3][2]); gacc[3][3] = fmaf(gv.w, wv.w, gacc[3][3]);
+      }
+      // ---- grad post_conv.{weight,bias}: thread <-> stage row, accumulators live in registers
+      {
+        const int rl = tid;  // 0..191
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+          const float4 gv = ld4(gsm + swz128(rl, c));
+          const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 ov = ld4(os + (size_t)(4 * c + u) * FQ);
+            wacc[h][0] = fmaf(g4[u], ov.x, wacc[h][0]);
+            wacc[h][1] = fmaf(g4[u], ov.y, wacc[h][1]);
+            wacc[h][2] = fmaf(g4[u], ov.z, wacc[h][2]);
+            wacc[h][3] = fmaf(g4[u], ov.w, wacc[h][3]);
+            wacc[h][4] += g4[u];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // ---- reduce the 4 row classes, then the 6 warps through shared memory; one warp stores the tile's gout
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) {
+        float v = gacc[u][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        gacc[u][j] = v;
+      }
+    float* gr = gred + (size_t)(n & 1) * kGySW * FTW * FQ;
+    if (rr == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        st4(gr + ((size_t)warp * FTW + 4 * tl + u) * FQ, make_float4(gacc[u][0], gacc[u][1], gacc[u][2], gacc[u][3]));
+    }
+    __syncthreads();  // gred[n&1] complete; its previous readers (tile n-2) passed the barrier of tile n-1
+    if (warp == n % kGySW) {
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < kGySW; ++w) {
+        const float4 pv = ld4(gr + ((size_t)w * FTW + lane) * FQ);
+        sacc.x += pv.x; sacc.y += pv.y; sacc.z += pv.z; sacc.w += pv.w;
+      }
+      if (i < a.Lout) st4(a.gout + ((size_t)b * a.Lout + i) * FQ, sacc);
+    }
+  }
+  // ---- partial row of this CTA: [O*4 grad post_conv.weight][O grad post_conv.bias][pad]
+  float* prow = a.part + (size_t)blockIdx.x * a.PA1;
+#pragma unroll
+  for (int m = 0; m < NHALF; ++m) {
+    const int r = m * kGyStageRows + tid;
+    if (r < a.O) {
+      st4(prow + (size_t)r * FQ, make_float4(wacc[m][0], wacc[m][1], wacc[m][2], wacc[m][3]));
+      prow[a.O * FQ + r] = wacc[m][4];
+    }
+  }
+  for (int e = a.O * (FQ + 1) + tid; e < a.PA1; e += kGyStream) prow[e] = 0.f;
+}
+
+// adjoint differentiation of the circuit, one window per thread; partial row per CTA: [gb_pre 4 + pad 28][Lq*32 gate matrices]
+constexpr int kAdjThreads = 128;
+
+__global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdjArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  const int NE = FQ + a.Lq * 32;
+  float* gates = reinterpret_cast<float*>(smem_dyn);             // [Lq][4][16]
+  float* macc = gates + (size_t)a.Lq * FQ * kGateStride;         // [4 warps][NE][kGyMS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  for (int e = tid; e < 4 * NE * kGyMS; e += kAdjThreads) macc[e] = 0.f;
+  {  // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
+    const int per = (kHaloL + kHaloR) * FQ;
+    for (long long idx = (long long)blockIdx.x * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kAdjThreads) {
+      const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
+      const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
+      a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
+    }
+  }
+  __syncthreads();
+  float* mymacc = macc + (size_t)warp * NE * kGyMS;
+  for (long long w0 = (long long)blockIdx.x * kAdjThreads; w0 < a.W; w0 += (long long)gridDim.x * kAdjThreads) {
+    const long long w = w0 + tid;
+    const bool valid = w < a.W;
+    const float4 pv = valid ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+    const float4 gv = valid ? ld4(a.gout + (size_t)w * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
+    const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
+    float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
+    const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+    SmemGateAcc<float, FQ> acc{mymacc + (size_t)FQ * kGyMS + lane, kGyMS, 0};
+    circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
+    if (valid) {
+      const int b = (int)(w / a.Lout), i = (int)(w - (long long)b * a.Lout);
+      st4(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
+    }
+#pragma unroll
+    for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
+  }
+  __syncthreads();
+  float* prow = a.part + (size_t)blockIdx.x * a.PA2;
+  for (int e = warp; e < a.PA2; e += kAdjThreads / 32) {
+    // e in [0,4): grad pre_conv.bias; [32, 32+Lq*32): gate matrices; everything else padding
+    float v = 0.f;
+    const int src = e < FQ ? e : (e >= 32 && e < 32 + a.Lq * 32) ? FQ + (e - 32) : -1;
+    if (src >= 0) {
+#pragma unroll
+      for (int wq = 0; wq < 4; ++wq) v += macc[((size_t)wq * NE + src) * kGyMS + lane];
+      v = warp_sum(v);
+    }
+    if (lane == 0) prow[e] = v;
+  }
+}
+
 // =============================================================================================== backward: pre_conv^T
 struct FastPreArgs {
   const float *gpre_pad, *w_pre;
@@ -678,18 +897,21 @@ struct FastFinArgs {
   float *gw_pre, *gb_pre, *gqw, *gw_post, *gb_post;
   int G1, P1, G3, P3;
   int C, O, Lq;
+  const float* part2;  // split backward: [G2][P2] rows of the adjoint kernel ([gb_pre 4 + pad 28][Lq*32]); null when fused
+  int G2, P2;
 };
 
 __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFinArgs a) {
   __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb1 = a.P1 / 32;
+  const int nb1 = a.P1 / 32, nb2 = a.part2 ? a.P2 / 32 : 0;
   const bool seg1 = (int)blockIdx.x < nb1;
-  const int blk = seg1 ? blockIdx.x : blockIdx.x - nb1;
-  const int G = seg1 ? a.G1 : a.G3;
-  const int P = seg1 ? a.P1 : a.P3;
-  const float* __restrict__ part = seg1 ? a.part1 : a.part3;
+  const bool seg2 = !seg1 && (int)blockIdx.x < nb1 + nb2;
+  const int blk = seg1 ? blockIdx.x : seg2 ? blockIdx.x - nb1 : blockIdx.x - nb1 - nb2;
+  const int G = seg1 ? a.G1 : seg2 ? a.G2 : a.G3;
+  const int P = seg1 ? a.P1 : seg2 ? a.P2 : a.P3;
+  const float* __restrict__ part = seg1 ? a.part1 : seg2 ? a.part2 : a.part3;
   const int blk0 = blk * 32, p = blk0 + lane;
   double s = 0.0;
   if (p < P) {
@@ -709,11 +931,14 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   for (int w = 0; w < kFFWarps; ++w) t += red[w][lane];
   tot[lane] = t;
   __syncwarp();
-  if (seg1) {
-    const int nW = a.O * FQ, moff = gy_moff(a.O);
-    if (p < nW) a.gw_post[p] = (float)t;
-    else if (p < nW + a.O) a.gb_post[p - nW] = (float)t;
-    else if (blk0 == moff) {
+  if (seg1 || seg2) {
+    const int nW = a.O * FQ;
+    const int moff = seg2 ? 0 : gy_moff(a.O);  // start of the [gb_pre | gate matrices] section inside the row
+    if (seg1 && p < nW) a.gw_post[p] = (float)t;
+    else if (seg1 && p < nW + a.O) a.gb_post[p - nW] = (float)t;
+    else if (seg1 && a.part2) {
+      // split backward: the gy rows carry no adjoint section
+    } else if (blk0 == moff) {
       if (lane < FQ) a.gb_pre[lane] = (float)t;
     } else if (blk0 > moff && lane < 4) {
       const int gi = (blk0 - moff - 32) / 8 + lane;
@@ -777,6 +1002,11 @@ bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const 
          aligned16(gx) && tmap_encode_fn() != nullptr;
 }
 
+// NOTE (measured, round 1): sizing the persistent grids for EQUAL tile counts (e.g. 251 CTAs x 3 tiles instead of 296 CTAs of
+// which 160 run a third tile) is SLOWER (step 0.1435 -> 0.1525 ms): the kernels are bound by per-CTA pipeline latency, not by
+// shared HBM bandwidth, so an SM left with one CTA loses more than the ragged last round costs.  Likewise a 4-lanes-per-window
+// adjoint (shorter dependency chain, 4x the warps) lost to one window per thread (17.6 vs 10.9 us): shuffles + the CNOT pass
+// through shared memory outweigh the chain shortening at q = 4.
 FastPlan make_fast_plan(const ConvDims& d) {
   FastPlan p{};
   const int sms = num_sms();
@@ -794,8 +1024,12 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.gridGy = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
   p.PA1 = gy_plen(d.O, d.Lq);
   const long long W = (long long)d.B * d.Lout;
-  p.gridAdj = 0;
-  p.PA2 = 0;
+  {
+    const long long need = (W + kAdjThreads - 1) / kAdjThreads;
+    const long long cap = (long long)sms * 8;
+    p.gridAdj = (int)(need < cap ? need : cap);
+  }
+  p.PA2 = 32 + (int)align_up((size_t)d.Lq * 32, 32);
   p.LP = kHaloL + d.Lout + kHaloR;
   p.ptiles_per_utt = (d.L + 127) / 128;
   p.num_ptiles = d.B * p.ptiles_per_utt;
@@ -806,10 +1040,10 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
   p.PB = p.Cpad * 12;
   size_t o = 0;
-  p.off_gout = o;
+  p.off_gout = o; o = align_up(o + (size_t)W * FQ * 4, 256);
   p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
   p.off_p1 = o;   o = align_up(o + (size_t)p.gridGy * p.PA1 * 4, 256);
-  p.off_p2 = o;
+  p.off_p2 = o;   o = align_up(o + (size_t)p.gridAdj * p.PA2 * 4, 256);
   p.off_p3 = o;   o = align_up(o + (size_t)p.gridPx * p.PB * 4, 256);
   p.ws_bytes = o;
   return p;
@@ -868,6 +1102,28 @@ static int launch_fast_gy(const CUtensorMap& tg, const CUtensorMap& tq, const Fa
   return 0;
 }
 
+template <int NHALF>
+static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
+  const size_t smem = fast_gy2_smem_bytes(a.O);
+  QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
+  auto k = fast_bwd_gy2_kernel<NHALF>;
+  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelTimer kt(kKBwdPost, st);
+    k<<<p.gridGy, kGyStream, smem, st>>>(tg, tq, a);
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static bool gy_fused() {
+  static const bool v = [] {
+    const char* e = getenv("QW_GY_FUSED");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 template <int S, int PAR, bool GX>
 static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const FastPreArgs& a, const FastPlan& p, cudaStream_t st) {
   const size_t smem = fast_pre_smem_bytes<S>();
@@ -894,8 +1150,28 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
   if (int e = make_tmap_3d_f32(&tm_x, x, d.L, d.C, d.B, 32, 32, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
-  // 1) stream gy (+ adjoint circuit on a dedicated warp)
-  {
+  const bool split = !gy_fused();
+  float* gout = reinterpret_cast<float*>(ws + p.off_gout);
+  float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
+  if (split) {
+    // 1) stream gy: gout + partials of grad post_conv.{weight,bias}
+    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1};
+    const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
+    int e = nhalf == 1 ? launch_fast_gy2<1>(tm_gy, tm_qout, a, p, st)
+          : nhalf == 2 ? launch_fast_gy2<2>(tm_gy, tm_qout, a, p, st)
+                       : launch_fast_gy2<3>(tm_gy, tm_qout, a, p, st);
+    if (e) return e;
+    // 2) adjoint differentiation of the circuit, one window per thread
+    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W};
+    const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
+    if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      KernelTimer kt(kKBwdAdj, st);
+      fast_bwd_adj_kernel<<<p.gridAdj, kAdjThreads, smem, st>>>(aa);
+    }
+    QW_CUDA_OK(cudaGetLastError());
+  } else {
+    // 1) stream gy (+ adjoint circuit on dedicated warps)
     FastGyArgs a{w_post, pre_save, qwts, gpre, part1, d.B, d.O, d.Lout, p.LP, d.Lq, p.tiles_per_utt, p.num_tiles, p.PA1};
     const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
     int e = nhalf == 1 ? launch_fast_gy<1>(tm_gy, tm_qout, a, p, st)
@@ -915,8 +1191,9 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   }
   // 4) finalize
   {
-    FastFinArgs a{part1, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridPx, p.PB, d.C, d.O, d.Lq};
-    const int nblk = p.PA1 / 32 + p.PB / 32;
+    FastFinArgs a{part1, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridPx, p.PB, d.C, d.O, d.Lq,
+                  split ? part2 : nullptr, p.gridAdj, p.PA2};
+    const int nblk = p.PA1 / 32 + (split ? p.PA2 / 32 : 0) + p.PB / 32;
     {
       KernelTimer kt(kKBwdFinalize, st);
       fast_finalize_kernel<<<nblk, kFFThreads, 0, st>>>(a);

@@ -42,6 +42,14 @@ struct FastPlan {
   int ptiles_per_utt, num_ptiles, nchunks, Cpad, gridPx, PB;
   size_t off_gout, off_gpre, off_p1, off_p2, off_p3, ws_bytes;
 };
+constexpr int kHaloL = 8;    // gpre is stored halo-padded per utterance: [B][kHaloL + L_out + kHaloR][4]
+constexpr int kHaloR = 144;
+struct FastAdjArgs {
+  const float *pre_save, *gout, *qw;
+  float *gpre_pad, *part;  // part: [grid][PA2] rows: [grad pre_conv.bias 4 + pad 28][Lq*32 gate-gradient matrices M]
+  int B, Lout, LP, Lq, PA2;
+  long long W;
+};
 void set_fast_path(bool on);
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd);
 FastPlan make_fast_plan(const ConvDims& d);

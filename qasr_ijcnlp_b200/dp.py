@@ -127,6 +127,7 @@ class P2PGradAllReduce:
         self.rank = dist.get_rank(group) if inited else 0
         nbuf = self.lib.qw_grads_allreduce_p2p_buffer_bytes(self.numel) // 4
         nflag = self.lib.qw_grads_allreduce_p2p_flag_bytes(self.world) // 4
+        self.nflag = nflag
         if self.world == 1:
             self.buf = torch.zeros(nbuf, device=self.device, dtype=torch.float32)
             self.flags = torch.zeros(nflag, device=self.device, dtype=torch.int32)
@@ -136,7 +137,7 @@ class P2PGradAllReduce:
 
             grp = group if group is not None else dist.group.WORLD
             self.buf = symm_mem.empty(nbuf, dtype=torch.float32, device=self.device)
-            self.flags = symm_mem.empty(max(nflag, 64), dtype=torch.int32, device=self.device)
+            self.flags = symm_mem.empty(nflag, dtype=torch.int32, device=self.device)
             self.buf.zero_()
             self.flags.zero_()
             self._hb = symm_mem.rendezvous(self.buf, grp)
@@ -159,6 +160,10 @@ class P2PGradAllReduce:
         self._lib_mod.check(st, "qw_grads_allreduce_p2p")
         return flat
 
+    def epoch(self) -> int:
+        """Number of completed calls (read from the first chunk's epoch word; synchronises)."""
+        return int(self.flags[self.nflag - 1 - 64].item())
+
     def status(self) -> int:
         """0 ok; 1 if some call timed out waiting for a peer (synchronises)."""
-        return int(self.flags[2 * self.world + 1].item())
+        return int(self.flags[self.nflag - 1].item())
