@@ -4,6 +4,7 @@
 #include <vector>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/qw.h"
 #include "qw_common.cuh"
@@ -19,6 +20,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int pdl_mode() {
+  static const int v = [] {
+    const char* e = getenv("QW_PDL");
+    return (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;
+  }();
+  return v;
+}
 
 // ---- per-kernel event timing.  Events are recorded on the launching stream around each kernel and resolved
 // lazily in qw_profile_read (which synchronises on them).  Not usable during stream capture.

@@ -98,6 +98,31 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining; everything it does before pdl_wait() (parameter staging into shared memory, barrier init,
+// tensor-map prefetch) overlaps the predecessor's tail.  Rules kept by every kernel that uses it: (1) nothing produced by an
+// earlier kernel is read, and no global memory is written, before pdl_wait(); (2) pdl_launch() comes right after it, so at
+// most two kernels of the chain ever overlap.  QW_PDL=0 turns the launch attribute off (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// QW_PDL: 0 = never, 2 = always, unset / 1 = when the caller says the launch is latency-dominated (`small`): measured on B200,
+// PDL gains 4 % on the batch-16 stem step (5 tiles per CTA) and loses 4 % at batch 64 (20 tiles per CTA).
+int pdl_mode();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool small, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_mode() == 2 || (pdl_mode() == 1 && small)) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // streaming (evict-first) global store / load for data touched exactly once
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }

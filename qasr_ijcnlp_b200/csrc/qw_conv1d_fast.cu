@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
   if (tid < FQ) bpre[tid] = a.b_pre[tid];
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   __syncthreads();
+  pdl_wait();    // x may be the previous kernel's output; nothing global is written above
+  pdl_launch();
 
   const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total_chunks = my_tiles * a.chunks_per_tile;
@@ -577,6 +579,8 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
   }
   for (int u = tid; u < a.O; u += kGyStream) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
   __syncthreads();
+  pdl_wait();
+  pdl_launch();
 
   const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total_stages = my_tiles * NHALF;
@@ -713,6 +717,7 @@ __global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdj
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   for (int e = tid; e < 4 * NE * kGyMS; e += kAdjThreads) macc[e] = 0.f;
+  pdl_wait();
   {  // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
     const int per = (kHaloL + kHaloR) * FQ;
     for (long long idx = (long long)blockIdx.x * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kAdjThreads) {
@@ -741,6 +746,7 @@ __global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdj
 #pragma unroll
     for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
   }
+  pdl_launch();  // late: this grid is not fully resident, an early trigger would let the next kernel's CTAs take its slots
   __syncthreads();
   float* prow = a.part + (size_t)blockIdx.x * a.PA2;
   for (int e = warp; e < a.PA2; e += kAdjThreads / 32) {
@@ -798,6 +804,8 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
       gw[j][k] = 0.f;
     }
   __syncthreads();
+  pdl_wait();
+  pdl_launch();
 
   const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   auto issue = [&](int n) {
@@ -904,6 +912,8 @@ struct FastFinArgs {
 __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFinArgs a) {
   __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb1 = a.P1 / 32, nb2 = a.part2 ? a.P2 / 32 : 0;
   const bool seg1 = (int)blockIdx.x < nb1;
@@ -1022,6 +1032,7 @@ FastPlan make_fast_plan(const ConvDims& d) {
     p.gridF = p.num_tiles < per_sm * sms ? p.num_tiles : per_sm * sms;
   }
   p.gridGy = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
+  p.small = p.num_tiles <= 6 * 2 * sms;   // <= 6 tiles per CTA: launch / ramp latency matters more than steady-state streaming
   p.PA1 = gy_plen(d.O, d.Lq);
   const long long W = (long long)d.B * d.Lout;
   {
@@ -1057,7 +1068,7 @@ static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const Fa
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKFwd, st);
-    k<<<p.gridF, kFwdThreads, smem, st>>>(tm, a);
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridF), dim3(kFwdThreads), smem, st, tm, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1110,7 +1121,7 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKBwdPost, st);
-    k<<<p.gridGy, kGyStream, smem, st>>>(tg, tq, a);
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(kGyStream), smem, st, tg, tq, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1131,7 +1142,7 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKBwdPre, st);
-    k<<<dim3(p.gridPx, p.nchunks), kThreads, smem, st>>>(tx, tgx, a);
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridPx, p.nchunks), dim3(kThreads), smem, st, tx, tgx, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1167,7 +1178,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       KernelTimer kt(kKBwdAdj, st);
-      fast_bwd_adj_kernel<<<p.gridAdj, kAdjThreads, smem, st>>>(aa);
+      QW_CUDA_OK(launch_pdl(p.small, fast_bwd_adj_kernel, dim3(p.gridAdj), dim3(kAdjThreads), smem, st, aa));
     }
     QW_CUDA_OK(cudaGetLastError());
   } else {
@@ -1196,7 +1207,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     const int nblk = p.PA1 / 32 + (split ? p.PA2 / 32 : 0) + p.PB / 32;
     {
       KernelTimer kt(kKBwdFinalize, st);
-      fast_finalize_kernel<<<nblk, kFFThreads, 0, st>>>(a);
+      QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel, dim3(nblk), dim3(kFFThreads), 0, st, a));
     }
     QW_CUDA_OK(cudaGetLastError());
   }

@@ -41,6 +41,7 @@ struct FastPlan {
   int gridGy, PA1, gridAdj, PA2, LP;
   int ptiles_per_utt, num_ptiles, nchunks, Cpad, gridPx, PB;
   size_t off_gout, off_gpre, off_p1, off_p2, off_p3, ws_bytes;
+  bool small;  // latency-dominated launch: use programmatic dependent launch
 };
 constexpr int kHaloL = 8;    // gpre is stored halo-padded per utterance: [B][kHaloL + L_out + kHaloR][4]
 constexpr int kHaloR = 144;
