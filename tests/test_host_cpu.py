@@ -111,3 +111,32 @@ def test_grad_bucket_single_process():
     b.allreduce_mean()
     for p, w in zip(lin.parameters(), want):
         assert torch.equal(p.grad, w) and p.grad.data_ptr() >= b.flat.data_ptr()
+
+
+def test_reference_checkpoint_formats_load(tmp_path):
+    """a reference-style checkpoint (bare state_dict or utils.save_model dict, with the text decoder's
+    extra keys) loads into the B200 modules key for key."""
+    from qasr_ijcnlp_b200 import checkpoint as ck
+    dims = qw.ModelDimensions(n_mels=8, n_audio_ctx=10, n_audio_state=16, n_audio_head=2, n_audio_layer=1)
+    torch.manual_seed(3)
+    src = qw.QuantumWhisperClassifier(qw.QuantumWhisper(dims, n_qubits=4), 35)
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    sd["quantum_whisper.decoder.token_embedding.weight"] = torch.zeros(4, 16)  # reference-only (text decoder)
+    torch.manual_seed(4)
+    dst = qw.QuantumWhisperClassifier(qw.QuantumWhisper(dims, n_qubits=4), 35)
+    missing, ref_only = ck.load_reference_state_dict(dst, sd)
+    assert missing == [] and ref_only == ["quantum_whisper.decoder.token_embedding.weight"]
+    for (ka, a), (kb, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert ka == kb and torch.equal(a, b)
+    # utils.save_model format, through a file
+    path = str(tmp_path / "ckpt.pth")
+    torch.save({"model_state_dict": sd, "model_info": {"epoch": 3}, "training_history": {"loss": [1.0]}}, path)
+    torch.manual_seed(5)
+    dst2 = qw.QuantumWhisperClassifier(qw.QuantumWhisper(dims, n_qubits=4), 35)
+    _, hist, info = ck.load_reference_checkpoint(dst2, path)
+    assert info["epoch"] == 3 and hist["loss"] == [1.0]
+    assert torch.equal(dst2.quantum_whisper.encoder.conv2.quantum_weights, src.quantum_whisper.encoder.conv2.quantum_weights)
+    # a checkpoint trained with another n_qubits does not fit: strict load says so
+    other = qw.QuantumWhisperClassifier(qw.QuantumWhisper(dims, n_qubits=3), 35)
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        ck.load_reference_state_dict(other, sd)
