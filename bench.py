@@ -190,9 +190,12 @@ class StemParams:
         sizes = [(name, i, (t.numel() + 3) // 4 * 4) for name in self.mods for i, t in enumerate(self.p[name])]
         self.flat_grads = torch.zeros(sum(n for _, _, n in sizes), device=dev)
         off = 0
+        self.span = {}  # layer -> (start, end) inside the flat bucket
         for name, i, n in sizes:
             t = self.p[name][i]
             self.g.setdefault(name, []).append(self.flat_grads[off:off + t.numel()].view_as(t))
+            lo, _ = self.span.get(name, (off, off))
+            self.span[name] = (lo, off + n)
             off += n
 
 
@@ -232,11 +235,30 @@ class StemRunner:
         self.fwd("conv1", s)
         self.fwd("conv2", s)
         self.bwd("conv2", s)
+        if self.allreduce_split is not None:
+            # conv2's gradients are final: reduce them on a side stream while conv1's backward runs; only conv1's (smaller)
+            # bucket is reduced on the critical path
+            ar1, ar2, side = self.allreduce_split
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            lo, hi = self.params.span["conv2"]
+            with torch.cuda.stream(side):
+                ar2(self.params.flat_grads[lo:hi])
+                ev2 = torch.cuda.Event()
+                ev2.record(side)
+            self.bwd("conv1", s)
+            lo, hi = self.params.span["conv1"]
+            ar1(self.params.flat_grads[lo:hi])
+            main.wait_event(ev2)
+            return
         self.bwd("conv1", s)
         if self.allreduce is not None:
             self.allreduce(self.params.flat_grads)
 
-    allreduce = None                 # set by run_b200 when world > 1
+    allreduce = None                 # set by run_b200 when world > 1 (single collective at the end of the step)
+    allreduce_split = None           # or (reducer conv1, reducer conv2, side stream): per-layer buckets, conv2's overlapped
 
 
 def algorithmic_bytes(kernel, layer, B):
@@ -298,8 +320,11 @@ def run_b200(args):
         try:
             if args.collective == "nccl":
                 raise RuntimeError("forced")
-            runner.allreduce = dp.P2PGradAllReduce(n, dev)
-            collective = f"own one-shot NVLink peer-memory all-reduce kernel ({4 * n} B bucket, fused 1/N scale, in the step's CUDA graph)"
+            sp = runner.params.span
+            n1, n2 = sp["conv1"][1] - sp["conv1"][0], sp["conv2"][1] - sp["conv2"][0]
+            runner.allreduce_split = (dp.P2PGradAllReduce(n1, dev), dp.P2PGradAllReduce(n2, dev), torch.cuda.Stream())
+            collective = (f"own one-shot NVLink peer-memory all-reduce kernel, fused 1/N scale, in the step's CUDA graph: conv2's "
+                          f"{4 * n2} B bucket on a side stream under conv1's backward, conv1's {4 * n1} B bucket at the end")
         except Exception as e:  # symmetric memory unavailable -> NCCL
             flat = runner.params.flat_grads
             runner.allreduce = lambda t: torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG)
@@ -326,8 +351,13 @@ def run_b200(args):
     try:
         graphs = capture()
     except Exception as e:  # a collective that cannot be captured: keep it eager, right behind the graph
-        if runner.allreduce is None:
+        if runner.allreduce is None and runner.allreduce_split is None:
             raise
+        if runner.allreduce_split is not None:
+            ar1, ar2, _ = runner.allreduce_split
+            sp = runner.params.span
+            runner.allreduce_split = None
+            runner.allreduce = lambda t: (ar2(t[sp["conv2"][0]:sp["conv2"][1]]), ar1(t[sp["conv1"][0]:sp["conv1"][1]]))
         post, runner.allreduce = runner.allreduce, None
         collective += f" [not capturable: {type(e).__name__}; issued eagerly after the graph]"
         torch.cuda.synchronize()

@@ -19,7 +19,7 @@ emb = {"amplitude": 0, "angle": 1}[a.embedding]
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
     if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}
 HBM = peaks["hbm_gbs"] * 1e9
-FMA = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6  # fp32 flop/s at max clock (not measured by the driver)
+FMA = 69.4e12  # fp32 FMA flop/s measured on B200 by tools/probe/ffma2_probe.cu (profiles/r1_fp32_issue_probe.txt; theoretical 74.4)
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 rows = []
