@@ -1016,7 +1016,10 @@ bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const 
 // which 160 run a third tile) is SLOWER (step 0.1435 -> 0.1525 ms): the kernels are bound by per-CTA pipeline latency, not by
 // shared HBM bandwidth, so an SM left with one CTA loses more than the ragged last round costs.  Likewise a 4-lanes-per-window
 // adjoint (shorter dependency chain, 4x the warps) lost to one window per thread (17.6 vs 10.9 us): shuffles + the CNOT pass
-// through shared memory outweigh the chain shortening at q = 4.
+// through shared memory outweigh the chain shortening at q = 4.  Packed fp32x2 FMAs (FFMA2, __ffma2_rn) in the two contractions
+// of fast_bwd_gy2_kernel: no change (26.3 / 19.0 us vs 26.7 / 19.1 us) -- FFMA2 issues at ~0.42x the FFMA rate
+// (profiles/r1_fp32_issue_probe.txt) and the kernel is bound by shared-memory / barrier latency at 3 warps per scheduler, not by
+// FMA issue slots.
 FastPlan make_fast_plan(const ConvDims& d) {
   FastPlan p{};
   const int sms = num_sms();
