@@ -86,6 +86,13 @@ int qw_circuit_backward_f64(const double* pre, const double* qw, const double* g
 size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels);
 int qw_log_mel(const float* audio, const float* filters, float* mel, void* workspace, size_t ws_bytes, int B,
                int n_samples, int n_mels, void* stream);
+/* The same in two steps, for callers that keep the filterbank (mel_filters(), audio.py:91-107, is a constant asset):
+ * qw_log_mel_prepare analyses `filters` once into `prep` (qw_log_mel_prep_bytes(n_mels) bytes, 256-byte aligned, caller-owned);
+ * qw_log_mel_prepared then needs only B floats of workspace and skips the analysis kernel on every call. */
+size_t qw_log_mel_prep_bytes(int n_mels);
+int qw_log_mel_prepare(const float* filters, int n_mels, void* prep, size_t prep_bytes, void* stream);
+int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B,
+                        int n_samples, int n_mels, void* stream);
 
 /* ---- data-parallel training collective (the reference is single-process, train_quantum_whisper.py:195-214):
  * one-shot all-reduce of a small fp32 gradient bucket over NVLink peer memory, fused with the `scale` (1/world) multiply.

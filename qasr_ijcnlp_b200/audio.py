@@ -82,6 +82,24 @@ def _mel_filterbank_np(n_mels: int) -> np.ndarray:
 
 
 _FILTER_CACHE = {}
+_PREP_CACHE = {}
+
+
+def _prepared_filters(device, n_mels: int) -> torch.Tensor:
+    """Device buffer holding the library's one-time analysis of the filterbank (qw_log_mel_prepare), cached per device."""
+    key = (str(device), n_mels)
+    if key not in _PREP_CACHE:
+        lib = _lib.load()
+        filt = mel_filters(device, n_mels)
+        n = lib.qw_log_mel_prep_bytes(n_mels)
+        prep = torch.empty(n, device=device, dtype=torch.uint8)
+        with torch.cuda.device(device):
+            st = lib.qw_log_mel_prepare(ctypes.c_void_p(filt.data_ptr()), n_mels, ctypes.c_void_p(prep.data_ptr()), n,
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(st, "qw_log_mel_prepare")
+        torch.cuda.current_stream(device).synchronize()  # later calls may come from other streams
+        _PREP_CACHE[key] = prep
+    return _PREP_CACHE[key]
 
 
 def mel_filters(device, n_mels: int) -> torch.Tensor:
@@ -121,13 +139,12 @@ def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80
         raise ValueError(f"n_samples={n} must be a multiple of {HOP_LENGTH} (use pad_or_trim)")
     lib = _lib.load()
     T = n // HOP_LENGTH
-    filt = mel_filters(a.device, n_mels)
+    prep = _prepared_filters(a.device, n_mels)
     mel = torch.empty(B, n_mels, T, device=a.device, dtype=torch.float32)
-    nbytes = lib.qw_log_mel_workspace_bytes(B, n, n_mels)
-    ws = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
+    ws = torch.empty(B, device=a.device, dtype=torch.float32)
     with torch.cuda.device(a.device):
-        st = lib.qw_log_mel(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(filt.data_ptr()), ctypes.c_void_p(mel.data_ptr()),
-                            ctypes.c_void_p(ws.data_ptr()), nbytes, B, n, n_mels,
-                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    _lib.check(st, "qw_log_mel")
+        st = lib.qw_log_mel_prepared(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(prep.data_ptr()), ctypes.c_void_p(mel.data_ptr()),
+                                     ctypes.c_void_p(ws.data_ptr()), 4 * B, B, n, n_mels,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "qw_log_mel_prepared")
     return mel[0] if single else mel

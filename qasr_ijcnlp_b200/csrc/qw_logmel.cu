@@ -46,6 +46,7 @@ struct Args {
   const Meta* meta;
   const float* vals;
   int B, n, T, n_mels, tiles_per_utt, num_tiles;
+
 };
 
 __global__ void __launch_bounds__(1024) logmel_prep_kernel(const float* __restrict__ filters, int n_mels, Meta* meta, float* vals) {
@@ -143,13 +144,13 @@ __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
 
   if ((int)blockIdx.x < a.num_tiles) fill(blockIdx.x);
   const int nnz = a.meta->total;
-  const bool cached = nnz <= kMaxNnz;
+  const bool CACHED = nnz <= kMaxNnz;  // uniform across the grid
   for (int m = tid; m < a.n_mels; m += NT) {
     mlo[m] = a.meta->lo[m];
     mhi[m] = a.meta->hi[m];
     moff[m] = a.meta->off[m];
   }
-  if (cached)
+  if (CACHED)
     for (int e = tid; e < nnz; e += NT) fvals[e] = a.vals[e];
 
   SmemCol col{work + lane};
@@ -170,18 +171,25 @@ __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
     float vmax = -INFINITY;
     for (int m = g; m < a.n_mels; m += G) {
       const int lo = mlo[m], hi = mhi[m];
-      const float* fv = (cached ? fvals : a.vals) + moff[m];
       const bool top = hi == kNfreq;          // P[200] lives at float slot 1, everything else at float 2k
       const int n = (top ? 200 : hi) - lo;
       const float* pw = work + lane + 2 * kFrames * lo;
       float acc0 = 0.f, acc1 = 0.f;
-      int e = 0;
-      for (; e + 1 < n; e += 2) {
-        acc0 = fmaf(fv[e], pw[e * 2 * kFrames], acc0);
-        acc1 = fmaf(fv[e + 1], pw[(e + 1) * 2 * kFrames], acc1);
+      if (CACHED) {  // filter values from shared memory (shared-space pointer: LDS with immediate offsets)
+        const float* fv = fvals + moff[m];
+        int e = 0;
+#pragma unroll 2
+        for (; e + 1 < n; e += 2) {
+          acc0 = fmaf(fv[e], pw[e * 2 * kFrames], acc0);
+          acc1 = fmaf(fv[e + 1], pw[(e + 1) * 2 * kFrames], acc1);
+        }
+        if (e < n) acc0 = fmaf(fv[e], pw[e * 2 * kFrames], acc0);
+        if (top) acc1 = fmaf(fv[200 - lo], work[kFrames + lane], acc1);
+      } else {       // dense / very wide filter banks: values stay in global memory
+        const float* fv = a.vals + moff[m];
+        for (int e = 0; e < n; ++e) acc0 = fmaf(__ldg(fv + e), pw[e * 2 * kFrames], acc0);
+        if (top) acc1 = fmaf(__ldg(fv + 200 - lo), work[kFrames + lane], acc1);
       }
-      if (e < n) acc0 = fmaf(fv[e], pw[e * 2 * kFrames], acc0);
-      if (top) acc1 = fmaf(fv[200 - lo], work[kFrames + lane], acc1);
       const float v = 0.30102999566398120f * __log2f(fmaxf(acc0 + acc1, 1e-10f));  // audio.py:154
       if (t < a.T) {
         a.mel[((size_t)b * a.n_mels + m) * a.T + t] = v;
@@ -240,37 +248,29 @@ static int launch_stft(const Args& a, cudaStream_t st) {
 }  // namespace lm
 }  // namespace qw
 
-extern "C" {
+namespace qw {
+namespace lm {
+static size_t prep_bytes(int n_mels) { return sizeof(Meta) + align_up((size_t)n_mels * kNfreq * sizeof(float), 256); }
 
-size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels) {
-  if (B <= 0 || n_samples <= 0 || n_mels <= 0) return 0;
-  return qw::align_up((size_t)B * sizeof(float), 256) + sizeof(qw::lm::Meta) +
-         qw::align_up((size_t)n_mels * qw::lm::kNfreq * sizeof(float), 256);
+static int run_prepare(const float* filters, int n_mels, void* prep, cudaStream_t st) {
+  Meta* meta = (Meta*)prep;
+  float* vals = (float*)((unsigned char*)prep + sizeof(Meta));
+  {
+    KernelTimer kt(kKLogMelPrep, st);
+    logmel_prep_kernel<<<1, 1024, 0, st>>>(filters, n_mels, meta, vals);
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
-int qw_log_mel(const float* audio, const float* filters, float* mel, void* workspace, size_t ws_bytes, int B, int n_samples,
-               int n_mels, void* stream) {
-  using namespace qw;
-  using namespace qw::lm;
-  QW_CHECK_ARG(audio && filters && mel && workspace, -1, "qw_log_mel: null pointer argument");
-  QW_CHECK_ARG(B > 0 && n_mels > 0 && n_mels <= kMaxMels, -1, "qw_log_mel: bad shape B=%d n_mels=%d (n_mels <= %d)", B, n_mels,
-               kMaxMels);
-  QW_CHECK_ARG(n_samples > kNfft / 2 && n_samples % kHop == 0, -1,
-               "qw_log_mel: n_samples=%d must be a multiple of %d and > %d (reflect padding)", n_samples, kHop, kNfft / 2);
-  QW_CHECK_ARG(ws_bytes >= qw_log_mel_workspace_bytes(B, n_samples, n_mels), -3, "qw_log_mel: workspace too small");
-  QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "qw_log_mel: workspace must be 256-byte aligned");
-  QW_CHECK_ARG((long long)B * n_samples < (1LL << 40), -1, "qw_log_mel: tensor too large");
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned char* ws = (unsigned char*)workspace;
+static int run_prepared(const float* audio, const void* prep, float* mel, float* umax, int B, int n_samples, int n_mels, cudaStream_t st) {
   Args a{};
   a.audio = audio;
-  a.filters = filters;
+  a.filters = nullptr;
   a.mel = mel;
-  a.umax = (float*)ws;
-  Meta* meta = (Meta*)(ws + align_up((size_t)B * sizeof(float), 256));
-  float* vals = (float*)((unsigned char*)meta + sizeof(Meta));
-  a.meta = meta;
-  a.vals = vals;
+  a.umax = umax;
+  a.meta = (const Meta*)prep;
+  a.vals = (const float*)((const unsigned char*)prep + sizeof(Meta));
   a.B = B;
   a.n = n_samples;
   a.T = n_samples / kHop;  // frame T (the 3001st for 30 s) is dropped, audio.py:149
@@ -278,11 +278,6 @@ int qw_log_mel(const float* audio, const float* filters, float* mel, void* works
   a.tiles_per_utt = (a.T + kFrames - 1) / kFrames;
   a.num_tiles = B * a.tiles_per_utt;
   QW_CUDA_OK(cudaMemsetAsync(a.umax, 0xff, (size_t)B * sizeof(float), st));
-  {
-    KernelTimer kt(kKLogMelPrep, st);
-    logmel_prep_kernel<<<1, 1024, 0, st>>>(filters, n_mels, meta, vals);
-  }
-  QW_CUDA_OK(cudaGetLastError());
   if (g_warps == 0) {
     const char* e = getenv("QW_LOGMEL_WARPS");
     g_warps = (e && atoi(e) == 4) ? 4 : 8;
@@ -300,6 +295,57 @@ int qw_log_mel(const float* audio, const float* filters, float* mel, void* works
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static int check_shape(int B, int n_samples, int n_mels) {
+  QW_CHECK_ARG(B > 0 && n_mels > 0 && n_mels <= kMaxMels, -1, "qw_log_mel: bad shape B=%d n_mels=%d (n_mels <= %d)", B, n_mels, kMaxMels);
+  QW_CHECK_ARG(n_samples > kNfft / 2 && n_samples % kHop == 0, -1,
+               "qw_log_mel: n_samples=%d must be a multiple of %d and > %d (reflect padding)", n_samples, kHop, kNfft / 2);
+  QW_CHECK_ARG((long long)B * n_samples < (1LL << 40), -1, "qw_log_mel: tensor too large");
+  return 0;
+}
+}  // namespace lm
+}  // namespace qw
+
+extern "C" {
+
+size_t qw_log_mel_prep_bytes(int n_mels) { return n_mels > 0 ? qw::lm::prep_bytes(n_mels) : 0; }
+
+int qw_log_mel_prepare(const float* filters, int n_mels, void* prep, size_t prep_bytes, void* stream) {
+  using namespace qw;
+  QW_CHECK_ARG(filters && prep, -1, "qw_log_mel_prepare: null pointer argument");
+  QW_CHECK_ARG(n_mels > 0 && n_mels <= lm::kMaxMels, -1, "qw_log_mel_prepare: n_mels=%d outside [1, %d]", n_mels, lm::kMaxMels);
+  QW_CHECK_ARG(prep_bytes >= lm::prep_bytes(n_mels), -3, "qw_log_mel_prepare: prep buffer too small");
+  QW_CHECK_ARG(((uintptr_t)prep & 255) == 0, -1, "qw_log_mel_prepare: prep buffer must be 256-byte aligned");
+  return lm::run_prepare(filters, n_mels, prep, (cudaStream_t)stream);
+}
+
+int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B, int n_samples,
+                        int n_mels, void* stream) {
+  using namespace qw;
+  QW_CHECK_ARG(audio && prep && mel && workspace, -1, "qw_log_mel_prepared: null pointer argument");
+  if (int e = lm::check_shape(B, n_samples, n_mels)) return e;
+  QW_CHECK_ARG(ws_bytes >= (size_t)B * sizeof(float), -3, "qw_log_mel_prepared: workspace too small (B floats)");
+  QW_CHECK_ARG(((uintptr_t)prep & 255) == 0 && ((uintptr_t)workspace & 3) == 0, -1, "qw_log_mel_prepared: misaligned buffer");
+  return lm::run_prepared(audio, prep, mel, (float*)workspace, B, n_samples, n_mels, (cudaStream_t)stream);
+}
+
+size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels) {
+  if (B <= 0 || n_samples <= 0 || n_mels <= 0) return 0;
+  return qw::align_up((size_t)B * sizeof(float), 256) + qw::lm::prep_bytes(n_mels);
+}
+
+int qw_log_mel(const float* audio, const float* filters, float* mel, void* workspace, size_t ws_bytes, int B, int n_samples,
+               int n_mels, void* stream) {
+  using namespace qw;
+  QW_CHECK_ARG(audio && filters && mel && workspace, -1, "qw_log_mel: null pointer argument");
+  if (int e = lm::check_shape(B, n_samples, n_mels)) return e;
+  QW_CHECK_ARG(ws_bytes >= qw_log_mel_workspace_bytes(B, n_samples, n_mels), -3, "qw_log_mel: workspace too small");
+  QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "qw_log_mel: workspace must be 256-byte aligned");
+  unsigned char* ws = (unsigned char*)workspace;
+  void* prep = ws + align_up((size_t)B * sizeof(float), 256);
+  if (int e = lm::run_prepare(filters, n_mels, prep, (cudaStream_t)stream)) return e;
+  return lm::run_prepared(audio, prep, mel, (float*)ws, B, n_samples, n_mels, (cudaStream_t)stream);
 }
 
 }  // extern "C"
