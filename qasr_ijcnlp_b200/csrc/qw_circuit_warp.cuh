@@ -37,6 +37,8 @@ struct Cfg {
   static constexpr int GPC = THREADS / TG;          // windows (groups) per CTA iteration
   static constexpr int WARPS = THREADS / 32;
   static constexpr int GS = NT == 0 ? 0 : 2 * N + TG;  // exchange-buffer elements per group (re plane, im plane, skew)
+  // (measured: capping the adjoint kernel's registers through __launch_bounds__ min-CTAs -- 255 -> 168 at R = 5, 168 -> 128
+  // at R = 4 -- changes nothing, q = 8: -7 %, q = 10: +2 %; the kernels are not occupancy-bound.  Not applied.)
 };
 
 template <typename T>
@@ -71,31 +73,36 @@ __device__ __forceinline__ void group_sync() {
   else if constexpr (Cfg<Q>::TG > 1) __syncwarp();
 }
 
-// partner's copy of (vr, vi)[r] across thread bit P
+// Access to the partner thread's copy of (vr, vi)[r] across thread bit P, ELEMENT BY ELEMENT (no NR-sized staging buffer in
+// registers: at R = 5 that buffer alone was 64 registers and pinned the adjoint kernels at 255 registers / 2 warps per
+// scheduler).  Lane bits: a pair of __shfl_xor per element.  Warp bits (Q >= 11): the whole register file of the group goes
+// through the exchange buffer once (partner_begin), elements are then read from the partner's slot, partner_end closes it.
 template <typename T, int Q, int P>
-__device__ __forceinline__ void fetch_partner(const T (&vr)[Cfg<Q>::NR], const T (&vi)[Cfg<Q>::NR], T (&qr)[Cfg<Q>::NR],
-                                              T (&qi)[Cfg<Q>::NR], const Ctx<T>& c) {
+__device__ __forceinline__ void partner_begin(const T (&vr)[Cfg<Q>::NR], const T (&vi)[Cfg<Q>::NR], const Ctx<T>& c) {
   using C = Cfg<Q>;
-  if constexpr (P < 5) {
-#pragma unroll
-    for (int r = 0; r < C::NR; ++r) {
-      qr[r] = __shfl_xor_sync(0xffffffffu, vr[r], 1 << P);
-      qi[r] = __shfl_xor_sync(0xffffffffu, vi[r], 1 << P);
-    }
-  } else {
+  if constexpr (P >= 5) {
 #pragma unroll
     for (int r = 0; r < C::NR; ++r) {
       c.xr[r * C::TG + c.tsub] = vr[r];
       c.xi[r * C::TG + c.tsub] = vi[r];
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < C::NR; ++r) {
-      qr[r] = c.xr[r * C::TG + (c.tsub ^ (1 << P))];
-      qi[r] = c.xi[r * C::TG + (c.tsub ^ (1 << P))];
-    }
-    __syncthreads();
   }
+}
+template <typename T, int Q, int P>
+__device__ __forceinline__ void partner_get(T mr, T mi, int r, const Ctx<T>& c, T& qr, T& qi) {
+  using C = Cfg<Q>;
+  if constexpr (P < 5) {
+    qr = __shfl_xor_sync(0xffffffffu, mr, 1 << P);
+    qi = __shfl_xor_sync(0xffffffffu, mi, 1 << P);
+  } else {
+    qr = c.xr[r * C::TG + (c.tsub ^ (1 << P))];
+    qi = c.xi[r * C::TG + (c.tsub ^ (1 << P))];
+  }
+}
+template <int Q, int P>
+__device__ __forceinline__ void partner_end() {
+  if constexpr (P >= 5) __syncthreads();
 }
 
 // g: 8 reals, row-major complex 2x2 (00r 00i 01r 01i 10r 10i 11r 11i) acting on bit position P
@@ -119,14 +126,16 @@ __device__ __forceinline__ void apply_gate_w(T (&re)[Cfg<Q>::NR], T (&im)[Cfg<Q>
     const bool hi = (c.tsub >> P) & 1;
     const T ar = hi ? g[6] : g[0], ai = hi ? g[7] : g[1];  // coefficient of my own amplitude
     const T br = hi ? g[4] : g[2], bi = hi ? g[5] : g[3];  // coefficient of the partner's
-    T qr[C::NR], qi[C::NR];
-    fetch_partner<T, Q, P>(re, im, qr, qi, c);
+    partner_begin<T, Q, P>(re, im, c);
 #pragma unroll
     for (int r = 0; r < C::NR; ++r) {
       const T mr = re[r], mi = im[r];
-      re[r] = ar * mr - ai * mi + br * qr[r] - bi * qi[r];
-      im[r] = ar * mi + ai * mr + br * qi[r] + bi * qr[r];
+      T qr, qi;
+      partner_get<T, Q, P>(mr, mi, r, c, qr, qi);
+      re[r] = ar * mr - ai * mi + br * qr - bi * qi;
+      im[r] = ar * mi + ai * mr + br * qi + bi * qr;
     }
+    partner_end<Q, P>();
   }
 }
 
@@ -350,31 +359,36 @@ __device__ __forceinline__ void adj_gate_w(T (&pr)[Cfg<Q>::NR], T (&pi)[Cfg<Q>::
     const bool hi = (c.tsub >> P) & 1;
     const T ar = hi ? gd[6] : gd[0], ai = hi ? gd[7] : gd[1];
     const T br = hi ? gd[4] : gd[2], bi = hi ? gd[5] : gd[3];
-    T qr[C::NR], qi[C::NR];
-    fetch_partner<T, Q, P>(pr, pi, qr, qi, c);
     T mmr = T(0), mmi = T(0), mpr = T(0), mpi = T(0);
+    partner_begin<T, Q, P>(pr, pi, c);
 #pragma unroll
     for (int r = 0; r < C::NR; ++r) {
-      mmr += lr[r] * pr[r] + li[r] * pi[r];
-      mmi += lr[r] * pi[r] - li[r] * pr[r];
-      mpr += lr[r] * qr[r] + li[r] * qi[r];
-      mpi += lr[r] * qi[r] - li[r] * qr[r];
       const T mr = pr[r], mi = pi[r];
-      pr[r] = ar * mr - ai * mi + br * qr[r] - bi * qi[r];
-      pi[r] = ar * mi + ai * mr + br * qi[r] + bi * qr[r];
+      T qr, qi;
+      partner_get<T, Q, P>(mr, mi, r, c, qr, qi);
+      mmr += lr[r] * mr + li[r] * mi;
+      mmi += lr[r] * mi - li[r] * mr;
+      mpr += lr[r] * qr + li[r] * qi;
+      mpi += lr[r] * qi - li[r] * qr;
+      pr[r] = ar * mr - ai * mi + br * qr - bi * qi;
+      pi[r] = ar * mi + ai * mr + br * qi + bi * qr;
     }
+    partner_end<Q, P>();
     // row a = my bit; column = my bit (mm) / the other bit (mp)
     n[0] = hi ? T(0) : mmr;  n[1] = hi ? T(0) : mmi;
     n[2] = hi ? T(0) : mpr;  n[3] = hi ? T(0) : mpi;
     n[4] = hi ? mpr : T(0);  n[5] = hi ? mpi : T(0);
     n[6] = hi ? mmr : T(0);  n[7] = hi ? mmi : T(0);
-    fetch_partner<T, Q, P>(lr, li, qr, qi, c);
+    partner_begin<T, Q, P>(lr, li, c);
 #pragma unroll
     for (int r = 0; r < C::NR; ++r) {
       const T mr = lr[r], mi = li[r];
-      lr[r] = ar * mr - ai * mi + br * qr[r] - bi * qi[r];
-      li[r] = ar * mi + ai * mr + br * qi[r] + bi * qr[r];
+      T qr, qi;
+      partner_get<T, Q, P>(mr, mi, r, c, qr, qi);
+      lr[r] = ar * mr - ai * mi + br * qr - bi * qi;
+      li[r] = ar * mi + ai * mr + br * qi + bi * qr;
     }
+    partner_end<Q, P>();
   }
   warp_reduce8_acc<T>(n, nacc, c.lane);
 }
@@ -416,16 +430,18 @@ struct AngleGrad {
         }
       } else {
         const bool b = (c.tsub >> P) & 1;
-        T qr[C::NR], qi[C::NR];
-        fetch_partner<T, Q, P>(pr, pi, qr, qi, c);
         const T dr = b ? T(0.5) * cx : T(-0.5) * cx, di = T(0.5) * sx;
         const T sgn = b ? T(0.5) : T(-0.5);
+        partner_begin<T, Q, P>(pr, pi, c);
 #pragma unroll
         for (int r = 0; r < C::NR; ++r) {
-          const T vr = -sgn * pi[r] + dr * qr[r] - di * qi[r];
-          const T vi = sgn * pr[r] + dr * qi[r] + di * qr[r];
+          T qr, qi;
+          partner_get<T, Q, P>(pr[r], pi[r], r, c, qr, qi);
+          const T vr = -sgn * pi[r] + dr * qr - di * qi;
+          const T vi = sgn * pr[r] + dr * qi + di * qr;
           t += lr[r] * vr + li[r] * vi;
         }
+        partner_end<Q, P>();
       }
       gpre[i] = T(2) * t;
       AngleGrad<T, Q, P + 1>::run(pr, pi, lr, li, pre, gpre, c);
