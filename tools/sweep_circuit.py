@@ -44,7 +44,9 @@ for q in (4, 6, 8, 10, 12):
         t_f, t_b = ms["circuit_fwd_kernel"], ms["circuit_bwd_kernel"] + ms.get("circuit_finalize_kernel", 0.0)
         N = 1 << q
         flop_f = 14.0 * q * N * Lq + (3 + q) * N
-        flop_fb = flop_f * 4.0                             # fwd + (recompute + 2 adjoint sweeps + products) ~ 3x
+        # fwd + adjoint backward: recompute (1x) + un-apply psi (1x) + un-apply lambda (1x) + gate-gradient products
+        # (8 of 14 flop per amplitude-gate, 0.6x) = 4.6x the forward flops; the adjoint method keeps no state per window
+        flop_fb = flop_f * 4.6
         bytes_fb = 4.0 * q * (2 + 3)                       # fwd: pre in, out out; bwd: pre, gout in, gpre out
         ceil = min(FMA / flop_fb, HBM / bytes_fb)
         wps = W / ((t_f + t_b) * 1e-3)
