@@ -139,12 +139,77 @@ __device__ __forceinline__ void apply_gate_w(T (&re)[Cfg<Q>::NR], T (&im)[Cfg<Q>
   }
 }
 
+// lane-bit gate with a RUN-TIME bit position (P < min(NT, 5)): the code of the five lane-bit gates differs only in the shuffle
+// mask, so one body in a rolled loop replaces five unrolled copies.  ncu showed these kernels starved for instructions
+// (stall "no_inst" 42 % forward / 64 % backward at q = 10: ~50 / ~200 KB of straight-line SASS per layer body).
+template <typename T, int Q>
+__device__ __forceinline__ void apply_gate_lane_rt(T (&re)[Cfg<Q>::NR], T (&im)[Cfg<Q>::NR], const T* __restrict__ g, int P,
+                                                   const Ctx<T>& c) {
+  using C = Cfg<Q>;
+  const bool hi = (c.tsub >> P) & 1;
+  const int mask = 1 << P;
+  const T ar = hi ? g[6] : g[0], ai = hi ? g[7] : g[1];
+  const T br = hi ? g[4] : g[2], bi = hi ? g[5] : g[3];
+#pragma unroll
+  for (int r = 0; r < C::NR; ++r) {
+    const T mr = re[r], mi = im[r];
+    const T qr = __shfl_xor_sync(0xffffffffu, mr, mask), qi = __shfl_xor_sync(0xffffffffu, mi, mask);
+    re[r] = ar * mr - ai * mi + br * qr - bi * qi;
+    im[r] = ar * mi + ai * mr + br * qi + bi * qr;
+  }
+}
+
+// new[j] = old[rol(j)]: the amplitude at register index (b_{R-1} ... b_1 b_0) moves to (b_0 b_{R-1} ... b_1), i.e. register bit
+// i+1 becomes bit i.  R rotations are the identity, so a rolled loop "gate on register bit 0; rotate" visits every register
+// bit with ONE copy of the gate code (2 NR moves per gate buy a 5x smaller loop body that fits the instruction cache).
+template <typename T, int Q>
+__device__ __forceinline__ void rotate_regs(T (&re)[Cfg<Q>::NR], T (&im)[Cfg<Q>::NR]) {
+  using C = Cfg<Q>;
+  if constexpr (C::R >= 2) {
+    T nr[C::NR], ni[C::NR];
+#pragma unroll
+    for (int j = 0; j < C::NR; ++j) {
+      const int src = ((j << 1) | (j >> (C::R - 1))) & (C::NR - 1);
+      nr[j] = re[src];
+      ni[j] = im[src];
+    }
+#pragma unroll
+    for (int j = 0; j < C::NR; ++j) {
+      re[j] = nr[j];
+      im[j] = ni[j];
+    }
+  }
+}
+
 template <typename T, int Q, int P>
-struct FwdGates {
+struct FwdGatesFrom {  // compile-time bit positions P .. Q-1 (warp bits and register bits)
   static __device__ __forceinline__ void run(T (&re)[Cfg<Q>::NR], T (&im)[Cfg<Q>::NR], const T* __restrict__ gl, const Ctx<T>& c) {
     if constexpr (P < Q) {
       apply_gate_w<T, Q, P>(re, im, gl + (Q - 1 - P) * kGateStride, c);
-      FwdGates<T, Q, P + 1>::run(re, im, gl, c);
+      FwdGatesFrom<T, Q, P + 1>::run(re, im, gl, c);
+    }
+  }
+};
+
+template <typename T, int Q, int P>
+struct FwdGates {  // one Rot layer; P is kept for source compatibility (always instantiated with 0)
+  static __device__ __forceinline__ void run(T (&re)[Cfg<Q>::NR], T (&im)[Cfg<Q>::NR], const T* __restrict__ gl, const Ctx<T>& c) {
+    using C = Cfg<Q>;
+    constexpr int NTL = C::NT < 5 ? C::NT : 5;
+#pragma unroll 1
+    for (int p = 0; p < NTL; ++p) apply_gate_lane_rt<T, Q>(re, im, gl + (Q - 1 - p) * kGateStride, p, c);
+    if constexpr (C::NT > NTL) {  // warp bits (Q >= 11): through the exchange buffer, unrolled (1 or 2 gates)
+      apply_gate_w<T, Q, 5>(re, im, gl + (Q - 1 - 5) * kGateStride, c);
+      if constexpr (C::NT > 6) apply_gate_w<T, Q, 6>(re, im, gl + (Q - 1 - 6) * kGateStride, c);
+    }
+    if constexpr (C::R >= 3) {    // register bits: one copy of the bit-0 gate, rolled over the R bits by register rotation
+#pragma unroll 1
+      for (int i = 0; i < C::R; ++i) {
+        apply_gate_w<T, Q, C::NT>(re, im, gl + (Q - 1 - C::NT - i) * kGateStride, c);
+        rotate_regs<T, Q>(re, im);
+      }
+    } else {
+      FwdGatesFrom<T, Q, C::NT>::run(re, im, gl, c);
     }
   }
 };
@@ -393,14 +458,73 @@ __device__ __forceinline__ void adj_gate_w(T (&pr)[Cfg<Q>::NR], T (&pi)[Cfg<Q>::
   warp_reduce8_acc<T>(n, nacc, c.lane);
 }
 
-template <typename T, int Q, int P>
-struct AdjGates {
+// adjoint sweep of one lane-bit gate with a run-time bit position (see apply_gate_lane_rt)
+template <typename T, int Q>
+__device__ __forceinline__ void adj_gate_lane_rt(T (&pr)[Cfg<Q>::NR], T (&pi)[Cfg<Q>::NR], T (&lr)[Cfg<Q>::NR], T (&li)[Cfg<Q>::NR],
+                                                 const T* __restrict__ gd, T* nacc, int P, const Ctx<T>& c) {
+  using C = Cfg<Q>;
+  const bool hi = (c.tsub >> P) & 1;
+  const int mask = 1 << P;
+  const T ar = hi ? gd[6] : gd[0], ai = hi ? gd[7] : gd[1];
+  const T br = hi ? gd[4] : gd[2], bi = hi ? gd[5] : gd[3];
+  T mmr = T(0), mmi = T(0), mpr = T(0), mpi = T(0);
+#pragma unroll
+  for (int r = 0; r < C::NR; ++r) {
+    const T mr = pr[r], mi = pi[r];
+    const T qr = __shfl_xor_sync(0xffffffffu, mr, mask), qi = __shfl_xor_sync(0xffffffffu, mi, mask);
+    mmr += lr[r] * mr + li[r] * mi;
+    mmi += lr[r] * mi - li[r] * mr;
+    mpr += lr[r] * qr + li[r] * qi;
+    mpi += lr[r] * qi - li[r] * qr;
+    pr[r] = ar * mr - ai * mi + br * qr - bi * qi;
+    pi[r] = ar * mi + ai * mr + br * qi + bi * qr;
+  }
+  T n[8];
+  n[0] = hi ? T(0) : mmr;  n[1] = hi ? T(0) : mmi;
+  n[2] = hi ? T(0) : mpr;  n[3] = hi ? T(0) : mpi;
+  n[4] = hi ? mpr : T(0);  n[5] = hi ? mpi : T(0);
+  n[6] = hi ? mmr : T(0);  n[7] = hi ? mmi : T(0);
+#pragma unroll
+  for (int r = 0; r < C::NR; ++r) {
+    const T mr = lr[r], mi = li[r];
+    const T qr = __shfl_xor_sync(0xffffffffu, mr, mask), qi = __shfl_xor_sync(0xffffffffu, mi, mask);
+    lr[r] = ar * mr - ai * mi + br * qr - bi * qi;
+    li[r] = ar * mi + ai * mr + br * qi + bi * qr;
+  }
+  warp_reduce8_acc<T>(n, nacc, c.lane);
+}
+
+template <typename T, int Q, int P, int PLO>
+struct AdjGatesDown {  // compile-time bit positions P down to PLO (register bits and warp bits)
   static __device__ __forceinline__ void run(T (&pr)[Cfg<Q>::NR], T (&pi)[Cfg<Q>::NR], T (&lr)[Cfg<Q>::NR], T (&li)[Cfg<Q>::NR],
                                              const T* __restrict__ gl, T* nl, const Ctx<T>& c) {
-    if constexpr (P >= 0) {
+    if constexpr (P >= PLO) {
       adj_gate_w<T, Q, P>(pr, pi, lr, li, gl + (Q - 1 - P) * kGateStride + 8, nl + (Q - 1 - P) * 8, c);
-      AdjGates<T, Q, P - 1>::run(pr, pi, lr, li, gl, nl, c);
+      AdjGatesDown<T, Q, P - 1, PLO>::run(pr, pi, lr, li, gl, nl, c);
     }
+  }
+};
+
+template <typename T, int Q, int P>
+struct AdjGates {  // adjoint sweep of one Rot layer (P kept for source compatibility: always Q - 1)
+  static __device__ __forceinline__ void run(T (&pr)[Cfg<Q>::NR], T (&pi)[Cfg<Q>::NR], T (&lr)[Cfg<Q>::NR], T (&li)[Cfg<Q>::NR],
+                                             const T* __restrict__ gl, T* nl, const Ctx<T>& c) {
+    using C = Cfg<Q>;
+    constexpr int NTL = C::NT < 5 ? C::NT : 5;
+    if constexpr (C::R >= 3) {  // register bits, rolled (see FwdGates): psi and lambda rotate together
+#pragma unroll 1
+      for (int i = 0; i < C::R; ++i) {
+        adj_gate_w<T, Q, C::NT>(pr, pi, lr, li, gl + (Q - 1 - C::NT - i) * kGateStride + 8, nl + (Q - 1 - C::NT - i) * 8, c);
+        rotate_regs<T, Q>(pr, pi);
+        rotate_regs<T, Q>(lr, li);
+      }
+      AdjGatesDown<T, Q, C::NT - 1, NTL>::run(pr, pi, lr, li, gl, nl, c);  // warp bits
+    } else {
+      AdjGatesDown<T, Q, Q - 1, NTL>::run(pr, pi, lr, li, gl, nl, c);
+    }
+#pragma unroll 1
+    for (int p = NTL - 1; p >= 0; --p)
+      adj_gate_lane_rt<T, Q>(pr, pi, lr, li, gl + (Q - 1 - p) * kGateStride + 8, nl + (Q - 1 - p) * 8, p, c);
   }
 };
 
@@ -494,6 +618,7 @@ __global__ void __launch_bounds__(Cfg<Q>::THREADS) wcirc_fwd_kernel(const WArgs<
 #pragma unroll
       for (int j = 0; j < Q; ++j) a.out[w * Q + j] = out[j];
     }
+    __syncthreads();  // keeps the CTA's warps in phase so they share instruction-cache lines (the loop body is >> L0)
   }
 }
 
@@ -568,6 +693,7 @@ __global__ void __launch_bounds__(Cfg<Q>::THREADS) wcirc_bwd_kernel(const WArgs<
 #pragma unroll
       for (int j = 0; j < Q; ++j) a.gpre[w * Q + j] = gpre[j];
     }
+    __syncthreads();  // in-phase warps share instruction-cache lines
   }
   __syncthreads();
   for (int e = tid; e < a.PA; e += C::THREADS) {
