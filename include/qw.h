@@ -39,6 +39,11 @@ long long qw_launch_count(void);
 void qw_profile_enable(int on);
 int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset);
 const char* qw_kernel_name(int kernel_id);
+/* Debug timeline: register a caller-owned DEVICE buffer of 2*nslots uint64 (pre-filled by the caller with ~0 for even and 0 for
+ * odd entries).  Every fast-path QuantumConv1d kernel launched afterwards takes the next slot (round robin from 0) and records
+ * min(CTA start) / max(CTA end) of %globaltimer in nanoseconds there -- also inside a replayed CUDA graph, which events cannot
+ * see.  dev_buf = NULL turns it off (the default).  Tools only; not part of the reference-facing path. */
+int qw_timeline_set(unsigned long long* dev_buf, int nslots);
 /* 1 (default): use the TMA fast path when the shape qualifies (fp32, q=4, K=3, stride 1|2, L%4==0, L_out%4==0,
  * O%4==0, O<=576, 16-byte aligned tensors; the forward additionally needs padding==1); 0: always use the generic kernels (used by the parity tests). */
 void qw_set_fast_path(int enable);
@@ -66,6 +71,19 @@ int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_
                            const double* qw, const double* w_post, double* gx, double* gw_pre, double* gb_pre,
                            double* gqw, double* gw_post, double* gb_post, void* workspace, size_t ws_bytes, int B,
                            int C, int L, int K, int S, int P, int O, int q, int n_layers, int embedding, void* stream);
+
+/* ---- fused INFERENCE forward of the encoder stem (whisper/whisper/model.py:193-198 with the two QuantumConv1d layers of
+ * quantum_whisper.py:136-137):
+ *     out[b, t, :] = gelu(conv2(gelu(conv1(x))))[b, :, t] + pos_emb[t, :]
+ * x (B,C,L) -> out (B, L/2, O); conv1 = (C -> hidden, K=3, S=1, P=1), conv2 = (hidden -> O, K=3, S=2, P=1), n_qubits = 4,
+ * amplitude embedding, gelu = the exact erf form (torch default).  pos_emb (L/2, O) or NULL.  The (B, hidden, L) activation
+ * between the layers is never materialised.  Nothing is saved for a backward pass.  Fast-path regime only (-2 otherwise):
+ * L % 4 == 0, hidden % 4 == 0, O % 4 == 0, hidden, O <= 576, 16-byte aligned tensors. */
+size_t qw_stem_workspace_bytes(int B, int L);
+int qw_stem_forward(const float* x, const float* w_pre1, const float* b_pre1, const float* qw1, const float* w_post1,
+                    const float* b_post1, const float* w_pre2, const float* b_pre2, const float* qw2, const float* w_post2,
+                    const float* b_post2, const float* pos_emb, float* out, void* workspace, size_t ws_bytes, int B, int C,
+                    int L, int hidden, int O, int n_layers, void* stream);
 
 /* ---- the QNode alone (quantum_whisper.py:64-85), batched over W windows: pre (W,q) -> out (W,q);
  * backward: gout (W,q) -> gpre (W,q) and gqw (n_layers,q,3) (overwritten).  BASELINE.json config 4. */

@@ -260,6 +260,19 @@ def qconv1d_forward(
     return y
 
 
+def stem_forward(x, params1, params2, positional_embedding=None):
+    """fp64 restatement of the stem of the quantum audio encoder: whisper/whisper/model.py:193-198 with conv1/conv2 the
+    QuantumConv1d layers of quantum_whisper.py:136-137 (k3/s1/p1 then k3/s2/p1); exact-erf GELU (torch default).
+    x (B, n_mels, L) -> (B, L_out2, n_state)."""
+    h = torch.nn.functional.gelu(qconv1d_forward(x, *params1, K=3, S=1, P=1))
+    h = torch.nn.functional.gelu(qconv1d_forward(h, *params2, K=3, S=2, P=1))
+    h = h.permute(0, 2, 1)
+    if positional_embedding is not None:
+        assert tuple(h.shape[1:]) == tuple(positional_embedding.shape), "incorrect audio shape"  # model.py:197
+        h = h + positional_embedding
+    return h
+
+
 def qconv1d_literal(x, w_pre, b_pre, qweights, w_post, b_post, K, S=1, P=0, max_windows: Optional[int] = None):
     """Literal loop nest of the reference forward (quantum_whisper.py:107-126): for each output
     column, for each batch element, one single-window simulation.  float64.  Used as the

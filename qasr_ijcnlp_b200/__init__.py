@@ -3,14 +3,16 @@
 Only what the path needs: the CUDA kernels + C ABI (`csrc/`, `libqw_b200.so`), the drop-in `QuantumConv1d`
 module, the log-mel front end, and the encoder classes that call them.  See DESIGN.md.
 """
-from .quantum_conv1d import QuantumConv1d, quantum_conv1d, quantum_circuit, out_length  # noqa: F401
+from .quantum_conv1d import (  # noqa: F401
+    QuantumConv1d, quantum_conv1d, quantum_circuit, out_length, fused_stem_forward, fused_stem_eligible,
+)
 from .encoder import (  # noqa: F401
     ModelDimensions, AudioEncoder, QuantumAudioEncoder, QuantumWhisper, QuantumWhisperClassifier, QuantumWhisperASR,
     CharASRHead, CHAR_VOCAB, get_whisper_tiny_dims, freeze_non_quantum_layers,
 )
 
 __all__ = [
-    "QuantumConv1d", "quantum_conv1d", "quantum_circuit", "out_length", "ModelDimensions", "AudioEncoder",
+    "QuantumConv1d", "quantum_conv1d", "quantum_circuit", "out_length", "fused_stem_forward", "fused_stem_eligible", "ModelDimensions", "AudioEncoder",
     "QuantumAudioEncoder", "QuantumWhisper", "QuantumWhisperClassifier", "QuantumWhisperASR", "CharASRHead",
     "CHAR_VOCAB", "get_whisper_tiny_dims", "freeze_non_quantum_layers",
 ]

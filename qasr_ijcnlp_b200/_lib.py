@@ -30,12 +30,15 @@ _SIGNATURES = {
     "qw_profile_enable": (None, [_I]),
     "qw_profile_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_LL), _I]),
     "qw_kernel_name": (ctypes.c_char_p, [_I]),
+    "qw_timeline_set": (_I, [_P, _I]),
     "qw_set_fast_path": (None, [_I]),
     "qw_conv1d_forward": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_forward_f64": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_workspace_bytes": (_SZ, [_I] * 10),
     "qw_conv1d_backward": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [_P]),
     "qw_conv1d_backward_f64": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [_P]),
+    "qw_stem_workspace_bytes": (_SZ, [_I, _I]),
+    "qw_stem_forward": (_I, [_P] * 13 + [_P, _SZ] + [_I] * 6 + [_P]),
     "qw_circuit_workspace_bytes": (_SZ, [_LL, _I, _I, _I]),
     "qw_circuit_forward": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),
     "qw_circuit_forward_f64": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),

@@ -28,6 +28,17 @@ int pdl_mode() {
   return v;
 }
 
+// ---- debug timeline: caller-owned device buffer of 2 x nslots u64 (start, end) pairs
+static std::atomic<unsigned long long*> g_tl_buf{nullptr};
+static std::atomic<int> g_tl_slots{0};
+static std::atomic<int> g_tl_next{0};
+unsigned long long* timeline_next_slot() {
+  unsigned long long* b = g_tl_buf.load(std::memory_order_relaxed);
+  if (!b) return nullptr;
+  const int n = g_tl_slots.load(std::memory_order_relaxed);
+  return b + 2 * (size_t)(g_tl_next.fetch_add(1, std::memory_order_relaxed) % n);
+}
+
 // ---- per-kernel event timing.  Events are recorded on the launching stream around each kernel and resolved
 // lazily in qw_profile_read (which synchronises on them).  Not usable during stream capture.
 struct ProfRec {
@@ -60,6 +71,14 @@ int qw_abi_version(void) { return QW_ABI_VERSION; }
 const char* qw_last_error(void) { return qw::g_err; }
 long long qw_launch_count(void) { return qw::g_launches.load(std::memory_order_relaxed); }
 
+int qw_timeline_set(unsigned long long* dev_buf, int nslots) {
+  if (dev_buf && nslots <= 0) return -1;
+  qw::g_tl_slots.store(nslots > 0 ? nslots : 1);
+  qw::g_tl_next.store(0);
+  qw::g_tl_buf.store(dev_buf);
+  return 0;
+}
+
 void qw_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(qw::g_pmu);
   qw::g_prof = on != 0;
@@ -90,7 +109,7 @@ int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset
 const char* qw_kernel_name(int kernel_id) {
   static const char* names[] = {"qconv_fwd_kernel", "qconv_bwd_post_kernel", "qconv_bwd_pre_kernel", "qconv_bwd_finalize_kernel",
                                 "circuit_fwd_kernel", "circuit_bwd_kernel", "circuit_finalize_kernel", "logmel_stft_kernel",
-                                "logmel_finish_kernel", "qconv_bwd_adj_kernel", "logmel_prep_kernel", "grads_allreduce_p2p_kernel"};
+                                "logmel_finish_kernel", "qconv_bwd_adj_kernel", "logmel_prep_kernel", "grads_allreduce_p2p_kernel", "stem2_kernel"};
   return (kernel_id >= 0 && kernel_id < qw::kKCount) ? names[kernel_id] : "";
 }
 }

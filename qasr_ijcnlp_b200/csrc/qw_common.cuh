@@ -13,7 +13,7 @@ void count_launch(int n = 1);
 int num_sms();
 
 // Optional per-kernel CUDA-event timing (qw_profile_enable): KernelTimer brackets one launch on `st`.
-enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKGradAllReduce, kKCount };
+enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKGradAllReduce, kKStem2, kKCount };
 bool profiling_enabled();
 void profile_begin(int id, cudaStream_t st);
 void profile_end(int id, cudaStream_t st);
@@ -121,6 +121,22 @@ inline cudaError_t launch_pdl(bool small, void (*kernel)(KArgs...), dim3 grid, d
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- debug timeline (qw_timeline_set): when a device buffer is registered, every fast-path launch takes the next slot and its
+// CTAs record min(start) / max(end) of %globaltimer there, so the spans and gaps of the kernels INSIDE a replayed CUDA graph
+// (which events cannot see) can be read back.  Null pointer (the default): one predictable branch per CTA.
+unsigned long long* timeline_next_slot();
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* s) {
+  if (s && threadIdx.x == 0) atomicMin(s, global_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* s) {
+  if (s && threadIdx.x == 0) atomicMax(s + 1, global_ns());
 }
 
 // streaming (evict-first) global store / load for data touched exactly once

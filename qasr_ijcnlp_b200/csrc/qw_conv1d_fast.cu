@@ -41,6 +41,8 @@ struct FastFwdArgs {
   float *y, *pre_save, *qout_save;
   int B, C, L, P, O, Lq, Lout;
   int tiles_per_utt, num_tiles, chunks_per_tile;
+  int early_tma;
+  unsigned long long* tl;
 };
 
 constexpr int kFwdStages = 4;
@@ -88,8 +90,21 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 3, tl = lane & 7;
+  tl_begin(a.tl);
 
-  if (tid == 0) {
+  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_chunks = my_tiles * a.chunks_per_tile;
+  // producer (thread 0): chunk g of this CTA -> stage g % kFwdStages
+  auto issue = [&](int g) {
+    const int n = g / a.chunks_per_tile, ch = g - n * a.chunks_per_tile;
+    const int tile = blockIdx.x + n * gridDim.x;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int s = g % kFwdStages;
+    mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * 4);
+    tma_load_3d(stage + (size_t)s * STAGE_ELEMS, &tm_x, i0 * S - 4, ch * RC, b, &full[s]);
+  };
+  if (tid == kFwdSW * 32) {  // lane 0 of the circuit warp: it stages no parameters, so it can sit in the dependency wait
     tma_prefetch_desc(&tm_x);
     for (int s = 0; s < kFwdStages; ++s) {
       mbar_init(&full[s], 1);
@@ -102,10 +117,17 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       mbar_init(&oempty[s], kFwdSW);
     }
     fence_mbar_init();
+    // x may be the previous kernel's output: wait for it here, then get the first tiles moving while the other threads stage
+    // the parameters (73 KB of pre_conv weights per CTA at C = 384)
+    if (a.early_tma) {
+      pdl_wait();
+      for (int g = 0; g < kFwdStages - 1 && g < total_chunks; ++g) issue(g);
+    }
   }
   // ---- stage parameters (vectorised: 4 features x 4 qubits per step, transposed in registers)
+  if (warp < kFwdSW) {
   if ((CK & 3) == 0) {
-    for (int u = tid; u < CK / 4; u += kFwdThreads) {
+    for (int u = tid; u < CK / 4; u += kFwdSW * 32) {
       const float4 r0 = ld4(a.w_pre + 0 * (size_t)CK + 4 * u), r1 = ld4(a.w_pre + 1 * (size_t)CK + 4 * u);
       const float4 r2 = ld4(a.w_pre + 2 * (size_t)CK + 4 * u), r3 = ld4(a.w_pre + 3 * (size_t)CK + 4 * u);
       st4(wpre_t + (size_t)(4 * u + 0) * FQ, make_float4(r0.x, r1.x, r2.x, r3.x));
@@ -114,21 +136,21 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       st4(wpre_t + (size_t)(4 * u + 3) * FQ, make_float4(r0.w, r1.w, r2.w, r3.w));
     }
   } else {
-    for (int idx = tid; idx < CK * FQ; idx += kFwdThreads) {
+    for (int idx = tid; idx < CK * FQ; idx += kFwdSW * 32) {
       const int j = idx / CK, f = idx - j * CK;
       wpre_t[f * FQ + j] = a.w_pre[idx];
     }
   }
-  for (int u = tid; u < a.O; u += kFwdThreads) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
-  for (int idx = tid; idx < a.O; idx += kFwdThreads) bpost[idx] = a.b_post[idx];
+  for (int u = tid; u < a.O; u += kFwdSW * 32) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
+  for (int idx = tid; idx < a.O; idx += kFwdSW * 32) bpost[idx] = a.b_post[idx];
   if (tid < FQ) bpre[tid] = a.b_pre[tid];
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  }
   __syncthreads();
-  pdl_wait();    // x may be the previous kernel's output; nothing global is written above
+  pdl_wait();    // nothing global is written above
   pdl_launch();
-
-  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int total_chunks = my_tiles * a.chunks_per_tile;
+  if (tid == 0 && !a.early_tma)
+    for (int g = 0; g < kFwdStages - 1 && g < total_chunks; ++g) issue(g);
 
   if (warp == kFwdSW) {
     // ======================================================== circuit warp: one lane per window
@@ -166,19 +188,6 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
   }
 
   // ========================================================== streaming warps
-  // producer (thread 0): chunk g of this CTA -> stage g % kFwdStages
-  auto issue = [&](int g) {
-    const int n = g / a.chunks_per_tile, ch = g - n * a.chunks_per_tile;
-    const int tile = blockIdx.x + n * gridDim.x;
-    const int b = tile / a.tiles_per_utt;
-    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
-    const int s = g % kFwdStages;
-    mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * 4);
-    tma_load_3d(stage + (size_t)s * STAGE_ELEMS, &tm_x, i0 * S - 4, ch * RC, b, &full[s]);
-  };
-  if (tid == 0)
-    for (int g = 0; g < kFwdStages - 1 && g < total_chunks; ++g) issue(g);
-
   int g = 0;  // running chunk counter
   for (int n = 0; n <= my_tiles; ++n) {
     // ---- pre_conv partial sums of tile n
@@ -272,6 +281,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&oempty[ob]);
+      if (a.y == nullptr) continue;  // readouts only (fused stem, qw_stem.cu): the circuit warp has stored them
       const bool store_ok = (i0 + 4 * tl) < a.Lout;  // Lout % 4 == 0: a lane's 4 windows are all valid or all invalid
       float* __restrict__ yb = a.y + (size_t)b * a.O * a.Lout + i0 + 4 * tl;
       const int ngroups = a.O >> 2;
@@ -289,255 +299,18 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       }
     }
   }
+  tl_end(a.tl);
 }
 
 // =============================================================================================== backward: gy streaming + adjoint
-struct FastGyArgs {
-  const float *w_post, *pre_save, *qw;
-  float *gpre_pad, *part;  // gpre_pad: [B][LP][4]; part: [gridDim.x][PA1]
-  int B, O, Lout, LP, Lq, tiles_per_utt, num_tiles, PA1;
-};
 constexpr int kGySW = 6;                          // streaming warps (192 threads = one stage row each)
-constexpr int kGyAW = 2;                          // adjoint warps (alternate tiles)
-constexpr int kGyThreads = (kGySW + kGyAW) * 32;
 constexpr int kGyStream = kGySW * 32;
 constexpr int kGyStages = 3;                      // ring of 192-row x 32-window stages (3 TMA boxes of 64 rows)
 constexpr int kGyStageRows = 192;
 constexpr int kGyStageElems = kGyStageRows * 32;
 constexpr int kGyMS = 33;                         // per-lane accumulator column stride
-// partial-row layout: [O*4 gw_post][O gb_post][pad to 32][gb_pre 4 + pad 28][Lq*32 gate matrices][pad to 32]
-__host__ __device__ inline int gy_moff(int O) { return (int)align_up((size_t)O * 5, 32); }
-__host__ __device__ inline int gy_plen(int O, int Lq) { return gy_moff(O) + 32 + (int)align_up((size_t)Lq * 32, 32); }
-
-__host__ __device__ constexpr size_t fast_gy_smem_bytes(int O, int Lq) {
-  return 1024 + (size_t)kGyStages * kGyStageElems * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)O * FQ * 4 +
-         (size_t)3 * kGySW * FTW * FQ * 4 + (size_t)Lq * FQ * kGateStride * 4 + (size_t)kGyAW * (FQ + Lq * 32) * kGyMS * 4 +
-         (2 * kGyStages + 6) * 8;
-}
-
-// Warp-specialised, mbarrier-coupled:
-//   warps 0-5 (streaming): per tile, NHALF stages of 192 output channels: gout partials (time-major lanes) and
-//                          grad post_conv.{weight,bias} (channel-major lanes, register accumulators); gout partials of
-//                          tile n -> gred[n%3].
-//   warps 6-7 (adjoint)  : tile n (n%2 == warp-6): gred[n%3] -> adjoint circuit -> gpre (halo-padded), gate-gradient
-//                          and grad pre_conv.bias sums in per-lane shared-memory columns.
-template <int NHALF>
-__global__ void __launch_bounds__(kGyThreads, 2) fast_bwd_gy_kernel(const __grid_constant__ CUtensorMap tm_gy,
-                                                                    const __grid_constant__ CUtensorMap tm_qout, const FastGyArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  unsigned char* base = align1024(smem_dyn);
-  const int NE = FQ + a.Lq * 32;
-  float* stages = reinterpret_cast<float*>(base);                      // [kGyStages][192][32] swizzled
-  float* outs = stages + (size_t)kGyStages * kGyStageElems;            // [3][32][4]
-  float* wpost = outs + 3 * FTW * FQ;                                  // [O][4]
-  float* gred = wpost + (size_t)a.O * FQ;                              // [3][kGySW][32][4]
-  float* gates = gred + 3 * kGySW * FTW * FQ;                          // [Lq][4][16]
-  float* macc = gates + (size_t)a.Lq * FQ * kGateStride;               // [kGyAW][NE][kGyMS]
-  uint64_t* full = reinterpret_cast<uint64_t*>(macc + (size_t)kGyAW * NE * kGyMS);
-  uint64_t* empty = full + kGyStages;
-  uint64_t* gfull = empty + kGyStages;   // [3]
-  uint64_t* gempty = gfull + 3;          // [3]
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rr = lane >> 3, tl = lane & 7;
-  if (tid == 0) {
-    tma_prefetch_desc(&tm_gy);
-    tma_prefetch_desc(&tm_qout);
-    for (int s = 0; s < kGyStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kGySW);
-    }
-    for (int s = 0; s < 3; ++s) {
-      mbar_init(&gfull[s], kGySW);
-      mbar_init(&gempty[s], 1);
-    }
-    fence_mbar_init();
-  }
-  for (int u = tid; u < a.O; u += kGyThreads) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
-  if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
-  for (int e = tid; e < kGyAW * NE * kGyMS; e += kGyThreads) macc[e] = 0.f;
-  // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
-  {
-    const int per = (kHaloL + kHaloR) * FQ;
-    for (long long idx = (long long)blockIdx.x * kGyThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kGyThreads) {
-      const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
-      const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
-      a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
-    }
-  }
-  __syncthreads();
-
-  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int total_stages = my_tiles * NHALF;
-  float wacc[NHALF][FQ + 1];
-#pragma unroll
-  for (int m = 0; m < NHALF; ++m)
-#pragma unroll
-    for (int j = 0; j <= FQ; ++j) wacc[m][j] = 0.f;
-
-  if (warp >= kGySW) {
-    // ======================================================== adjoint warps
-    const int aw = warp - kGySW;
-    float* mymacc = macc + (size_t)aw * NE * kGyMS;
-    auto load_pre = [&](int n) {
-      const int tile = blockIdx.x + n * gridDim.x;
-      const int b = tile / a.tiles_per_utt;
-      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
-      return (i < a.Lout) ? ld4(a.pre_save + ((size_t)b * a.Lout + i) * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
-    };
-    float4 pre_cur = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (aw < my_tiles) pre_cur = load_pre(aw);
-    for (int n = aw; n < my_tiles; n += kGyAW) {
-      const int tile = blockIdx.x + n * gridDim.x;
-      const int b = tile / a.tiles_per_utt;
-      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
-      const bool valid = i < a.Lout;
-      const int gb = n % 3;
-      mbar_wait(&gfull[gb], (n / 3) & 1);
-      const float* gr = gred + (size_t)gb * kGySW * FTW * FQ;
-      float gout[FQ] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int w = 0; w < kGySW; ++w) {
-        const float4 pv = ld4(gr + ((size_t)w * FTW + lane) * FQ);
-        gout[0] += pv.x; gout[1] += pv.y; gout[2] += pv.z; gout[3] += pv.w;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gempty[gb]);
-      if (!valid) gout[0] = gout[1] = gout[2] = gout[3] = 0.f;
-      const float pre[FQ] = {pre_cur.x, pre_cur.y, pre_cur.z, pre_cur.w};
-      if (n + kGyAW < my_tiles) pre_cur = load_pre(n + kGyAW);  // prefetch for this warp's next tile
-      float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
-      const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
-      SmemGateAcc<float, FQ> acc{mymacc + (size_t)FQ * kGyMS + lane, kGyMS, 0};
-      circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
-      if (valid) st4(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
-#pragma unroll
-      for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
-    }
-  } else {
-    // ======================================================== streaming warps
-    auto issue = [&](int gs) {
-      const int n = gs / NHALF, h = gs - n * NHALF;
-      const int tile = blockIdx.x + n * gridDim.x;
-      const int b = tile / a.tiles_per_utt;
-      const int i0 = (tile - b * a.tiles_per_utt) * FTW;
-      const int s = gs % kGyStages;
-      mbar_arrive_expect_tx(&full[s], (uint32_t)(kGyStageElems + (h == 0 ? FTW * FQ : 0)) * 4);
-#pragma unroll
-      for (int bx = 0; bx < 3; ++bx)
-        tma_load_3d(stages + (size_t)s * kGyStageElems + bx * 64 * 32, &tm_gy, i0, h * kGyStageRows + bx * 64, b, &full[s]);
-      if (h == 0) tma_load_3d(outs + (n % 3) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
-    };
-    if (tid == 0)
-      for (int gs = 0; gs < kGyStages - 1 && gs < total_stages; ++gs) issue(gs);
-
-    int gs = 0;
-    for (int n = 0; n < my_tiles; ++n) {
-      float gacc[4][FQ];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < FQ; ++j) gacc[u][j] = 0.f;
-      const float* os = outs + (n % 3) * FTW * FQ;
-#pragma unroll
-      for (int h = 0; h < NHALF; ++h, ++gs) {
-        if (tid == 0) {
-          const int gn = gs + kGyStages - 1;
-          if (gn < total_stages) {
-            if (gn >= kGyStages) mbar_wait(&empty[gn % kGyStages], ((gn / kGyStages) - 1) & 1);
-            issue(gn);
-          }
-        }
-        const int s = gs % kGyStages;
-        mbar_wait(&full[s], (gs / kGyStages) & 1);
-        const float* gsm = stages + (size_t)s * kGyStageElems;
-        const int row0 = h * kGyStageRows;
-        // ---- gout partials: lanes (4 rows x 8 chunks of 4 windows); 48 row groups per stage, 8 per warp
-#pragma unroll 4
-        for (int og = warp; og < kGyStageRows / 4; og += kGySW) {
-          const int rl = og * 4 + rr;
-          const int r = row0 + rl;
-          const float4 gv = ld4(gsm + swz128(rl, tl));
-          const float4 wv = (r < a.O) ? ld4(wpost + (size_t)r * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
-          gacc[0][0] = fmaf(gv.x, wv.x, gacc[0][0]); gacc[0][1] = fmaf(gv.x, wv.y, gacc[0][1]);
-          gacc[0][2] = fmaf(gv.x, wv.z, gacc[0][2]); gacc[0][3] = fmaf(gv.x, wv.w, gacc[0][3]);
-          gacc[1][0] = fmaf(gv.y, wv.x, gacc[1][0]); gacc[1][1] = fmaf(gv.y, wv.y, gacc[1][1]);
-          gacc[1][2] = fmaf(gv.y, wv.z, gacc[1][2]); gacc[1][3] = fmaf(gv.y, wv.w, gacc[1][3]);
-          gacc[2][0] = fmaf(gv.z, wv.x, gacc[2][0]); gacc[2][1] = fmaf(gv.z, wv.y, gacc[2][1]);
-          gacc[2][2] = fmaf(gv.z, wv.z, gacc[2][2]); gacc[2][3] = fmaf(gv.z, wv.w, gacc[2][3]);
-          gacc[3][0] = fmaf(gv.w, wv.x, gacc[3][0]); gacc[3][1] = fmaf(gv.w, wv.y, gacc[3][1]);
-          gacc[3][2] = fmaf(gv.w, wv.z, gacc[3][2]); gacc[3][3] = fmaf(gv.w, wv.w, gacc[3][3]);
-        }
-        // ---- grad post_conv.{weight,bias}: thread <-> stage row, accumulators live in registers
-        {
-          const int rl = tid;  // 0..191
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 gv = ld4(gsm + swz128(rl, c));
-            const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float4 ov = ld4(os + (size_t)(4 * c + u) * FQ);
-              wacc[h][0] = fmaf(g4[u], ov.x, wacc[h][0]);
-              wacc[h][1] = fmaf(g4[u], ov.y, wacc[h][1]);
-              wacc[h][2] = fmaf(g4[u], ov.z, wacc[h][2]);
-              wacc[h][3] = fmaf(g4[u], ov.w, wacc[h][3]);
-              wacc[h][4] += g4[u];
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
-      // ---- reduce the 4 row classes and hand the warp partial to the adjoint warps
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < FQ; ++j) {
-          float v = gacc[u][j];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          gacc[u][j] = v;
-        }
-      const int gb = n % 3;
-      if (n >= 3) mbar_wait(&gempty[gb], ((n / 3) - 1) & 1);
-      if (rr == 0) {
-        float* gr = gred + (size_t)gb * kGySW * FTW * FQ;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          st4(gr + ((size_t)warp * FTW + 4 * tl + u) * FQ, make_float4(gacc[u][0], gacc[u][1], gacc[u][2], gacc[u][3]));
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gfull[gb]);
-    }
-  }
-  __syncthreads();
-  // ---- partial row of this CTA
-  float* prow = a.part + (size_t)blockIdx.x * a.PA1;
-  if (warp < kGySW) {
-#pragma unroll
-    for (int m = 0; m < NHALF; ++m) {
-      const int r = m * kGyStageRows + tid;
-      if (r < a.O) {
-        st4(prow + (size_t)r * FQ, make_float4(wacc[m][0], wacc[m][1], wacc[m][2], wacc[m][3]));
-        prow[a.O * FQ + r] = wacc[m][4];
-      }
-    }
-  }
-  const int moff = gy_moff(a.O);
-  for (int e = a.O * (FQ + 1) + tid; e < moff; e += kGyThreads) prow[e] = 0.f;
-  for (int e = warp; e < a.PA1 - moff; e += kGyThreads / 32) {
-    // e in [0,4): grad pre_conv.bias; [32, 32+Lq*32): gate matrices; everything else padding
-    float v = 0.f;
-    const int src = e < FQ ? e : (e >= 32 && e < 32 + a.Lq * 32) ? FQ + (e - 32) : -1;
-    if (src >= 0) {
-#pragma unroll
-      for (int w = 0; w < kGyAW; ++w) v += macc[((size_t)w * NE + src) * kGyMS + lane];
-      v = warp_sum(v);
-    }
-    if (lane == 0) prow[moff + e] = v;
-  }
-}
+// partial-row layout of the gy kernel: [O*4 grad post_conv.weight][O grad post_conv.bias][pad to 32]
+__host__ __device__ inline int gy_plen(int O) { return (int)align_up((size_t)O * 5, 32); }
 
 // =============================================================================================== backward: gy streaming (lean) + adjoint kernel
 // Split form of the kernel above (default; QW_GY_FUSED=1 selects the fused one): ncu showed the fused kernel bound by its two
@@ -548,6 +321,7 @@ struct FastGy2Args {
   const float* w_post;
   float *gout, *part;  // gout: [B*Lout][4]; part: [gridDim.x][PA1]
   int B, O, Lout, tiles_per_utt, num_tiles, PA1;
+  unsigned long long* tl;
 };
 __host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O) {
   return 1024 + (size_t)kGyStages * kGyStageElems * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)O * FQ * 4 +
@@ -568,6 +342,7 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 3, tl = lane & 7;
+  tl_begin(a.tl);
   if (tid == 0) {
     tma_prefetch_desc(&tm_gy);
     tma_prefetch_desc(&tm_qout);
@@ -704,39 +479,100 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
     }
   }
   for (int e = a.O * (FQ + 1) + tid; e < a.PA1; e += kGyStream) prow[e] = 0.f;
+  tl_end(a.tl);
 }
 
 // adjoint differentiation of the circuit, one window per thread; partial row per CTA: [gb_pre 4 + pad 28][Lq*32 gate matrices]
+//
+// The first a.nlead CTAs of the grid do not run the adjoint: they reduce the partial rows the gy kernel has just written
+// (grad post_conv.{weight,bias}: G1 rows x O*5 columns, 16 columns per CTA, fixed-order fp64 sums -> deterministic) while the
+// adjoint CTAs -- a latency-bound dependent chain that leaves most of every SM idle -- run beside them.  This is the first
+// third of what used to be a separate finalize kernel at the end of the backward (its launch + drain was ~8 us per layer on
+// the critical path at batch 16); the second third (grad pre_conv.bias, grad quantum_weights) rides in fast_bwd_pre_kernel
+// the same way, and only grad pre_conv.weight -- whose rows the LAST kernel of the backward produces -- is left to
+// fast_finalize_kernel.  (Measured and rejected: reducing those rows inside fast_bwd_pre_kernel too, by a two-level
+// last-arriver scheme; its fence + atomic + L2 round trips at the tail of every CTA cost 8 us per step more than the
+// programmatically launched finalize kernel they replaced: 147.6 vs 139.5 us.)
 constexpr int kAdjThreads = 128;
+constexpr int kAdjRedCols = 16;
 
 __global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdjArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  tl_begin(a.tl);
+  if ((int)blockIdx.x < a.nlead) {
+    // ======================================================== reduce CTA: columns [blk*16, blk*16+16) of part1
+    double* red = reinterpret_cast<double*>(smem_dyn);  // [8][16]
+    const int col = lane & 15, slot = warp * 2 + (lane >> 4);
+    const int pcol = (int)blockIdx.x * kAdjRedCols + col;
+    const int ncols = a.O * (FQ + 1);
+    pdl_wait();
+    double s = 0.0;
+    if (pcol < ncols) {
+      const float* __restrict__ src = a.part1 + pcol;
+      int g = slot;
+      for (; g + 56 < a.G1; g += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + 8 * u) * a.P1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+      }
+      for (; g < a.G1; g += 8) s += (double)__ldcg(src + (size_t)g * a.P1);
+    }
+    red[slot * kAdjRedCols + col] = s;
+    __syncthreads();
+    if (tid < kAdjRedCols && pcol < ncols) {
+      double t = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += red[u * kAdjRedCols + tid];
+      if (pcol < a.O * FQ) a.gw_post[pcol] = (float)t;
+      else a.gb_post[pcol - a.O * FQ] = (float)t;
+    }
+    tl_end(a.tl);
+    return;
+  }
+  const int bid = (int)blockIdx.x - a.nlead, nblk = (int)gridDim.x - a.nlead;
   const int NE = FQ + a.Lq * 32;
   float* gates = reinterpret_cast<float*>(smem_dyn);             // [Lq][4][16]
   float* macc = gates + (size_t)a.Lq * FQ * kGateStride;         // [4 warps][NE][kGyMS]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   for (int e = tid; e < 4 * NE * kGyMS; e += kAdjThreads) macc[e] = 0.f;
+  __syncthreads();
+  // The forward recomputation of this thread's first window needs only pre_save (written by the forward kernel, at least two
+  // launches back in the stream), so it runs BEFORE the dependency wait: under programmatic dependent launch these CTAs are
+  // resident microseconds before the gy kernel drains (they are small), and this hides ~40 % of the adjoint's dependent chain.
+  const long long wfirst = (long long)bid * kAdjThreads;
+  float pre[FQ], out[FQ], re[1 << FQ], im[1 << FQ];
+  float inv;
+  if (a.early_trigger & 2) {
+    const long long w = wfirst + tid;
+    const float4 pv = (w < a.W) ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+    pre[0] = pv.x; pre[1] = pv.y; pre[2] = pv.z; pre[3] = pv.w;
+    inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+  }
   pdl_wait();
+  if (a.early_trigger & 1) pdl_launch();  // the whole grid is resident: the next kernel's CTAs may come in and stage their tiles
   {  // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
     const int per = (kHaloL + kHaloR) * FQ;
-    for (long long idx = (long long)blockIdx.x * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kAdjThreads) {
+    for (long long idx = (long long)bid * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)nblk * kAdjThreads) {
       const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
       const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
       a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
     }
   }
-  __syncthreads();
   float* mymacc = macc + (size_t)warp * NE * kGyMS;
-  for (long long w0 = (long long)blockIdx.x * kAdjThreads; w0 < a.W; w0 += (long long)gridDim.x * kAdjThreads) {
+  for (long long w0 = wfirst; w0 < a.W; w0 += (long long)nblk * kAdjThreads) {
     const long long w = w0 + tid;
     const bool valid = w < a.W;
-    const float4 pv = valid ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+    if (w0 != wfirst || !(a.early_trigger & 2)) {
+      const float4 pv = valid ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+      pre[0] = pv.x; pre[1] = pv.y; pre[2] = pv.z; pre[3] = pv.w;
+      inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+    }
     const float4 gv = valid ? ld4(a.gout + (size_t)w * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
     const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
-    float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
-    const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+    float gpre[FQ];
     SmemGateAcc<float, FQ> acc{mymacc + (size_t)FQ * kGyMS + lane, kGyMS, 0};
     circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
     if (valid) {
@@ -746,9 +582,9 @@ __global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdj
 #pragma unroll
     for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
   }
-  pdl_launch();  // late: this grid is not fully resident, an early trigger would let the next kernel's CTAs take its slots
+  if (!(a.early_trigger & 1)) pdl_launch();  // late: this grid is not fully resident, an early trigger would let the next kernel's CTAs take its slots
   __syncthreads();
-  float* prow = a.part + (size_t)blockIdx.x * a.PA2;
+  float* prow = a.part + (size_t)bid * a.PA2;
   for (int e = warp; e < a.PA2; e += kAdjThreads / 32) {
     // e in [0,4): grad pre_conv.bias; [32, 32+Lq*32): gate matrices; everything else padding
     float v = 0.f;
@@ -760,13 +596,22 @@ __global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdj
     }
     if (lane == 0) prow[e] = v;
   }
+  tl_end(a.tl);
 }
 
 // =============================================================================================== backward: pre_conv^T
 struct FastPreArgs {
   const float *gpre_pad, *w_pre;
-  float* part;  // [gridDim.x][Cpad][12]
+  float* part;  // [gridPx][Cpad][12]
   int B, C, L, P, Lout, LP, tiles_per_utt, num_tiles, Cpad;
+  int gridPx;  // streaming CTAs per channel chunk; the grid is 1-D: [nlead reduce CTAs][nchunks x gridPx streaming CTAs]
+  // leading reduce CTAs: part2 = [G2][P2] rows of the adjoint kernel -> grad pre_conv.bias, grad quantum_weights
+  int nlead;
+  const float *part2, *qw;
+  int G2, P2, Lq;
+  float *gb_pre, *gqw;
+  int early_x;
+  unsigned long long* tl;
 };
 constexpr int kPreSlots = 3;
 template <int S> __host__ __device__ constexpr int pre_gpn() { return S == 1 ? 136 : 72; }  // gpre rows staged per tile
@@ -787,7 +632,54 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
   float* gps = xs + (size_t)kPreSlots * 4096;                   // [kPreSlots][GPN][4]
   uint64_t* full = reinterpret_cast<uint64_t*>(gps + (size_t)kPreSlots * GPN * FQ);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int c0 = blockIdx.y * 32, c = c0 + lane;
+  tl_begin(a.tl);
+  if ((int)blockIdx.x < a.nlead) {
+    // ======================================================== reduce CTA: 32 columns of the adjoint kernel's partial rows
+    // (block 0: grad pre_conv.bias; block 1 + l: the 4 gate-gradient matrices of layer l -> (phi, theta, omega) chain rule)
+    double* red = reinterpret_cast<double*>(base);  // [kWarps][32] + tot[32]
+    double* tot = red + kWarps * 32;
+    const int pcol = (int)blockIdx.x * 32 + lane;
+    pdl_wait();
+    double sacc = 0.0;
+    {
+      const float* __restrict__ src = a.part2 + pcol;
+      int g = warp;
+      for (; g + 7 * kWarps < a.G2; g += 8 * kWarps) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + u * kWarps) * a.P2);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sacc += (double)v[u];
+      }
+      for (; g < a.G2; g += kWarps) sacc += (double)__ldcg(src + (size_t)g * a.P2);
+    }
+    red[warp * 32 + lane] = sacc;
+    __syncthreads();
+    if (warp != 0) return;
+    tl_end(a.tl);
+    double t = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < kWarps; ++wq) t += red[wq * 32 + lane];
+    tot[lane] = t;
+    __syncwarp();
+    if (blockIdx.x == 0) {
+      if (lane < FQ) a.gb_pre[lane] = (float)t;
+    } else if (lane < FQ) {
+      const int gi = ((int)blockIdx.x - 1) * FQ + lane;
+      if (gi < a.Lq * FQ) {
+        double w3[3], g3[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) w3[e] = (double)a.qw[gi * 3 + e];
+        gate_grad_to_angles(w3, &tot[lane * 8], g3);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a.gqw[gi * 3 + e] = (float)g3[e];
+      }
+    }
+    return;
+  }
+  const int lin = (int)blockIdx.x - a.nlead;
+  const int by = lin / a.gridPx, bx = lin - by * a.gridPx;  // channel chunk, CTA inside the chunk
+  const int c0 = by * 32, c = c0 + lane;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_x);
@@ -803,23 +695,39 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
       w[j][k] = (c < a.C) ? a.w_pre[(size_t)j * a.C * 3 + c * 3 + k] : 0.f;
       gw[j][k] = 0.f;
     }
-  __syncthreads();
-  pdl_wait();
-  pdl_launch();
-
-  const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto issue = [&](int n) {
-    const int tile = blockIdx.x + n * gridDim.x;
+  const int my_tiles = (bx < a.num_tiles) ? (a.num_tiles - 1 - bx) / a.gridPx + 1 : 0;
+  // a tile = its x boxes (this layer's forward input: long complete) + its gpre rows (the adjoint kernel's output)
+  auto issue_x = [&](int n) {
+    const int tile = bx + n * a.gridPx;
+    const int b = tile / a.tiles_per_utt;
+    const int l0 = (tile - b * a.tiles_per_utt) * 128;
+    const int s = n % kPreSlots;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(4096 + GPN * FQ) * 4);
+    for (int q = 0; q < 4; ++q) tma_load_3d(xs + (size_t)s * 4096 + q * 1024, &tm_x, l0 + q * 32, c0, b, &full[s]);
+  };
+  auto issue_g = [&](int n) {
+    const int tile = bx + n * a.gridPx;
     const int b = tile / a.tiles_per_utt;
     const int l0 = (tile - b * a.tiles_per_utt) * 128;
     const int i_lo = floor_div(l0 + a.P - 2, S);
     const int s = n % kPreSlots;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(4096 + GPN * FQ) * 4);
-    for (int bx = 0; bx < 4; ++bx) tma_load_3d(xs + (size_t)s * 4096 + bx * 1024, &tm_x, l0 + bx * 32, c0, b, &full[s]);
     bulk_g2s(gps + (size_t)s * GPN * FQ, a.gpre_pad + ((size_t)b * a.LP + kHaloL + i_lo) * FQ, GPN * FQ * 4, &full[s]);
   };
+  auto issue = [&](int n) {
+    issue_x(n);
+    issue_g(n);
+  };
+  // the x boxes of the first tiles are requested BEFORE the dependency wait (they overlap the adjoint kernel's tail)
+  if (tid == 0 && a.early_x)
+    for (int n = 0; n < kPreSlots - 1 && n < my_tiles; ++n) issue_x(n);
+  __syncthreads();
+  pdl_wait();
+  pdl_launch();
   if (tid == 0)
-    for (int n = 0; n < kPreSlots - 1 && n < my_tiles; ++n) issue(n);
+    for (int n = 0; n < kPreSlots - 1 && n < my_tiles; ++n) {
+      if (!a.early_x) issue_x(n);
+      issue_g(n);
+    }
 
   for (int n = 0; n < my_tiles; ++n) {
     const int s = n % kPreSlots;
@@ -869,10 +777,10 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
-        const int tile = blockIdx.x + n * gridDim.x;
+        const int tile = bx + n * a.gridPx;
         const int b = tile / a.tiles_per_utt;
         const int l0 = (tile - b * a.tiles_per_utt) * 128;
-        for (int bx = 0; bx < 4; ++bx) tma_store_3d(&tm_gx, l0 + bx * 32, c0, b, xs + (size_t)s * 4096 + bx * 1024);
+        for (int q = 0; q < 4; ++q) tma_store_3d(&tm_gx, l0 + q * 32, c0, b, xs + (size_t)s * 4096 + q * 1024);
         bulk_commit();
       }
     } else {
@@ -888,34 +796,38 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
 #pragma unroll
     for (int k = 0; k < 3; ++k) red[((size_t)warp * 32 + lane) * 12 + j * 3 + k] = gw[j][k];
   __syncthreads();
-  float* prow = a.part + ((size_t)blockIdx.x * a.Cpad + c0) * 12;
+  float* prow = a.part + ((size_t)bx * a.Cpad + c0) * 12;
   for (int e = tid; e < 32 * 12; e += kThreads) {
     float sum = 0.f;
 #pragma unroll
     for (int wq = 0; wq < kWarps; ++wq) sum += red[(size_t)wq * 32 * 12 + e];
     prow[e] = sum;
   }
+  tl_end(a.tl);
 }
 
 // =============================================================================================== finalize
+// Deterministic fixed-order fp64 reduction of per-CTA partial rows.  Segment 3 (grad pre_conv.weight, rows of the pre_conv^T
+// kernel) always runs here; segments 1 and 2 only with QW_FINALIZE_KERNEL=1 (A/B switch) -- by default they ride as leading
+// CTAs inside the adjoint and pre_conv^T kernels.
 constexpr int kFFThreads = 1024;  // 32 warps per 32-column block: short dependent chains over the partial rows
 constexpr int kFFWarps = kFFThreads / 32;
 struct FastFinArgs {
-  const float *part1, *part3, *qw;
+  const float *part1, *part2, *part3, *qw;
   float *gw_pre, *gb_pre, *gqw, *gw_post, *gb_post;
-  int G1, P1, G3, P3;
+  int G1, P1, G2, P2, G3, P3;
   int C, O, Lq;
-  const float* part2;  // split backward: [G2][P2] rows of the adjoint kernel ([gb_pre 4 + pad 28][Lq*32]); null when fused
-  int G2, P2;
+  unsigned long long* tl;
 };
 
 __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFinArgs a) {
   __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
+  tl_begin(a.tl);
   pdl_wait();
   pdl_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb1 = a.P1 / 32, nb2 = a.part2 ? a.P2 / 32 : 0;
+  const int nb1 = a.part1 ? a.P1 / 32 : 0, nb2 = a.part2 ? a.P2 / 32 : 0;
   const bool seg1 = (int)blockIdx.x < nb1;
   const bool seg2 = !seg1 && (int)blockIdx.x < nb1 + nb2;
   const int blk = seg1 ? blockIdx.x : seg2 ? blockIdx.x - nb1 : blockIdx.x - nb1 - nb2;
@@ -936,22 +848,21 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   red[warp][lane] = s;
   __syncthreads();
   if (warp != 0) return;
+  tl_end(a.tl);
   double t = 0.0;
 #pragma unroll
   for (int w = 0; w < kFFWarps; ++w) t += red[w][lane];
   tot[lane] = t;
   __syncwarp();
-  if (seg1 || seg2) {
+  if (seg1) {
     const int nW = a.O * FQ;
-    const int moff = seg2 ? 0 : gy_moff(a.O);  // start of the [gb_pre | gate matrices] section inside the row
-    if (seg1 && p < nW) a.gw_post[p] = (float)t;
-    else if (seg1 && p < nW + a.O) a.gb_post[p - nW] = (float)t;
-    else if (seg1 && a.part2) {
-      // split backward: the gy rows carry no adjoint section
-    } else if (blk0 == moff) {
+    if (p < nW) a.gw_post[p] = (float)t;
+    else if (p < nW + a.O) a.gb_post[p - nW] = (float)t;
+  } else if (seg2) {
+    if (blk0 == 0) {
       if (lane < FQ) a.gb_pre[lane] = (float)t;
-    } else if (blk0 > moff && lane < 4) {
-      const int gi = (blk0 - moff - 32) / 8 + lane;
+    } else if (lane < 4) {
+      const int gi = (blk0 - 32) / 8 + lane;
       if (gi < a.Lq * FQ) {
         double w3[3], g3[3];
 #pragma unroll
@@ -1001,6 +912,18 @@ int make_tmap_3d_f32(CUtensorMap* tm, const void* base, unsigned long long d0, u
   return 0;
 }
 
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// Experiment switches (defaults = the measured winners on B200, batch-16 stem step):
+//   QW_FWD_ETMA  1: the forward kernel requests its first x tiles before staging its parameters        (-1.0 us / step)
+//   QW_ADJ_FLAGS bit 1: forward recomputation of the adjoint kernel before the dependency wait         (-1.1 us)
+//                bit 0: adjoint kernel triggers its dependent right after the wait                     (+0.3 us: off)
+//   QW_PRE_EX    1: the pre_conv^T kernel requests its first x tiles before the dependency wait        (-1.7 us)
+static int flag_fwd_etma() { static const int v = env_flag("QW_FWD_ETMA", 1); return v; }
+static int flag_adj() { static const int v = env_flag("QW_ADJ_FLAGS", 2); return v; }
+static int flag_pre_ex() { static const int v = env_flag("QW_PRE_EX", 1); return v; }
 static bool g_fast_enabled = true;
 void set_fast_path(bool on) { g_fast_enabled = on; }
 
@@ -1036,7 +959,7 @@ FastPlan make_fast_plan(const ConvDims& d) {
   }
   p.gridGy = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
   p.small = p.num_tiles <= 6 * 2 * sms;   // <= 6 tiles per CTA: launch / ramp latency matters more than steady-state streaming
-  p.PA1 = gy_plen(d.O, d.Lq);
+  p.PA1 = gy_plen(d.O);
   const long long W = (long long)d.B * d.Lout;
   {
     const long long need = (W + kAdjThreads - 1) / kAdjThreads;
@@ -1053,6 +976,8 @@ FastPlan make_fast_plan(const ConvDims& d) {
   if (cap < 1) cap = 1;
   p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
   p.PB = p.Cpad * 12;
+  p.nlead_adj = (d.O * (FQ + 1) + kAdjRedCols - 1) / kAdjRedCols;
+  p.nlead_pre = p.PA2 / 32;
   size_t o = 0;
   p.off_gout = o; o = align_up(o + (size_t)W * FQ * 4, 256);
   p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
@@ -1085,7 +1010,7 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
   if (int e = make_tmap_3d_f32(&tm, x, d.L, d.C, d.B, xw, p.rc, false)) return e;
   const size_t W = (size_t)d.B * d.Lout;
   FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
-                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile};
+                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, flag_fwd_etma(), timeline_next_slot()};
   if (d.S == 1) {
     switch (p.rc) {
       case 32: return launch_fast_fwd<1, 32>(tm, a, p, st);
@@ -1103,20 +1028,6 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
 }
 
 template <int NHALF>
-static int launch_fast_gy(const CUtensorMap& tg, const CUtensorMap& tq, const FastGyArgs& a, const FastPlan& p, cudaStream_t st) {
-  const size_t smem = fast_gy_smem_bytes(a.O, a.Lq);
-  QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
-  auto k = fast_bwd_gy_kernel<NHALF>;
-  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    KernelTimer kt(kKBwdPost, st);
-    k<<<p.gridGy, kGyThreads, smem, st>>>(tg, tq, a);
-  }
-  QW_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-template <int NHALF>
 static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
   const size_t smem = fast_gy2_smem_bytes(a.O);
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
@@ -1130,9 +1041,9 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
   return 0;
 }
 
-static bool gy_fused() {
+static bool finalize_kernel_mode() {
   static const bool v = [] {
-    const char* e = getenv("QW_GY_FUSED");
+    const char* e = getenv("QW_FINALIZE_KERNEL");
     return e && e[0] == '1';
   }();
   return v;
@@ -1145,7 +1056,7 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKBwdPre, st);
-    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridPx, p.nchunks), dim3(kThreads), smem, st, tx, tgx, a));
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(a.nlead + p.gridPx * p.nchunks), dim3(kThreads), smem, st, tx, tgx, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1164,38 +1075,35 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
   if (int e = make_tmap_3d_f32(&tm_x, x, d.L, d.C, d.B, 32, 32, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
-  const bool split = !gy_fused();
   float* gout = reinterpret_cast<float*>(ws + p.off_gout);
   float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
-  if (split) {
-    // 1) stream gy: gout + partials of grad post_conv.{weight,bias}
-    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1};
+  const bool fin = finalize_kernel_mode();
+  // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
+  {
+    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, timeline_next_slot()};
     const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
     int e = nhalf == 1 ? launch_fast_gy2<1>(tm_gy, tm_qout, a, p, st)
           : nhalf == 2 ? launch_fast_gy2<2>(tm_gy, tm_qout, a, p, st)
                        : launch_fast_gy2<3>(tm_gy, tm_qout, a, p, st);
     if (e) return e;
-    // 2) adjoint differentiation of the circuit, one window per thread
-    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W};
+  }
+  // 2) adjoint differentiation of the circuit, one window per thread (+ leading CTAs: grad post_conv.* from the rows of 1)
+  {
+    const int nlead = fin ? 0 : p.nlead_adj;
+    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W,
+                   nlead, part1, p.gridGy, p.PA1, d.O, gw_post, gb_post, flag_adj(), timeline_next_slot()};
     const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
     if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       KernelTimer kt(kKBwdAdj, st);
-      QW_CUDA_OK(launch_pdl(p.small, fast_bwd_adj_kernel, dim3(p.gridAdj), dim3(kAdjThreads), smem, st, aa));
+      QW_CUDA_OK(launch_pdl(p.small, fast_bwd_adj_kernel, dim3(nlead + p.gridAdj), dim3(kAdjThreads), smem, st, aa));
     }
     QW_CUDA_OK(cudaGetLastError());
-  } else {
-    // 1) stream gy (+ adjoint circuit on dedicated warps)
-    FastGyArgs a{w_post, pre_save, qwts, gpre, part1, d.B, d.O, d.Lout, p.LP, d.Lq, p.tiles_per_utt, p.num_tiles, p.PA1};
-    const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
-    int e = nhalf == 1 ? launch_fast_gy<1>(tm_gy, tm_qout, a, p, st)
-          : nhalf == 2 ? launch_fast_gy<2>(tm_gy, tm_qout, a, p, st)
-                       : launch_fast_gy<3>(tm_gy, tm_qout, a, p, st);
-    if (e) return e;
   }
-  // 3) pre_conv^T
+  // 3) pre_conv^T (+ leading CTAs: grad pre_conv.bias / quantum_weights from the rows of 2)
   {
-    FastPreArgs a{gpre, w_pre, part3, d.B, d.C, d.L, d.P, d.Lout, p.LP, p.ptiles_per_utt, p.num_ptiles, p.Cpad};
+    FastPreArgs a{gpre, w_pre, part3, d.B, d.C, d.L, d.P, d.Lout, p.LP, p.ptiles_per_utt, p.num_ptiles, p.Cpad, p.gridPx,
+                  fin ? 0 : p.nlead_pre, part2, qwts, p.gridAdj, p.PA2, d.Lq, gb_pre, gqw, flag_pre_ex(), timeline_next_slot()};
     const int par = d.P & 1;
     int e;
     if (d.S == 1) e = gx ? launch_fast_pre<1, 0, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<1, 0, false>(tm_x, tm_gx, a, p, st);
@@ -1203,11 +1111,11 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     else          e = gx ? launch_fast_pre<2, 0, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<2, 0, false>(tm_x, tm_gx, a, p, st);
     if (e) return e;
   }
-  // 4) finalize
+  // 4) finalize: grad pre_conv.weight from the rows of 3 (QW_FINALIZE_KERNEL=1: all three segments)
   {
-    FastFinArgs a{part1, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridPx, p.PB, d.C, d.O, d.Lq,
-                  split ? part2 : nullptr, p.gridAdj, p.PA2};
-    const int nblk = p.PA1 / 32 + (split ? p.PA2 / 32 : 0) + p.PB / 32;
+    FastFinArgs a{fin ? part1 : nullptr, fin ? part2 : nullptr, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1,
+                  p.gridAdj, p.PA2, p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot()};
+    const int nblk = (fin ? p.PA1 / 32 + p.PA2 / 32 : 0) + p.PB / 32;
     {
       KernelTimer kt(kKBwdFinalize, st);
       QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel, dim3(nblk), dim3(kFFThreads), 0, st, a));

@@ -40,6 +40,7 @@ struct FastPlan {
   int tiles_per_utt, num_tiles, rc, chunks_per_tile, gridF;
   int gridGy, PA1, gridAdj, PA2, LP;
   int ptiles_per_utt, num_ptiles, nchunks, Cpad, gridPx, PB;
+  int nlead_adj, nlead_pre;  // reduce CTAs in front of the adjoint / pre_conv^T grids (the former finalize kernel)
   size_t off_gout, off_gpre, off_p1, off_p2, off_p3, ws_bytes;
   bool small;  // latency-dominated launch: use programmatic dependent launch
 };
@@ -50,6 +51,13 @@ struct FastAdjArgs {
   float *gpre_pad, *part;  // part: [grid][PA2] rows: [grad pre_conv.bias 4 + pad 28][Lq*32 gate-gradient matrices M]
   int B, Lout, LP, Lq, PA2;
   long long W;
+  // leading reduce CTAs: part1 = [G1][P1] rows of the gy kernel -> grad post_conv.{weight,bias}
+  int nlead;
+  const float* part1;
+  int G1, P1, O;
+  float *gw_post, *gb_post;
+  int early_trigger;  // bit 0: trigger the dependent launch right after the wait; bit 1: forward recomputation before the wait
+  unsigned long long* tl;
 };
 void set_fast_path(bool on);
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd);
@@ -59,6 +67,11 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
                   unsigned char* ws, const ConvDims& d, cudaStream_t st);
+
+// fused inference stem (qw_stem.cu)
+size_t stem_workspace_bytes(int B, int L);
+int stem_forward(const float* x, const float* const* p1, const float* const* p2, const float* pos, float* out, void* ws, size_t ws_bytes,
+                 int B, int Cin, int L, int Cmid, int O, int Lq, cudaStream_t st);
 
 // per-(T,Q) entry points, explicitly instantiated in qw_conv1d_inst.cu
 template <typename T, int Q>

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .quantum_conv1d import QuantumConv1d
+from .quantum_conv1d import QuantumConv1d, fused_stem_eligible, fused_stem_forward
 
 
 @dataclass
@@ -127,9 +127,21 @@ class QuantumAudioEncoder(AudioEncoder):
         self.conv1 = QuantumConv1d(n_mels, n_state, kernel_size=3, padding=1, n_qubits=n_qubits, **qkw)
         self.conv2 = QuantumConv1d(n_state, n_state, kernel_size=3, stride=2, padding=1, n_qubits=n_qubits, **qkw)
 
+        self.fused_stem = True  # inference only: both layers + GELUs + permute + positional embedding in two kernels
+
     def to(self, *args, **kwargs):
         super().to(*args, **kwargs)
         return self
+
+    def forward(self, x):
+        # when no autograd graph is being recorded the stem runs fused (qw_stem_forward); training and any
+        # shape outside the fast-path regime take the operator-by-operator path of AudioEncoder.forward
+        if self.fused_stem and not torch.is_grad_enabled() and fused_stem_eligible(self.conv1, self.conv2, x):
+            x = fused_stem_forward(self.conv1, self.conv2, x, self.positional_embedding)
+            for blk in self.blocks:
+                x = blk(x)
+            return self.ln_post(x)
+        return super().forward(x)
 
 
 class QuantumWhisper(nn.Module):

@@ -148,6 +148,55 @@ class QuantumConv1d(nn.Module):
                 f"embedding={self.embedding!r}")
 
 
+def fused_stem_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor) -> bool:
+    """True when ``gelu(conv2(gelu(conv1(x))))`` can run through ``qw_stem_forward`` (inference, fast-path regime)."""
+    def ok(m, K, S, P):
+        return (isinstance(m, QuantumConv1d) and m.kernel_size == K and m.stride == S and m.padding == P and m.n_qubits == 4
+                and m.embedding == "amplitude" and m.n_layers <= 4)
+    return (ok(conv1, 3, 1, 1) and ok(conv2, 3, 2, 1) and conv1.n_layers == conv2.n_layers and conv2.in_channels == conv1.out_channels
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[1] == conv1.in_channels and x.shape[2] % 4 == 0
+            and conv1.out_channels % 4 == 0 and conv2.out_channels % 4 == 0 and conv1.out_channels <= 576
+            and conv2.out_channels <= 576 and conv1.in_channels * 3 * 16 <= 96 * 1024)
+
+
+@torch.no_grad()
+def fused_stem_forward(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor,
+                       positional_embedding: torch.Tensor | None = None) -> torch.Tensor:
+    """Inference forward of the encoder stem in two kernels:
+
+        gelu(conv2(gelu(conv1(x)))).permute(0, 2, 1) + positional_embedding      # whisper/whisper/model.py:193-198
+
+    x (B, n_mels, L) -> (B, L // 2, n_state).  The (B, n_state, L) activation between the layers is never written.
+    No autograd graph is recorded: use the two modules for training."""
+    if not fused_stem_eligible(conv1, conv2, x):
+        raise ValueError("fused_stem_forward needs the Whisper stem regime (n_qubits=4, k3/s1/p1 + k3/s2/p1, fp32 CUDA input, "
+                         "L % 4 == 0, channel counts % 4 == 0 and <= 576)")
+    lib = _lib.load()
+    B, C, L = x.shape
+    hidden, O = conv1.out_channels, conv2.out_channels
+    x = x.contiguous()
+    p1 = [t.detach().contiguous() for t in (conv1.pre_conv.weight, conv1.pre_conv.bias, conv1.quantum_weights,
+                                            conv1.post_conv.weight, conv1.post_conv.bias)]
+    p2 = [t.detach().contiguous() for t in (conv2.pre_conv.weight, conv2.pre_conv.bias, conv2.quantum_weights,
+                                            conv2.post_conv.weight, conv2.post_conv.bias)]
+    for t in p1 + p2:
+        if t.device != x.device or t.dtype != torch.float32:
+            raise RuntimeError("stem parameters must be float32 on the input's device")
+    pos = None
+    if positional_embedding is not None:
+        if tuple(positional_embedding.shape) != (L // 2, O):
+            raise AssertionError("incorrect audio shape")  # whisper/model.py:197
+        pos = positional_embedding.to(device=x.device, dtype=torch.float32).contiguous()
+    out = torch.empty(B, L // 2, O, device=x.device, dtype=torch.float32)
+    nbytes = lib.qw_stem_workspace_bytes(B, L)
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        st = lib.qw_stem_forward(_ptr(x), *[_ptr(t) for t in p1], *[_ptr(t) for t in p2], _ptr(pos), _ptr(out), _ptr(ws), nbytes,
+                                 B, C, L, hidden, O, conv1.n_layers, _stream())
+    _lib.check(st, "qw_stem_forward")
+    return out
+
+
 class _CircuitFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pre, qw, n_layers, emb):

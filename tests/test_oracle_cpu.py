@@ -246,3 +246,18 @@ def test_logmel_batched_max_is_per_utterance():
     both = lo.log_mel_spectrogram(a)
     assert np.array_equal(both[0], lo.log_mel_spectrogram(a[0]))
     assert np.array_equal(both[1], lo.log_mel_spectrogram(a[1]))
+
+
+def test_stem_oracle_is_the_composition_of_the_literal_layers():
+    """oracle.stem_forward == literal loop nest of conv1 -> gelu -> literal conv2 -> gelu -> permute + pos (model.py:193-198)."""
+    p1 = qo.make_params(5, 8, 3, 4, seed=11)
+    p2 = qo.make_params(8, 8, 3, 4, seed=12)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 5, 12, generator=g, dtype=torch.float64)
+    pos = torch.randn(6, 8, generator=g, dtype=torch.float64)
+    h = torch.nn.functional.gelu(qo.qconv1d_literal(x, *p1, 3, 1, 1))
+    h = torch.nn.functional.gelu(qo.qconv1d_literal(h, *p2, 3, 2, 1))
+    ref = h.permute(0, 2, 1) + pos
+    got = qo.stem_forward(x, p1, p2, pos)
+    assert got.shape == (2, 6, 8)
+    assert (got - ref).abs().max().item() < 1e-12

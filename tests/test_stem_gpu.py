@@ -1,0 +1,96 @@
+"""Fused inference stem (qw_stem_forward) against the fp64 oracle and against the operator-by-operator path.
+
+    out = gelu(conv2(gelu(conv1(x)))).permute(0, 2, 1) + positional_embedding     (whisper/whisper/model.py:193-198)
+
+Tolerance: the stem output is a layer output after two post_conv maps (|y| up to a few units); 5e-5 relative to max(1, |ref|),
+the same bound the layer-output tests of test_qconv_gpu.py use.  Fused vs unfused (same kernels' arithmetic, torch's GELU in
+between) must agree to 2e-6: the only difference is erff vs ATen's erf.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qconv_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+
+def _stem(cuda, n_mels, n_state, seed, n_layers=1):
+    from qasr_ijcnlp_b200 import QuantumConv1d
+
+    torch.manual_seed(seed)
+    c1 = QuantumConv1d(n_mels, n_state, kernel_size=3, padding=1, n_qubits=4, n_layers=n_layers).to(cuda)
+    c2 = QuantumConv1d(n_state, n_state, kernel_size=3, stride=2, padding=1, n_qubits=4, n_layers=n_layers).to(cuda)
+    return c1, c2
+
+
+def _params64(m):
+    return tuple(t.detach().double().cpu() for t in (m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight,
+                                                     m.post_conv.bias))
+
+
+@pytest.mark.parametrize("B,n_mels,n_state,L,n_layers", [
+    (2, 80, 384, 3000, 1),    # Whisper-Tiny stem (ragged last tile: 1500 = 46 * 32 + 28)
+    (1, 80, 384, 64, 1),      # a single tile, left and right padding inside it
+    (3, 8, 64, 200, 2),       # small channels, two circuit layers, L_out2 = 100 (not a multiple of 32)
+    (1, 12, 132, 260, 1),     # channel counts that are not multiples of 32 / 128
+])
+def test_fused_stem_vs_oracle_and_unfused(cuda, B, n_mels, n_state, L, n_layers):
+    from qasr_ijcnlp_b200 import fused_stem_forward
+    from qasr_ijcnlp_b200.encoder import sinusoids
+
+    c1, c2 = _stem(cuda, n_mels, n_state, seed=B * 1000 + L, n_layers=n_layers)
+    g = torch.Generator().manual_seed(7 + L)
+    x64 = torch.rand(B, n_mels, L, generator=g, dtype=torch.float64) * 3 - 1.5   # log-mel range
+    pos = sinusoids(L // 2, n_state)
+    x = x64.float().to(cuda)
+    out = fused_stem_forward(c1, c2, x, pos.to(cuda))
+    assert out.shape == (B, L // 2, n_state) and out.dtype == torch.float32
+    ref = qo.stem_forward(x64.float().double(), _params64(c1), _params64(c2), pos.double())
+    err = (out.double().cpu() - ref).abs() / ref.abs().clamp(min=1.0)
+    assert err.max().item() <= 5e-5, err.max().item()
+    with torch.no_grad():
+        unf = torch.nn.functional.gelu(c2(torch.nn.functional.gelu(c1(x)))).permute(0, 2, 1) + pos.to(cuda)
+    assert (out - unf).abs().max().item() <= 2e-6
+    # without the positional table
+    out2 = fused_stem_forward(c1, c2, x, None)
+    assert (out2 + pos.to(cuda) - out).abs().max().item() <= 1e-6
+
+
+def test_encoder_uses_fused_stem_in_inference_only(cuda):
+    from qasr_ijcnlp_b200 import QuantumAudioEncoder, _lib
+
+    torch.manual_seed(3)
+    enc = QuantumAudioEncoder(80, 1500, 384, 6, 1, n_qubits=4).to(cuda)
+    mel = (torch.rand(2, 80, 3000, device=cuda) * 3 - 1.5)
+    names = lambda: {k: v[1] for k, v in _lib.profile_read(reset=True).items()}
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    with torch.no_grad():
+        y_fused = enc(mel)
+    torch.cuda.synchronize()
+    k_inf = names()
+    y_train = enc(mel)   # grad enabled: operator-by-operator path, autograd graph recorded
+    torch.cuda.synchronize()
+    k_train = names()
+    _lib.profile_enable(False)
+    assert k_inf.get("stem2_kernel") == 1 and k_inf.get("qconv_fwd_kernel") == 1
+    assert "stem2_kernel" not in k_train and k_train.get("qconv_fwd_kernel") == 2
+    assert y_train.requires_grad and not y_fused.requires_grad
+    assert (y_fused - y_train.detach()).abs().max().item() <= 2e-4   # through 1 transformer block + LayerNorm
+    enc.fused_stem = False
+    with torch.no_grad():
+        y_off = enc(mel)
+    assert torch.equal(y_off, y_train.detach())
+
+
+def test_fused_stem_rejects_other_regimes(cuda):
+    from qasr_ijcnlp_b200 import QuantumConv1d, fused_stem_eligible, fused_stem_forward
+
+    c1, c2 = _stem(cuda, 80, 384, seed=0)
+    assert not fused_stem_eligible(c1, c2, torch.zeros(1, 80, 3002, device=cuda))          # L % 4 != 0
+    assert not fused_stem_eligible(c1, c2, torch.zeros(1, 80, 3000))                        # CPU tensor
+    c3 = QuantumConv1d(384, 384, kernel_size=3, stride=2, padding=1, n_qubits=6).to(cuda)
+    assert not fused_stem_eligible(c1, c3, torch.zeros(1, 80, 3000, device=cuda))           # n_qubits != 4
+    with pytest.raises(ValueError):
+        fused_stem_forward(c1, c3, torch.zeros(1, 80, 3000, device=cuda))
