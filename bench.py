@@ -433,6 +433,13 @@ def run_b200(args):
         except Exception as e:  # keep the headline line alive
             enc = {"error": repr(e)[:200]}
 
+    stem_inf = None
+    if not args.no_encoder and rank == 0:
+        try:
+            stem_inf = run_stem_infer(B, max(3, min(K, 50)), dev)
+        except Exception as e:
+            stem_inf = {"error": repr(e)[:200]}
+
     enc_train = None
     if not args.no_encoder:
         try:
@@ -470,7 +477,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "step_roofline_frac": round(step_frac, 4), "kernels": kernels,
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
-            "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
+            "stem_infer": stem_inf, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
         }
         emit(line)
     if world > 1:
@@ -583,6 +590,37 @@ def run_encoder_fwd(B, K, dev, world):
     ms = max_over_ranks(time_events(step, K), world, dev)
     return {"value": round(world * B * K / (ms * 1e-3), 2), "unit": "utt/s", "ms_per_step": round(ms / K, 4),
             "workload": f"log-mel + QuantumWhisper-Tiny encoder fwd + Linear(384,35), batch {B}, host audio in"}
+
+
+def run_stem_infer(B, K, dev):
+    """inference stem mel (B,80,3000) -> (B,1500,384): gelu(conv2(gelu(conv1(x)))).permute(0,2,1) + pos, fused
+    (qw_stem_forward: two kernels, the (B,384,3000) intermediate never written) vs operator by operator (two QuantumConv1d
+    forwards + torch GELU / permute / add).  Inputs resident in HBM, rotating sets."""
+    import torch.nn.functional as F
+
+    from qasr_ijcnlp_b200 import QuantumConv1d, fused_stem_forward
+    from qasr_ijcnlp_b200.encoder import sinusoids
+
+    torch.manual_seed(0)
+    c1 = QuantumConv1d(N_MELS, N_STATE, kernel_size=3, padding=1, n_qubits=Q).to(dev)
+    c2 = QuantumConv1d(N_STATE, N_STATE, kernel_size=3, stride=2, padding=1, n_qubits=Q).to(dev)
+    pos = sinusoids(1500, N_STATE).to(dev)
+    xs = [torch.rand(B, N_MELS, 3000, device=dev) * 3 - 1.5 for _ in range(4)]
+
+    def fused(i):
+        return fused_stem_forward(c1, c2, xs[i % 4], pos)
+
+    def unfused(i):
+        with torch.no_grad():
+            return F.gelu(c2(F.gelu(c1(xs[i % 4])))).permute(0, 2, 1) + pos
+
+    diff = (fused(0) - unfused(0)).abs().max().item()
+    for i in range(3):
+        fused(i), unfused(i)
+    t_f, t_u = time_events(fused, K) / K, time_events(unfused, K) / K
+    return {"fused_ms": round(t_f, 5), "unfused_ms": round(t_u, 5), "fused_utt_per_s": round(B / t_f * 1e3, 1),
+            "unfused_utt_per_s": round(B / t_u * 1e3, 1), "max_abs_diff_fused_vs_unfused": diff,
+            "workload": f"inference stem, batch {B}: mel (B,80,3000) -> (B,1500,384) incl. both GELUs, permute, positional embedding"}
 
 
 def run_encoder_train(B, K, dev, world, rank):

@@ -25,7 +25,11 @@
 namespace qw {
 
 constexpr int FQ = 4;     // n_qubits on the fast path
-constexpr int FTW = 32;   // windows per tile (forward, gy streaming)
+constexpr int FTW = 32;   // windows a tile's shared-memory boxes cover (forward, gy streaming)
+// Tiles ADVANCE by a run-time stride tw <= FTW (a multiple of 4; default FTW, QW_TW=16..28 for experiments).  The idea was to
+// even out the rounds of the persistent grid (batch 16: 1 504 / 752 tiles of 32 windows for 296 CTAs = 5.08 / 2.54 tiles per
+// CTA, i.e. 6 / 3 rounds of which the last is nearly empty; a stride of 28 makes 6 / 3 rounds of 28 windows).  Measured: no gain
+// (see make_fast_plan).  The TMA boxes keep their size (the columns past tw are the neighbour tile's), lanes past tw do not store.
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -41,6 +45,7 @@ struct FastFwdArgs {
   float *y, *pre_save, *qout_save;
   int B, C, L, P, O, Lq, Lout;
   int tiles_per_utt, num_tiles, chunks_per_tile;
+  int tw;  // tile stride in windows
   int early_tma;
   unsigned long long* tl;
 };
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
     const int n = g / a.chunks_per_tile, ch = g - n * a.chunks_per_tile;
     const int tile = blockIdx.x + n * gridDim.x;
     const int b = tile / a.tiles_per_utt;
-    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int i0 = (tile - b * a.tiles_per_utt) * a.tw;
     const int s = g % kFwdStages;
     mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * 4);
     tma_load_3d(stage + (size_t)s * STAGE_ELEMS, &tm_x, i0 * S - 4, ch * RC, b, &full[s]);
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
     for (int n = 0; n < my_tiles; ++n) {
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / a.tiles_per_utt;
-      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      const int i = (tile - b * a.tiles_per_utt) * a.tw + lane;
       const int pb = n & 1, ph = (n >> 1) & 1;
       mbar_wait(&pfull[pb], ph);
       const float* pp = part + (size_t)pb * kFwdSW * FTW * FQ;
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&pempty[pb]);
       float out[FQ] = {0.f, 0.f, 0.f, 0.f};
-      if (i < a.Lout) {
+      if (lane < a.tw && i < a.Lout) {
         float re[1 << FQ], im[1 << FQ];
         circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
         const size_t wi = (size_t)b * a.Lout + i;
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       const int m = n - 1;
       const int tile = blockIdx.x + m * gridDim.x;
       const int b = tile / a.tiles_per_utt;
-      const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+      const int i0 = (tile - b * a.tiles_per_utt) * a.tw;
       const int ob = m & 1;
       mbar_wait(&ofull[ob], (m >> 1) & 1);
       const float* oo = outs + (size_t)ob * FTW * FQ;
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&oempty[ob]);
       if (a.y == nullptr) continue;  // readouts only (fused stem, qw_stem.cu): the circuit warp has stored them
-      const bool store_ok = (i0 + 4 * tl) < a.Lout;  // Lout % 4 == 0: a lane's 4 windows are all valid or all invalid
+      const bool store_ok = (i0 + 4 * tl) < a.Lout && 4 * tl < a.tw;  // Lout % 4 == 0: a lane's 4 windows are all valid or all invalid
       float* __restrict__ yb = a.y + (size_t)b * a.O * a.Lout + i0 + 4 * tl;
       const int ngroups = a.O >> 2;
 #pragma unroll 4
@@ -321,6 +326,7 @@ struct FastGy2Args {
   const float* w_post;
   float *gout, *part;  // gout: [B*Lout][4]; part: [gridDim.x][PA1]
   int B, O, Lout, tiles_per_utt, num_tiles, PA1;
+  int tw;  // tile stride in windows (the qout box has tw rows)
   unsigned long long* tl;
 };
 __host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O) {
@@ -369,9 +375,9 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
     const int n = gs / NHALF, h = gs - n * NHALF;
     const int tile = blockIdx.x + n * gridDim.x;
     const int b = tile / a.tiles_per_utt;
-    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int i0 = (tile - b * a.tiles_per_utt) * a.tw;
     const int s = gs % kGyStages;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(kGyStageElems + (h == 0 ? FTW * FQ : 0)) * 4);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(kGyStageElems + (h == 0 ? a.tw * FQ : 0)) * 4);
 #pragma unroll
     for (int bx = 0; bx < 3; ++bx)
       tma_load_3d(stages + (size_t)s * kGyStageElems + bx * 64 * 32, &tm_gy, i0, h * kGyStageRows + bx * 64, b, &full[s]);
@@ -381,6 +387,7 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
     for (int gs = 0; gs < kGyStages - 1 && gs < total_stages; ++gs) issue(gs);
 
   int gs = 0;
+  const int nchunk = a.tw >> 2;
   for (int n = 0; n < my_tiles; ++n) {
     float gacc[4][FQ];
 #pragma unroll
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
       {
         const int rl = tid;  // 0..191
 #pragma unroll 2
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < nchunk; ++c) {  // only the tile's own tw windows count towards the weight gradients
           const float4 gv = ld4(gsm + swz128(rl, c));
           const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
@@ -458,14 +465,14 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
     if (warp == n % kGySW) {
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / a.tiles_per_utt;
-      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      const int i = (tile - b * a.tiles_per_utt) * a.tw + lane;
       float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int w = 0; w < kGySW; ++w) {
         const float4 pv = ld4(gr + ((size_t)w * FTW + lane) * FQ);
         sacc.x += pv.x; sacc.y += pv.y; sacc.z += pv.z; sacc.w += pv.w;
       }
-      if (i < a.Lout) st4(a.gout + ((size_t)b * a.Lout + i) * FQ, sacc);
+      if (lane < a.tw && i < a.Lout) st4(a.gout + ((size_t)b * a.Lout + i) * FQ, sacc);
     }
   }
   // ---- partial row of this CTA: [O*4 grad post_conv.weight][O grad post_conv.bias][pad]
@@ -946,7 +953,16 @@ bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const 
 FastPlan make_fast_plan(const ConvDims& d) {
   FastPlan p{};
   const int sms = num_sms();
-  p.tiles_per_utt = (d.Lout + FTW - 1) / FTW;
+  {
+    // tile stride: FTW unless QW_TW forces 16..32 (A/B switch).  Measured on B200 at batch 16 (stem step, same box):
+    // stride 32: 140.1 us, 28: 140.2 us, 24: 154.4 us -- the rounds are bound by per-tile latency (TMA round trip + the
+    // circuit warp's dependent chain + the hand-offs), not by the bytes of a tile, so narrower tiles only add tiles.
+    static const int forced = env_flag("QW_TW", 0);
+    for (int tw = FTW; tw >= 16; tw -= 4)
+      if (tw == forced) p.tw = tw;
+    if (p.tw == 0) p.tw = FTW;
+  }
+  p.tiles_per_utt = (d.Lout + p.tw - 1) / p.tw;
   p.num_tiles = d.B * p.tiles_per_utt;
   p.rc = d.C <= 128 ? (int)align_up(d.C, 32) : 64;  // small C: the whole channel range is one TMA box per tile
   p.chunks_per_tile = (d.C + p.rc - 1) / p.rc;
@@ -1010,7 +1026,7 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
   if (int e = make_tmap_3d_f32(&tm, x, d.L, d.C, d.B, xw, p.rc, false)) return e;
   const size_t W = (size_t)d.B * d.Lout;
   FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
-                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, flag_fwd_etma(), timeline_next_slot()};
+                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot()};
   if (d.S == 1) {
     switch (p.rc) {
       case 32: return launch_fast_fwd<1, 32>(tm, a, p, st);
@@ -1072,7 +1088,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   float* part3 = reinterpret_cast<float*>(ws + p.off_p3);
   alignas(64) CUtensorMap tm_gy, tm_qout, tm_x, tm_gx;
   if (int e = make_tmap_3d_f32(&tm_gy, gy, d.Lout, d.O, d.B, 32, 64, true)) return e;
-  if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
+  if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, p.tw, false)) return e;
   if (int e = make_tmap_3d_f32(&tm_x, x, d.L, d.C, d.B, 32, 32, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
   float* gout = reinterpret_cast<float*>(ws + p.off_gout);
@@ -1080,7 +1096,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   const bool fin = finalize_kernel_mode();
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
   {
-    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, timeline_next_slot()};
+    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot()};
     const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
     int e = nhalf == 1 ? launch_fast_gy2<1>(tm_gy, tm_qout, a, p, st)
           : nhalf == 2 ? launch_fast_gy2<2>(tm_gy, tm_qout, a, p, st)

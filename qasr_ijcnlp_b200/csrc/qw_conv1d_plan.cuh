@@ -37,7 +37,7 @@ inline WsLayout<T> ws_layout(const ConvDims& d, const Plan& p) {
 
 // ---- fast path (qw_conv1d_fast.cu): fp32, q = 4, K = 3, stride 1|2, aligned shapes
 struct FastPlan {
-  int tiles_per_utt, num_tiles, rc, chunks_per_tile, gridF;
+  int tw, tiles_per_utt, num_tiles, rc, chunks_per_tile, gridF;
   int gridGy, PA1, gridAdj, PA2, LP;
   int ptiles_per_utt, num_ptiles, nchunks, Cpad, gridPx, PB;
   int nlead_adj, nlead_pre;  // reduce CTAs in front of the adjoint / pre_conv^T grids (the former finalize kernel)

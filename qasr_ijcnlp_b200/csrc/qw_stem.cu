@@ -34,8 +34,9 @@ __device__ __forceinline__ int q1_slot(int p) { return p + (p >> 3); }
 // torch.nn.functional.gelu (approximate='none'): 0.5 v (1 + erf(v / sqrt 2)) = max(v, 0) - 0.5 |v| erfc(|v| / sqrt 2).
 // The second form has no 1 - e cancellation, and erfc(u / sqrt 2) = 2^(-u Q(u)) with Q a degree-7 polynomial (weighted
 // least-squares fit on [0, 6] of -log2(erfc(u / sqrt 2)) / u, weight u erfc: the error of the RESULT is what is minimised;
-// Q stays > 4.8 beyond 6, so the tail underflows to the right limit).  12 instructions instead of erff's 24 (two coefficient
+// Q stays > 4.8 beyond 6, so the tail underflows to the right limit).  11 instructions instead of erff's 24 (two coefficient
 // sets + selects), max |error| 2.7e-7 against the fp64 GELU on [-40, 40] -- ATen's own fp32 gelu is 1.2e-6 off on that range.
+// The factor 0.5 rides in the exponent (-u Q - 1) and the final subtraction is one fma.
 __device__ __forceinline__ float gelu_erf(float v) {
   const float u = fabsf(v);
   float q = 2.8103786462452263e-06f;
@@ -47,8 +48,8 @@ __device__ __forceinline__ float gelu_erf(float v) {
   q = fmaf(q, u, 0.4592074155807495f);
   q = fmaf(q, u, 1.151105284690857f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(u * q)));
-  return fmaxf(v, 0.f) - (0.5f * u) * e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(-u, q, -1.f)));
+  return fmaf(-u, e, fmaxf(v, 0.f));
 }
 __device__ __forceinline__ void bar_stream() { asm volatile("bar.sync 1, %0;" ::"n"(kSW * 32) : "memory"); }
 
@@ -62,18 +63,21 @@ struct Stem2Args {
   unsigned long long* tl;
 };
 
-__host__ __device__ constexpr size_t stem2_smem_bytes(int C, int O, int Lq) {
+// hidden channels are padded to a multiple of the 32 rows one pass of the 8 streaming warps covers (zero weights: no branch)
+__host__ __device__ constexpr int stem2_cpad(int C) { return (int)align_up((size_t)C, 4 * kSW); }
+__host__ __device__ constexpr size_t stem2_smem_bytes(int Creal, int O, int Lq) {
+  const size_t C = stem2_cpad(Creal);
   return ((size_t)C * 3 * SQ + (size_t)C * SQ + align_up(C, 4) + (size_t)O * SQ + align_up(O, 4) + 4 + (size_t)Lq * SQ * kGateStride +
           (size_t)kQ1Slots * 4 + 2 * kSW * STW * SQ + 2 * STW * SQ) * 4 + 8 * 8;
 }
 
 __global__ void __launch_bounds__(kStemThreads, 2) stem2_kernel(const Stem2Args a) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
-  const int CK = a.C * 3;
-  float* wpre_t = reinterpret_cast<float*>(smem_dyn);            // [C*3][4]
-  float* wpost1 = wpre_t + (size_t)CK * SQ;                      // [C][4]
-  float* bpost1 = wpost1 + (size_t)a.C * SQ;                     // [C]
-  float* wpost2_t = bpost1 + align_up(a.C, 4);                   // [4][O]
+  const int CK = a.C * 3, Cp = stem2_cpad(a.C);
+  float* wpre_t = reinterpret_cast<float*>(smem_dyn);            // [Cp*3][4]
+  float* wpost1 = wpre_t + (size_t)Cp * 3 * SQ;                  // [Cp][4]
+  float* bpost1 = wpost1 + (size_t)Cp * SQ;                      // [Cp]
+  float* wpost2_t = bpost1 + Cp;                                 // [4][O]
   float* bpost2 = wpost2_t + (size_t)a.O * SQ;                   // [O]
   float* bpre = bpost2 + align_up(a.O, 4);                       // [4]
   float* gates = bpre + 4;                                       // [Lq][4][16]
@@ -117,6 +121,12 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem2_kernel(const Stem2Args 
     st4(wpost1 + (size_t)u * SQ, ld4(a.w_post1 + (size_t)u * SQ));
     bpost1[u] = a.b_post1[u];
   }
+  for (int u = a.C + tid; u < Cp; u += kStemThreads) {  // padding rows: h = gelu(0) = 0 times zero weights
+    st4(wpost1 + (size_t)u * SQ, make_float4(0.f, 0.f, 0.f, 0.f));
+    bpost1[u] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st4(wpre_t + (size_t)(u * 3 + k) * SQ, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
   for (int u = tid; u < a.O; u += kStemThreads) {
     const float4 w = ld4(a.w_post2 + (size_t)u * SQ);
     wpost2_t[0 * a.O + u] = w.x;
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem2_kernel(const Stem2Args 
     // ======================================================== circuit warp: one lane per window
     for (int n = 0; n < my_tiles; ++n) {
       const int pb = n & 1, ph = (n >> 1) & 1;
-      mbar_wait(&pfull[pb], ph);
+      while (!mbar_try_wait(&pfull[pb], ph)) __nanosleep(256);  // a tile of pre_conv takes microseconds: do not burn issue slots
       const float* pp = part + (size_t)pb * kSW * STW * SQ;
       float pre[SQ];
 #pragma unroll
@@ -160,58 +170,63 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem2_kernel(const Stem2Args 
   }
 
   // ========================================================== streaming warps
-  const int rows_it = a.C / (4 * kSW) + ((a.C % (4 * kSW)) ? 1 : 0);
+  const int rows_it = Cp / (4 * kSW);
+  // q1 tile of a tile: time steps 2*i0 - 4 ... 2*i0 + 67, one float4 per thread 0..71, fetched one tile ahead into a register
+  auto q1_fetch = [&](int n) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < kQ1Cols && n < my_tiles) {
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / a.tiles_per_utt;
+      const int t = 2 * (tile - b * a.tiles_per_utt) * STW - 4 + tid;
+      if (t >= 0 && t < a.L) v = ld4(a.q1 + ((size_t)b * a.L + t) * SQ);
+    }
+    return v;
+  };
+  float4 q1_next = q1_fetch(0);
   for (int n = 0; n <= my_tiles; ++n) {
     if (n < my_tiles) {
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / a.tiles_per_utt;
       const int i0 = (tile - b * a.tiles_per_utt) * STW;
-      // ---- q1 tile: time steps 2*i0 - 4 ... 2*i0 + 67 (zero outside [0, L): conv2's padding acts on h, see below)
       bar_stream();  // everyone is done with the previous tile's q1
-      if (tid < kQ1Cols) {
-        const int t = 2 * i0 - 4 + tid;
-        const float4 v = (t >= 0 && t < a.L) ? ld4(a.q1 + ((size_t)b * a.L + t) * SQ) : make_float4(0.f, 0.f, 0.f, 0.f);
-        st4(q1t + (size_t)q1_slot(tid) * 4, v);
-      }
+      if (tid < kQ1Cols) st4(q1t + (size_t)q1_slot(tid) * 4, q1_next);
       bar_stream();
+      q1_next = q1_fetch(n + 1);
       // this lane's 4 adjacent windows need the 9 time steps of columns 8*tl + 3 ... 8*tl + 11
       float4 qv[9];
-      unsigned vmask = 0;
 #pragma unroll
-      for (int m = 0; m < 9; ++m) {
-        const int p = 8 * tl + 3 + m;
-        qv[m] = ld4(q1t + (size_t)q1_slot(p) * 4);
-        const int t = 2 * i0 - 4 + p;
-        vmask |= (t >= 0 && t < a.L) ? (1u << m) : 0u;  // out-of-range taps are conv2's zero padding: h = 0 there, not gelu(b)
-      }
+      for (int m = 0; m < 9; ++m) qv[m] = ld4(q1t + (size_t)q1_slot(8 * tl + 3 + m) * 4);
+      // conv2's zero padding acts on h: the tap at time step -1 (window 0, k = 0) is 0, not gelu(b).  Time steps >= L are only
+      // ever touched by windows >= L_out, which are never stored.
+      const bool pad_left = (i0 == 0) && (tl == 0);
       float acc[4][SQ];
 #pragma unroll
       for (int w = 0; w < 4; ++w)
 #pragma unroll
         for (int j = 0; j < SQ; ++j) acc[w][j] = 0.f;
+#pragma unroll 2
       for (int it = 0; it < rows_it; ++it) {
-        const int c = it * (4 * kSW) + warp * 4 + rr;  // hidden channel
-        if (c < a.C) {
-          const float4 w1 = ld4(wpost1 + (size_t)c * SQ);
-          const float b1 = bpost1[c];
-          float xc[9];
+        const int c = it * (4 * kSW) + warp * 4 + rr;  // hidden channel (rows >= C carry zero weights)
+        const float4 w1 = ld4(wpost1 + (size_t)c * SQ);
+        const float b1 = bpost1[c];
+        float xc[9];
 #pragma unroll
-          for (int m = 0; m < 9; ++m) {
-            // same fma order as the forward kernel's post_conv, so h matches the unfused layer output bit for bit
-            const float v = fmaf(w1.w, qv[m].w, fmaf(w1.z, qv[m].z, fmaf(w1.y, qv[m].y, fmaf(w1.x, qv[m].x, b1))));
-            xc[m] = ((vmask >> m) & 1u) ? gelu_erf(v) : 0.f;
-          }
+        for (int m = 0; m < 9; ++m) {
+          // same fma order as the forward kernel's post_conv, so h matches the unfused layer output bit for bit
+          const float v = fmaf(w1.w, qv[m].w, fmaf(w1.z, qv[m].z, fmaf(w1.y, qv[m].y, fmaf(w1.x, qv[m].x, b1))));
+          xc[m] = gelu_erf(v);
+        }
+        if (pad_left) xc[0] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float4 wv = ld4(wpre_t + (size_t)(c * 3 + k) * SQ);
+        for (int k = 0; k < 3; ++k) {
+          const float4 wv = ld4(wpre_t + (size_t)(c * 3 + k) * SQ);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const float xv = xc[w * 2 + k];
-              acc[w][0] = fmaf(wv.x, xv, acc[w][0]);
-              acc[w][1] = fmaf(wv.y, xv, acc[w][1]);
-              acc[w][2] = fmaf(wv.z, xv, acc[w][2]);
-              acc[w][3] = fmaf(wv.w, xv, acc[w][3]);
-            }
+          for (int w = 0; w < 4; ++w) {
+            const float xv = xc[w * 2 + k];
+            acc[w][0] = fmaf(wv.x, xv, acc[w][0]);
+            acc[w][1] = fmaf(wv.y, xv, acc[w][1]);
+            acc[w][2] = fmaf(wv.z, xv, acc[w][2]);
+            acc[w][3] = fmaf(wv.w, xv, acc[w][3]);
           }
         }
       }
@@ -254,6 +269,12 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem2_kernel(const Stem2Args 
         const float4 w0 = ld4(wpost2_t + 0 * (size_t)a.O + o), w1 = ld4(wpost2_t + 1 * (size_t)a.O + o);
         const float4 w2 = ld4(wpost2_t + 2 * (size_t)a.O + o), w3 = ld4(wpost2_t + 3 * (size_t)a.O + o);
         const float4 bv = ld4(bpost2 + o);
+        float4 pe[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + warp * 4 + e;
+          pe[e] = (a.pos && i < a.Lout) ? __ldg(reinterpret_cast<const float4*>(a.pos + (size_t)i * a.O + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = i0 + warp * 4 + e;
@@ -264,10 +285,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem2_kernel(const Stem2Args 
             r.z = fmaf(w3.z, q2[e].w, fmaf(w2.z, q2[e].z, fmaf(w1.z, q2[e].y, fmaf(w0.z, q2[e].x, bv.z))));
             r.w = fmaf(w3.w, q2[e].w, fmaf(w2.w, q2[e].z, fmaf(w1.w, q2[e].y, fmaf(w0.w, q2[e].x, bv.w))));
             r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
-            if (a.pos) {
-              const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pos + (size_t)i * a.O + o));
-              r.x += pe.x; r.y += pe.y; r.z += pe.z; r.w += pe.w;
-            }
+            r.x += pe[e].x; r.y += pe[e].y; r.z += pe[e].z; r.w += pe[e].w;
             st4(a.out + ((size_t)b * a.Lout + i) * a.O + o, r);
           }
         }

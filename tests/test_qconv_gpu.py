@@ -185,8 +185,13 @@ def test_fast_and_generic_agree_full_size(cuda):
             grads = torch.autograd.grad(y, [x] + list(m.parameters()), gy)
             res.append([y.detach()] + [g for g in grads])
         lib.qw_set_fast_path(1)
-        for a, b in zip(*res):
-            assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item())
+        # y and grad_x are per-window quantities; the five parameter gradients are fp32 sums over N = 12 000 / 6 000 windows
+        # (this cotangent makes grad post_conv.bias an almost exactly cancelling sum of terms of magnitude <= 1), so they get
+        # the random-walk rounding allowance 2e-6 * sqrt(N) on top -- the two paths only differ in summation order.
+        N = y.shape[0] * y.shape[2]
+        for i, (a, b) in enumerate(zip(*res)):
+            tol = 2e-5 * max(1.0, b.abs().max().item()) + (2e-6 * N ** 0.5 if i >= 2 else 0.0)
+            assert (a - b).abs().max().item() <= tol, i
 
 
 @pytest.mark.parametrize("geom", GEOMS)
