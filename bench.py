@@ -519,25 +519,54 @@ def run_e2e(runner, B, K, Wm, world, dev, graphed=True):
     stem = torch.nn.Sequential(conv1, torch.nn.GELU(), conv2)
     api = "QuantumConv1d nn.Module x2 + GELU (nn.Sequential), eager autograd"
     call = stem
+
+    def step_math(x):
+        y2 = call(x)
+        loss = y2.square().mean()
+        grads = torch.autograd.grad(loss, params)
+        return torch.cat([loss.detach().reshape(1)] + [g_.reshape(-1) for g_ in grads])
+
+    # whole-step capture (the documented PyTorch pattern for static-shape training steps): forward, loss and backward of one
+    # input slot replay as ONE CUDA graph, so the Python side of a step is an event wait, a replay and a D2H copy
+    step_graphs = None
     if graphed:
         try:
-            call = torch.cuda.make_graphed_callables(stem, (torch.randn(B, N_MELS, N_FRAMES, device=dev),))
-            api = "QuantumConv1d nn.Module x2 + GELU (nn.Sequential) wrapped by torch.cuda.make_graphed_callables"
+            cap = torch.cuda.Stream()
+            cap.wait_stream(main)
+            with torch.cuda.stream(cap):
+                for _ in range(3):
+                    step_math(dev_in[0])
+            main.wait_stream(cap)
+            torch.cuda.synchronize()
+            step_graphs = []
+            for slot in range(2):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=cap):
+                    flat_static = step_math(dev_in[slot])
+                step_graphs.append((gph, flat_static))
+            torch.cuda.synchronize()
+            api = ("QuantumConv1d nn.Module x2 + GELU (nn.Sequential), loss and torch.autograd backward captured as one CUDA graph "
+                   "per input slot (torch.cuda.graph)")
         except Exception as e:
-            api += f" (make_graphed_callables failed: {type(e).__name__}: {str(e)[:80]})"
-            call = stem
+            step_graphs = None
+            api += f" [whole-step capture failed: {type(e).__name__}: {str(e)[:80]}]"
+            torch.cuda.synchronize()
+            try:  # second choice: PyTorch's per-module graphing utility
+                call = torch.cuda.make_graphed_callables(stem, (torch.randn(B, N_MELS, N_FRAMES, device=dev),))
+                api += " -> torch.cuda.make_graphed_callables"
+            except Exception as e2:
+                call = stem
+                api += f" -> eager ({type(e2).__name__})"
 
     def compute(i):
         slot = i % 2
         main.wait_event(ev_copied[slot])
-        x = dev_in[slot]
-        y2 = call(x)
-        loss = y2.square().mean()
-        for p_ in params:
-            p_.grad = None
-        loss.backward()
+        if step_graphs is not None:
+            gph, flat = step_graphs[slot]
+            gph.replay()
+        else:
+            flat = step_math(dev_in[slot])
         ev_free[slot].record(main)
-        flat = torch.cat([loss.detach().reshape(1)] + [p_.grad.reshape(-1) for p_ in params])
         if world > 1:
             torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.AVG)
         host_out[i % nhost].copy_(flat.detach(), non_blocking=True)

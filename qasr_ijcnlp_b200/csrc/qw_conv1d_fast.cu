@@ -491,95 +491,53 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
 
 // adjoint differentiation of the circuit, one window per thread; partial row per CTA: [gb_pre 4 + pad 28][Lq*32 gate matrices]
 //
-// The first a.nlead CTAs of the grid do not run the adjoint: they reduce the partial rows the gy kernel has just written
-// (grad post_conv.{weight,bias}: G1 rows x O*5 columns, 16 columns per CTA, fixed-order fp64 sums -> deterministic) while the
-// adjoint CTAs -- a latency-bound dependent chain that leaves most of every SM idle -- run beside them.  This is the first
-// third of what used to be a separate finalize kernel at the end of the backward (its launch + drain was ~8 us per layer on
-// the critical path at batch 16); the second third (grad pre_conv.bias, grad quantum_weights) rides in fast_bwd_pre_kernel
-// the same way, and only grad pre_conv.weight -- whose rows the LAST kernel of the backward produces -- is left to
-// fast_finalize_kernel.  (Measured and rejected: reducing those rows inside fast_bwd_pre_kernel too, by a two-level
-// last-arriver scheme; its fence + atomic + L2 round trips at the tail of every CTA cost 8 us per step more than the
-// programmatically launched finalize kernel they replaced: 147.6 vs 139.5 us.)
+// The forward recomputation of a window needs only pre_save (written by the forward kernel, at least two launches back in the
+// stream), so the dependency wait sits INSIDE the loop, between the recomputation and the first read of gout: under programmatic
+// dependent launch these small CTAs are resident microseconds before the gy kernel drains, and ~40 % of the dependent chain of
+// their first window is done by then.  One copy of the circuit code only -- the kernel is a ~1 650-instruction straight line per
+// window and sensitive to instruction-cache misses (a peeled first iteration, i.e. two inlined copies, cost 3.5 us per launch).
+//
+// Measured and rejected (B200, batch-16 stem step): folding the finalize kernel's work into this kernel and the pre_conv^T
+// kernel as leading "reduce" CTAs (grad post_conv.* here, grad pre_conv.bias / quantum_weights there), and reducing the
+// pre_conv^T rows by a two-level last-arriver scheme.  The first is +1 us (the reduce CTAs delay the dependent launch trigger and
+// grow the code of two cache-sensitive kernels), the second +8 us (fence + atomic + L2 round trips at the tail of every CTA)
+// against the programmatically launched 1 024-thread finalize kernel, which costs 3-4 us per layer in the graph.
 constexpr int kAdjThreads = 128;
-constexpr int kAdjRedCols = 16;
 
-__global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdjArgs a) {
+__global__ void __launch_bounds__(kAdjThreads, 4) fast_bwd_adj_kernel(const FastAdjArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  tl_begin(a.tl);
-  if ((int)blockIdx.x < a.nlead) {
-    // ======================================================== reduce CTA: columns [blk*16, blk*16+16) of part1
-    double* red = reinterpret_cast<double*>(smem_dyn);  // [8][16]
-    const int col = lane & 15, slot = warp * 2 + (lane >> 4);
-    const int pcol = (int)blockIdx.x * kAdjRedCols + col;
-    const int ncols = a.O * (FQ + 1);
-    pdl_wait();
-    double s = 0.0;
-    if (pcol < ncols) {
-      const float* __restrict__ src = a.part1 + pcol;
-      int g = slot;
-      for (; g + 56 < a.G1; g += 64) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + 8 * u) * a.P1);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += (double)v[u];
-      }
-      for (; g < a.G1; g += 8) s += (double)__ldcg(src + (size_t)g * a.P1);
-    }
-    red[slot * kAdjRedCols + col] = s;
-    __syncthreads();
-    if (tid < kAdjRedCols && pcol < ncols) {
-      double t = 0.0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t += red[u * kAdjRedCols + tid];
-      if (pcol < a.O * FQ) a.gw_post[pcol] = (float)t;
-      else a.gb_post[pcol - a.O * FQ] = (float)t;
-    }
-    tl_end(a.tl);
-    return;
-  }
-  const int bid = (int)blockIdx.x - a.nlead, nblk = (int)gridDim.x - a.nlead;
   const int NE = FQ + a.Lq * 32;
   float* gates = reinterpret_cast<float*>(smem_dyn);             // [Lq][4][16]
   float* macc = gates + (size_t)a.Lq * FQ * kGateStride;         // [4 warps][NE][kGyMS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  tl_begin(a.tl);
   if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   for (int e = tid; e < 4 * NE * kGyMS; e += kAdjThreads) macc[e] = 0.f;
   __syncthreads();
-  // The forward recomputation of this thread's first window needs only pre_save (written by the forward kernel, at least two
-  // launches back in the stream), so it runs BEFORE the dependency wait: under programmatic dependent launch these CTAs are
-  // resident microseconds before the gy kernel drains (they are small), and this hides ~40 % of the adjoint's dependent chain.
-  const long long wfirst = (long long)bid * kAdjThreads;
-  float pre[FQ], out[FQ], re[1 << FQ], im[1 << FQ];
-  float inv;
-  if (a.early_trigger & 2) {
-    const long long w = wfirst + tid;
-    const float4 pv = (w < a.W) ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
-    pre[0] = pv.x; pre[1] = pv.y; pre[2] = pv.z; pre[3] = pv.w;
-    inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
-  }
-  pdl_wait();
-  if (a.early_trigger & 1) pdl_launch();  // the whole grid is resident: the next kernel's CTAs may come in and stage their tiles
-  {  // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
+  float* mymacc = macc + (size_t)warp * NE * kGyMS;
+  bool waited = false;
+  auto wait_once = [&]() {
+    if (waited) return;
+    waited = true;
+    pdl_wait();
+    // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
     const int per = (kHaloL + kHaloR) * FQ;
-    for (long long idx = (long long)bid * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)nblk * kAdjThreads) {
+    for (long long idx = (long long)blockIdx.x * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kAdjThreads) {
       const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
       const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
       a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
     }
-  }
-  float* mymacc = macc + (size_t)warp * NE * kGyMS;
-  for (long long w0 = wfirst; w0 < a.W; w0 += (long long)nblk * kAdjThreads) {
+  };
+  for (long long w0 = (long long)blockIdx.x * kAdjThreads; w0 < a.W; w0 += (long long)gridDim.x * kAdjThreads) {
     const long long w = w0 + tid;
     const bool valid = w < a.W;
-    if (w0 != wfirst || !(a.early_trigger & 2)) {
-      const float4 pv = valid ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
-      pre[0] = pv.x; pre[1] = pv.y; pre[2] = pv.z; pre[3] = pv.w;
-      inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
-    }
+    const float4 pv = valid ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+    const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
+    float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
+    const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+    wait_once();
     const float4 gv = valid ? ld4(a.gout + (size_t)w * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
-    float gpre[FQ];
     SmemGateAcc<float, FQ> acc{mymacc + (size_t)FQ * kGyMS + lane, kGyMS, 0};
     circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
     if (valid) {
@@ -589,9 +547,10 @@ __global__ void __launch_bounds__(kAdjThreads) fast_bwd_adj_kernel(const FastAdj
 #pragma unroll
     for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
   }
-  if (!(a.early_trigger & 1)) pdl_launch();  // late: this grid is not fully resident, an early trigger would let the next kernel's CTAs take its slots
+  wait_once();   // a CTA without windows still owes the halo zeroing
+  pdl_launch();  // late: an early trigger (measured: +0.3 us) lets the next kernel's CTAs crowd the SMs this latency-bound grid needs
   __syncthreads();
-  float* prow = a.part + (size_t)bid * a.PA2;
+  float* prow = a.part + (size_t)blockIdx.x * a.PA2;
   for (int e = warp; e < a.PA2; e += kAdjThreads / 32) {
     // e in [0,4): grad pre_conv.bias; [32, 32+Lq*32): gate matrices; everything else padding
     float v = 0.f;
@@ -611,12 +570,7 @@ struct FastPreArgs {
   const float *gpre_pad, *w_pre;
   float* part;  // [gridPx][Cpad][12]
   int B, C, L, P, Lout, LP, tiles_per_utt, num_tiles, Cpad;
-  int gridPx;  // streaming CTAs per channel chunk; the grid is 1-D: [nlead reduce CTAs][nchunks x gridPx streaming CTAs]
-  // leading reduce CTAs: part2 = [G2][P2] rows of the adjoint kernel -> grad pre_conv.bias, grad quantum_weights
-  int nlead;
-  const float *part2, *qw;
-  int G2, P2, Lq;
-  float *gb_pre, *gqw;
+  int gridPx;  // streaming CTAs per channel chunk; the grid is 1-D: [nchunks x gridPx]
   int early_x;
   unsigned long long* tl;
 };
@@ -640,51 +594,7 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
   uint64_t* full = reinterpret_cast<uint64_t*>(gps + (size_t)kPreSlots * GPN * FQ);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   tl_begin(a.tl);
-  if ((int)blockIdx.x < a.nlead) {
-    // ======================================================== reduce CTA: 32 columns of the adjoint kernel's partial rows
-    // (block 0: grad pre_conv.bias; block 1 + l: the 4 gate-gradient matrices of layer l -> (phi, theta, omega) chain rule)
-    double* red = reinterpret_cast<double*>(base);  // [kWarps][32] + tot[32]
-    double* tot = red + kWarps * 32;
-    const int pcol = (int)blockIdx.x * 32 + lane;
-    pdl_wait();
-    double sacc = 0.0;
-    {
-      const float* __restrict__ src = a.part2 + pcol;
-      int g = warp;
-      for (; g + 7 * kWarps < a.G2; g += 8 * kWarps) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(g + u * kWarps) * a.P2);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sacc += (double)v[u];
-      }
-      for (; g < a.G2; g += kWarps) sacc += (double)__ldcg(src + (size_t)g * a.P2);
-    }
-    red[warp * 32 + lane] = sacc;
-    __syncthreads();
-    if (warp != 0) return;
-    tl_end(a.tl);
-    double t = 0.0;
-#pragma unroll
-    for (int wq = 0; wq < kWarps; ++wq) t += red[wq * 32 + lane];
-    tot[lane] = t;
-    __syncwarp();
-    if (blockIdx.x == 0) {
-      if (lane < FQ) a.gb_pre[lane] = (float)t;
-    } else if (lane < FQ) {
-      const int gi = ((int)blockIdx.x - 1) * FQ + lane;
-      if (gi < a.Lq * FQ) {
-        double w3[3], g3[3];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) w3[e] = (double)a.qw[gi * 3 + e];
-        gate_grad_to_angles(w3, &tot[lane * 8], g3);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) a.gqw[gi * 3 + e] = (float)g3[e];
-      }
-    }
-    return;
-  }
-  const int lin = (int)blockIdx.x - a.nlead;
+  const int lin = (int)blockIdx.x;
   const int by = lin / a.gridPx, bx = lin - by * a.gridPx;  // channel chunk, CTA inside the chunk
   const int c0 = by * 32, c = c0 + lane;
 
@@ -814,9 +724,9 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
 }
 
 // =============================================================================================== finalize
-// Deterministic fixed-order fp64 reduction of per-CTA partial rows.  Segment 3 (grad pre_conv.weight, rows of the pre_conv^T
-// kernel) always runs here; segments 1 and 2 only with QW_FINALIZE_KERNEL=1 (A/B switch) -- by default they ride as leading
-// CTAs inside the adjoint and pre_conv^T kernels.
+// Deterministic fixed-order fp64 reduction of the per-CTA partial rows of the three kernels above: segment 1 = rows of the gy
+// kernel (grad post_conv.*), 2 = rows of the adjoint kernel (grad pre_conv.bias, gate matrices -> grad quantum_weights),
+// 3 = rows of the pre_conv^T kernel (grad pre_conv.weight).
 constexpr int kFFThreads = 1024;  // 32 warps per 32-column block: short dependent chains over the partial rows
 constexpr int kFFWarps = kFFThreads / 32;
 struct FastFinArgs {
@@ -834,7 +744,7 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   pdl_wait();
   pdl_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb1 = a.part1 ? a.P1 / 32 : 0, nb2 = a.part2 ? a.P2 / 32 : 0;
+  const int nb1 = a.P1 / 32, nb2 = a.P2 / 32;
   const bool seg1 = (int)blockIdx.x < nb1;
   const bool seg2 = !seg1 && (int)blockIdx.x < nb1 + nb2;
   const int blk = seg1 ? blockIdx.x : seg2 ? blockIdx.x - nb1 : blockIdx.x - nb1 - nb2;
@@ -925,11 +835,8 @@ static int env_flag(const char* name, int dflt) {
 }
 // Experiment switches (defaults = the measured winners on B200, batch-16 stem step):
 //   QW_FWD_ETMA  1: the forward kernel requests its first x tiles before staging its parameters        (-1.0 us / step)
-//   QW_ADJ_FLAGS bit 1: forward recomputation of the adjoint kernel before the dependency wait         (-1.1 us)
-//                bit 0: adjoint kernel triggers its dependent right after the wait                     (+0.3 us: off)
 //   QW_PRE_EX    1: the pre_conv^T kernel requests its first x tiles before the dependency wait        (-1.7 us)
 static int flag_fwd_etma() { static const int v = env_flag("QW_FWD_ETMA", 1); return v; }
-static int flag_adj() { static const int v = env_flag("QW_ADJ_FLAGS", 2); return v; }
 static int flag_pre_ex() { static const int v = env_flag("QW_PRE_EX", 1); return v; }
 static bool g_fast_enabled = true;
 void set_fast_path(bool on) { g_fast_enabled = on; }
@@ -992,8 +899,6 @@ FastPlan make_fast_plan(const ConvDims& d) {
   if (cap < 1) cap = 1;
   p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
   p.PB = p.Cpad * 12;
-  p.nlead_adj = (d.O * (FQ + 1) + kAdjRedCols - 1) / kAdjRedCols;
-  p.nlead_pre = p.PA2 / 32;
   size_t o = 0;
   p.off_gout = o; o = align_up(o + (size_t)W * FQ * 4, 256);
   p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
@@ -1057,14 +962,6 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
   return 0;
 }
 
-static bool finalize_kernel_mode() {
-  static const bool v = [] {
-    const char* e = getenv("QW_FINALIZE_KERNEL");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
 template <int S, int PAR, bool GX>
 static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const FastPreArgs& a, const FastPlan& p, cudaStream_t st) {
   const size_t smem = fast_pre_smem_bytes<S>();
@@ -1072,7 +969,7 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKBwdPre, st);
-    QW_CUDA_OK(launch_pdl(p.small, k, dim3(a.nlead + p.gridPx * p.nchunks), dim3(kThreads), smem, st, tx, tgx, a));
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridPx * p.nchunks), dim3(kThreads), smem, st, tx, tgx, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1093,7 +990,6 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
   float* gout = reinterpret_cast<float*>(ws + p.off_gout);
   float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
-  const bool fin = finalize_kernel_mode();
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
   {
     FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot()};
@@ -1103,23 +999,21 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
                        : launch_fast_gy2<3>(tm_gy, tm_qout, a, p, st);
     if (e) return e;
   }
-  // 2) adjoint differentiation of the circuit, one window per thread (+ leading CTAs: grad post_conv.* from the rows of 1)
+  // 2) adjoint differentiation of the circuit, one window per thread
   {
-    const int nlead = fin ? 0 : p.nlead_adj;
-    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W,
-                   nlead, part1, p.gridGy, p.PA1, d.O, gw_post, gb_post, flag_adj(), timeline_next_slot()};
+    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W, timeline_next_slot()};
     const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
     if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       KernelTimer kt(kKBwdAdj, st);
-      QW_CUDA_OK(launch_pdl(p.small, fast_bwd_adj_kernel, dim3(nlead + p.gridAdj), dim3(kAdjThreads), smem, st, aa));
+      QW_CUDA_OK(launch_pdl(p.small, fast_bwd_adj_kernel, dim3(p.gridAdj), dim3(kAdjThreads), smem, st, aa));
     }
     QW_CUDA_OK(cudaGetLastError());
   }
-  // 3) pre_conv^T (+ leading CTAs: grad pre_conv.bias / quantum_weights from the rows of 2)
+  // 3) pre_conv^T
   {
     FastPreArgs a{gpre, w_pre, part3, d.B, d.C, d.L, d.P, d.Lout, p.LP, p.ptiles_per_utt, p.num_ptiles, p.Cpad, p.gridPx,
-                  fin ? 0 : p.nlead_pre, part2, qwts, p.gridAdj, p.PA2, d.Lq, gb_pre, gqw, flag_pre_ex(), timeline_next_slot()};
+                  flag_pre_ex(), timeline_next_slot()};
     const int par = d.P & 1;
     int e;
     if (d.S == 1) e = gx ? launch_fast_pre<1, 0, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<1, 0, false>(tm_x, tm_gx, a, p, st);
@@ -1127,11 +1021,11 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     else          e = gx ? launch_fast_pre<2, 0, true>(tm_x, tm_gx, a, p, st) : launch_fast_pre<2, 0, false>(tm_x, tm_gx, a, p, st);
     if (e) return e;
   }
-  // 4) finalize: grad pre_conv.weight from the rows of 3 (QW_FINALIZE_KERNEL=1: all three segments)
+  // 4) finalize
   {
-    FastFinArgs a{fin ? part1 : nullptr, fin ? part2 : nullptr, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1,
-                  p.gridAdj, p.PA2, p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot()};
-    const int nblk = (fin ? p.PA1 / 32 + p.PA2 / 32 : 0) + p.PB / 32;
+    FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridAdj, p.PA2,
+                  p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot()};
+    const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
     {
       KernelTimer kt(kKBwdFinalize, st);
       QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel, dim3(nblk), dim3(kFFThreads), 0, st, a));

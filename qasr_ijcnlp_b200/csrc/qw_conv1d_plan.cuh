@@ -40,7 +40,6 @@ struct FastPlan {
   int tw, tiles_per_utt, num_tiles, rc, chunks_per_tile, gridF;
   int gridGy, PA1, gridAdj, PA2, LP;
   int ptiles_per_utt, num_ptiles, nchunks, Cpad, gridPx, PB;
-  int nlead_adj, nlead_pre;  // reduce CTAs in front of the adjoint / pre_conv^T grids (the former finalize kernel)
   size_t off_gout, off_gpre, off_p1, off_p2, off_p3, ws_bytes;
   bool small;  // latency-dominated launch: use programmatic dependent launch
 };
@@ -51,12 +50,6 @@ struct FastAdjArgs {
   float *gpre_pad, *part;  // part: [grid][PA2] rows: [grad pre_conv.bias 4 + pad 28][Lq*32 gate-gradient matrices M]
   int B, Lout, LP, Lq, PA2;
   long long W;
-  // leading reduce CTAs: part1 = [G1][P1] rows of the gy kernel -> grad post_conv.{weight,bias}
-  int nlead;
-  const float* part1;
-  int G1, P1, O;
-  float *gw_post, *gb_post;
-  int early_trigger;  // bit 0: trigger the dependent launch right after the wait; bit 1: forward recomputation before the wait
   unsigned long long* tl;
 };
 void set_fast_path(bool on);
