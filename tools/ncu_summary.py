@@ -40,6 +40,17 @@ def main():
     blocks = re.split(r'(?m)^"Kernel Name",', src)[1:]
     if len(blocks) == 2 * len(launches):
         blocks = blocks[::2]
+    elif len(blocks) > len(launches):
+        # kernels compiled with -lineinfo come out twice (identical SASS views), library kernels without it once:
+        # drop exact consecutive duplicates until the counts agree
+        dedup = []
+        extra = len(blocks) - len(launches)
+        for b in blocks:
+            if extra and dedup and b == dedup[-1]:
+                extra -= 1
+                continue
+            dedup.append(b)
+        blocks = dedup
     for li, (row, blk) in enumerate(zip(launches, blocks)):
         name = row[hdr.index("Kernel Name")]
         if a.kernel and not re.search(a.kernel, name):
