@@ -308,11 +308,6 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
 }
 
 // =============================================================================================== backward: gy streaming + adjoint
-constexpr int kGySW = 6;                          // streaming warps (192 threads = one stage row each)
-constexpr int kGyStream = kGySW * 32;
-constexpr int kGyStages = 3;                      // ring of 192-row x 32-window stages (3 TMA boxes of 64 rows)
-constexpr int kGyStageRows = 192;
-constexpr int kGyStageElems = kGyStageRows * 32;
 constexpr int kGyMS = 33;                         // per-lane accumulator column stride
 // partial-row layout of the gy kernel: [O*4 grad post_conv.weight][O grad post_conv.bias][pad to 32]
 __host__ __device__ inline int gy_plen(int O) { return (int)align_up((size_t)O * 5, 32); }
@@ -329,21 +324,23 @@ struct FastGy2Args {
   int tw;  // tile stride in windows (the qout box has tw rows)
   unsigned long long* tl;
 };
-__host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O) {
-  return 1024 + (size_t)kGyStages * kGyStageElems * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)O * FQ * 4 +
-         (size_t)2 * kGySW * FTW * FQ * 4 + (2 * kGyStages) * 8;
+// NW warps, one thread per stage row (stage = 32*NW output channels x 32 windows), NST-deep ring
+__host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O, int NW, int NST) {
+  return 1024 + (size_t)NST * (32 * NW * 32) * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)O * FQ * 4 +
+         (size_t)NW * FTW * FQ * 4 + (2 * NST) * 8;
 }
 
-template <int NHALF>
-__global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid_constant__ CUtensorMap tm_gy,
+template <int NHALF, int NW, int NST>
+__global__ void __launch_bounds__(32 * NW, 2) fast_bwd_gy2_kernel(const __grid_constant__ CUtensorMap tm_gy,
                                                                     const __grid_constant__ CUtensorMap tm_qout, const FastGy2Args a) {
+  constexpr int kGySW = NW, kGyStream = 32 * NW, kGyStages = NST, kGyStageRows = 32 * NW, kGyStageElems = kGyStageRows * 32;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* base = align1024(smem_dyn);
-  float* stages = reinterpret_cast<float*>(base);                      // [kGyStages][192][32] swizzled
+  float* stages = reinterpret_cast<float*>(base);                      // [kGyStages][32*NW][32] swizzled
   float* outs = stages + (size_t)kGyStages * kGyStageElems;            // [3][32][4]
   float* wpost = outs + 3 * FTW * FQ;                                  // [O][4]
-  float* gred = wpost + (size_t)a.O * FQ;                              // [2][kGySW][32][4]
-  uint64_t* full = reinterpret_cast<uint64_t*>(gred + 2 * kGySW * FTW * FQ);
+  float* gred = wpost + (size_t)a.O * FQ;                              // [kGySW][32][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(gred + kGySW * FTW * FQ);
   uint64_t* empty = full + kGyStages;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -379,7 +376,7 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
     const int s = gs % kGyStages;
     mbar_arrive_expect_tx(&full[s], (uint32_t)(kGyStageElems + (h == 0 ? a.tw * FQ : 0)) * 4);
 #pragma unroll
-    for (int bx = 0; bx < 3; ++bx)
+    for (int bx = 0; bx < kGyStageRows / 64; ++bx)
       tma_load_3d(stages + (size_t)s * kGyStageElems + bx * 64 * 32, &tm_gy, i0, h * kGyStageRows + bx * 64, b, &full[s]);
     if (h == 0) tma_load_3d(outs + (n % 3) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
   };
@@ -455,13 +452,16 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         gacc[u][j] = v;
       }
-    float* gr = gred + (size_t)(n & 1) * kGySW * FTW * FQ;
+    // single gred buffer: the warp that summed tile n-1 out of it ARRIVES on named barrier 2 when it is done reading, every
+    // other warp SYNCS on it before overwriting (32 + 32 * (NW - 1) = all threads); the reader knows its own read is over
+    float* gr = gred;
+    if (n >= 1 && warp != (n - 1) % kGySW) asm volatile("bar.sync 2, %0;" ::"n"(kGyStream) : "memory");
     if (rr == 0) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         st4(gr + ((size_t)warp * FTW + 4 * tl + u) * FQ, make_float4(gacc[u][0], gacc[u][1], gacc[u][2], gacc[u][3]));
     }
-    __syncthreads();  // gred[n&1] complete; its previous readers (tile n-2) passed the barrier of tile n-1
+    __syncthreads();  // gred complete
     if (warp == n % kGySW) {
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / a.tiles_per_utt;
@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(kGyStream, 2) fast_bwd_gy2_kernel(const __grid
         const float4 pv = ld4(gr + ((size_t)w * FTW + lane) * FQ);
         sacc.x += pv.x; sacc.y += pv.y; sacc.z += pv.z; sacc.w += pv.w;
       }
+      if (n + 1 < my_tiles) asm volatile("bar.arrive 2, %0;" ::"n"(kGyStream) : "memory");
       if (lane < a.tw && i < a.Lout) st4(a.gout + ((size_t)b * a.Lout + i) * FQ, sacc);
     }
   }
@@ -950,18 +951,34 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
   }
 }
 
-template <int NHALF>
+template <int NHALF, int NW, int NST>
 static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
-  const size_t smem = fast_gy2_smem_bytes(a.O);
+  const size_t smem = fast_gy2_smem_bytes(a.O, NW, NST);
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
-  auto k = fast_bwd_gy2_kernel<NHALF>;
+  auto k = fast_bwd_gy2_kernel<NHALF, NW, NST>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(kKBwdPost, st);
-    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(kGyStream), smem, st, tg, tq, a));
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(32 * NW), smem, st, tg, tq, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
+}
+// 6 warps x 192-row stages, 3-deep ring (default).  QW_GY_WARPS=12 selects 12 warps x 384-row stages with a 2-deep ring (the
+// whole Whisper tile in one stage, twice the warps per scheduler): measured SLOWER on B200 at batch 16 (step 138.0 vs 135.4 us,
+// gy 14.7 / 23.2 vs 12.9 / 21.8 us) -- the extra warps do not raise the issue rate of the two contractions, the 2-deep ring
+// loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.
+static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
+  static const int forced = env_flag("QW_GY_WARPS", 0);
+  const bool wide = forced == 12;
+  if (wide) {
+    const int nhalf = (a.O + 383) / 384;
+    return nhalf == 1 ? launch_fast_gy2<1, 12, 2>(tg, tq, a, p, st) : launch_fast_gy2<2, 12, 2>(tg, tq, a, p, st);
+  }
+  const int nhalf = (a.O + 191) / 192;
+  return nhalf == 1 ? launch_fast_gy2<1, 6, 3>(tg, tq, a, p, st)
+       : nhalf == 2 ? launch_fast_gy2<2, 6, 3>(tg, tq, a, p, st)
+                    : launch_fast_gy2<3, 6, 3>(tg, tq, a, p, st);
 }
 
 template <int S, int PAR, bool GX>
@@ -995,11 +1012,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
   {
     FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot()};
-    const int nhalf = (d.O + kGyStageRows - 1) / kGyStageRows;
-    int e = nhalf == 1 ? launch_fast_gy2<1>(tm_gy, tm_qout, a, p, st)
-          : nhalf == 2 ? launch_fast_gy2<2>(tm_gy, tm_qout, a, p, st)
-                       : launch_fast_gy2<3>(tm_gy, tm_qout, a, p, st);
-    if (e) return e;
+    if (int e = launch_fast_gy2_any(tm_gy, tm_qout, a, p, st)) return e;
   }
   // 2) adjoint differentiation of the circuit, one window per thread
   {
