@@ -967,7 +967,8 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
 // 6 warps x 192-row stages, 3-deep ring (default).  QW_GY_WARPS=12 selects 12 warps x 384-row stages with a 2-deep ring (the
 // whole Whisper tile in one stage, twice the warps per scheduler): measured SLOWER on B200 at batch 16 (step 138.0 vs 135.4 us,
 // gy 14.7 / 23.2 vs 12.9 / 21.8 us) -- the extra warps do not raise the issue rate of the two contractions, the 2-deep ring
-// loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.
+// loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.  Also measured and dropped:
+// 3 CTAs per SM of the 6-warp form with a 2-deep ring (444 CTAs): 139.2 us.
 static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
   static const int forced = env_flag("QW_GY_WARPS", 0);
   const bool wide = forced == 12;
