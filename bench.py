@@ -68,7 +68,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true")
     ap.add_argument("--e2e-eager", action="store_true", help="do not wrap the e2e module in torch.cuda.make_graphed_callables")
-    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="gradient all-reduce at N > 1")
+    ap.add_argument("--collective", default="hybrid", choices=["hybrid", "fused", "p2p", "nccl"],
+                    help="gradient all-reduce at N > 1: fused into the backward's last kernel / own one-shot NVLink kernel / NCCL")
     return ap.parse_args()
 
 
@@ -223,9 +224,19 @@ class StemRunner:
                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         self._lib.check(st, "qw_conv1d_forward")
 
+    hybrid = None                    # (P2P reducer of conv2's bucket, side stream) with fused_dp = {"conv1": ...}
+    fused_dp = None                  # {layer: dp.FusedLayerGradAllReduce}: the all-reduce rides in the backward's finalize kernel
+
     def bwd(self, name, s):
         cfg, t, p, g = LAYERS[name], self.sets[s].t[name], self.params.p[name], self.params.g[name]
         ws, n = self.ws[name]
+        if self.fused_dp is not None and name in self.fused_dp:
+            st = self.lib.qw_conv1d_backward_dp(_p(t["gy"]), _p(t["x"]), _p(t["pre"]), _p(p[0]), _p(p[2]), _p(p[3]), _p(t["gx"]),
+                                                _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(ws), n, *self._dims(cfg),
+                                                *self.fused_dp[name].args(),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            self._lib.check(st, "qw_conv1d_backward_dp")
+            return
         st = self.lib.qw_conv1d_backward(_p(t["gy"]), _p(t["x"]), _p(t["pre"]), _p(p[0]), _p(p[2]), _p(p[3]), _p(t["gx"]),
                                          _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(ws), n, *self._dims(cfg),
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
@@ -236,6 +247,22 @@ class StemRunner:
         self.fwd("conv1", s)
         self.fwd("conv2", s)
         self.bwd("conv2", s)
+        if self.hybrid is not None:
+            # conv2's gradients: own one-shot NVLink all-reduce kernel on a side stream, hidden under conv1's backward;
+            # conv1's gradients (the last to be produced): all-reduce fused into conv1's finalize kernel -> nothing after it
+            ar2, side = self.hybrid
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            lo, hi = self.params.span["conv2"]
+            with torch.cuda.stream(side):
+                ar2(self.params.flat_grads[lo:hi])
+                ev2 = torch.cuda.Event()
+                ev2.record(side)
+            self.bwd("conv1", s)
+            main.wait_event(ev2)
+            return
         if self.allreduce_split is not None:
             # conv2's gradients are final: reduce them on a side stream while conv1's backward runs; only conv1's (smaller)
             # bucket is reduced on the critical path
@@ -319,6 +346,26 @@ def run_b200(args):
         from qasr_ijcnlp_b200 import dp
         n = runner.params.flat_grads.numel()
         try:
+            if args.collective not in ("fused", "hybrid"):
+                raise RuntimeError("not requested")
+            layers = LAYERS if args.collective == "fused" else {"conv1": LAYERS["conv1"]}
+            runner.fused_dp = {name: dp.FusedLayerGradAllReduce(cfg["C"], cfg["O"], cfg["K"], cfg["S"], cfg["P"], Q, 1, device=dev)
+                               for name, cfg in layers.items()}
+            collective = ("fused into each layer's backward: the finalize kernel exchanges its reduced columns over NVLink peer "
+                          "memory and averages them (qw_conv1d_backward_dp); no separate collective kernel")
+            if args.collective == "hybrid":
+                lo, hi = runner.params.span["conv2"]
+                runner.hybrid = (dp.P2PGradAllReduce(hi - lo, dev), torch.cuda.Stream())
+                collective = (f"conv1 (last gradients of the step): all-reduce fused into its backward's finalize kernel over NVLink "
+                              f"peer memory (qw_conv1d_backward_dp); conv2: own one-shot NVLink all-reduce kernel of its {4 * (hi - lo)} B "
+                              f"bucket on a side stream under conv1's backward; all inside the step's CUDA graph")
+        except Exception as e_f:
+            runner.fused_dp = None
+            runner.hybrid = None
+            fused_note = "" if args.collective != "fused" else f" [fused unavailable: {type(e_f).__name__}: {str(e_f)[:60]}]"
+        try:
+            if runner.fused_dp is not None:
+                raise StopIteration
             if args.collective == "nccl":
                 raise RuntimeError("forced")
             sp = runner.params.span
@@ -326,6 +373,8 @@ def run_b200(args):
             runner.allreduce_split = (dp.P2PGradAllReduce(n1, dev), dp.P2PGradAllReduce(n2, dev), torch.cuda.Stream())
             collective = (f"own one-shot NVLink peer-memory all-reduce kernel, fused 1/N scale, in the step's CUDA graph: conv2's "
                           f"{4 * n2} B bucket on a side stream under conv1's backward, conv1's {4 * n1} B bucket at the end")
+        except StopIteration:
+            pass
         except Exception as e:  # symmetric memory unavailable -> NCCL
             flat = runner.params.flat_grads
             runner.allreduce = lambda t: torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG)

@@ -72,6 +72,25 @@ int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_
                            double* gqw, double* gw_post, double* gb_post, void* workspace, size_t ws_bytes, int B,
                            int C, int L, int K, int S, int P, int O, int q, int n_layers, int embedding, void* stream);
 
+/* ---- data-parallel backward: the same as qw_conv1d_backward, with the all-reduce (mean over ranks) of the five parameter
+ * gradients FUSED into the backward's last kernel (the reference trains single-process, train_quantum_whisper.py,
+ * so this replaces what DistributedDataParallel would add around quantum_whisper.py:95-128).  Every rank owns a receive buffer
+ * of qw_conv1d_dp_buffer_bytes(..., world) bytes, zero-initialised once and mapped into every peer's address space (e.g.
+ * torch.distributed._symmetric_memory), and a LOCAL zero-initialised bookkeeping buffer of qw_conv1d_dp_flag_bytes(...) bytes;
+ * peer_bufs[r] is rank r's receive buffer as seen from the calling process, peer_flags[rank] the caller's own bookkeeping
+ * buffer (the other entries are ignored).  Each rank stores (epoch, value) words straight into its peers' buffers over NVLink.
+ * After the call (in stream order) gw_pre ... gb_post hold scale * sum over ranks, bitwise identical on every rank; gx stays
+ * local.  All ranks must call it the same number of times with the same shapes.  A peer that never arrives makes the kernel
+ * give up after ~1 s, keep the local gradient and set the last bookkeeping word to 1 (never hangs).  Fast-path regime only
+ * (-2 otherwise: use qw_conv1d_backward + qw_grads_allreduce_p2p / NCCL).  world == 1: plain backward. */
+size_t qw_conv1d_dp_buffer_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world);
+size_t qw_conv1d_dp_flag_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world);
+int qw_conv1d_backward_dp(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qw,
+                          const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post,
+                          float* gb_post, void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O,
+                          int q, int n_layers, int embedding, void* const* peer_bufs, void* const* peer_flags, int rank,
+                          int world, float scale, void* stream);
+
 /* ---- fused INFERENCE forward of the encoder stem (whisper/whisper/model.py:193-198 with the two QuantumConv1d layers of
  * quantum_whisper.py:136-137):
  *     out[b, t, :] = gelu(conv2(gelu(conv1(x))))[b, :, t] + pos_emb[t, :]

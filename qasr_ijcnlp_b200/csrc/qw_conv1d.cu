@@ -102,13 +102,15 @@ static int conv1d_forward_impl(const T* x, const T* w_pre, const T* b_pre, const
 template <typename T>
 static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* qwts, const T* w_post,
                                 T* gx, T* gw_pre, T* gb_pre, T* gqw, T* gw_post, T* gb_post, void* workspace,
-                                size_t ws_bytes, ConvDims d, void* stream) {
+                                size_t ws_bytes, ConvDims d, void* stream, const FastDp* dp = nullptr) {
   QW_CHECK_ARG(gy && x && pre_save && w_pre && qwts && w_post && gw_pre && gb_pre && gqw && gw_post && gb_post && workspace,
                -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
   QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = (unsigned char*)workspace;
+  const bool want_dp = dp && dp->world > 1;
+  QW_CHECK_ARG(!(want_dp && is_general(d)), -2, "the fused gradient all-reduce needs the fast-path regime (n_qubits=4, amplitude embedding)");
   if (is_general(d))
     return gen::general_backward<T>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, ws_bytes, d, st);
   QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
@@ -116,9 +118,10 @@ static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, cons
     if (fast_eligible(d, x, gy, gx, false) && (((uintptr_t)pre_save) & 15) == 0) {
       const FastPlan fp = make_fast_plan(d);
       QW_CHECK_ARG(ws_bytes >= fp.ws_bytes, -3, "workspace too small: %zu < %zu", ws_bytes, fp.ws_bytes);
-      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st);
+      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st, dp);
     }
   }
+  QW_CHECK_ARG(!want_dp, -2, "the fused gradient all-reduce needs the fast-path regime (fp32, K=3, stride 1|2, L %% 4 == 0, O %% 4 == 0, aligned tensors)");
   const Plan p = make_plan(d);
   const WsLayout<T> wl = ws_layout<T>(d, p);
   QW_CHECK_ARG(ws_bytes >= wl.total, -3, "workspace too small: %zu < %zu", ws_bytes, wl.total);
@@ -239,6 +242,40 @@ int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_
   ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
   return qw::conv1d_backward_impl<double>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
                                           workspace, ws_bytes, d, stream);
+}
+
+size_t qw_conv1d_dp_buffer_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, 0, 0};
+  if (qw::check_dims(d) || d.Q != 4 || world < 1 || world > qw::kDpMaxWorld) return 0;
+  return qw::fast_dp_buffer_bytes(qw::make_fast_plan(d), world);
+}
+size_t qw_conv1d_dp_flag_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, 0, 0};
+  if (qw::check_dims(d) || d.Q != 4 || world < 1 || world > qw::kDpMaxWorld) return 0;
+  return qw::fast_dp_flag_bytes(qw::make_fast_plan(d));
+}
+int qw_conv1d_backward_dp(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
+                          const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
+                          void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O, int q, int n_layers,
+                          int embedding, void* const* peer_bufs, void* const* peer_flags, int rank, int world, float scale,
+                          void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  QW_CHECK_ARG(world >= 1 && world <= qw::kDpMaxWorld && rank >= 0 && rank < world, -1, "qw_conv1d_backward_dp: bad rank/world %d/%d (world <= %d)",
+               rank, world, qw::kDpMaxWorld);
+  qw::FastDp dp{};
+  if (world > 1) {
+    QW_CHECK_ARG(peer_bufs && peer_flags, -1, "qw_conv1d_backward_dp: null peer pointer tables");
+    for (int r = 0; r < world; ++r) {
+      QW_CHECK_ARG(peer_bufs[r] && peer_flags[r], -1, "qw_conv1d_backward_dp: null peer pointer for rank %d", r);
+      dp.bufs[r] = (float*)peer_bufs[r];
+      dp.flags[r] = (unsigned*)peer_flags[r];
+    }
+  }
+  dp.rank = rank;
+  dp.world = world;
+  dp.scale = scale;
+  return qw::conv1d_backward_impl<float>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
+                                         workspace, ws_bytes, d, stream, &dp);
 }
 
 size_t qw_circuit_workspace_bytes(long long W, int q, int n_layers, int elem_size) {

@@ -728,17 +728,81 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
 // Deterministic fixed-order fp64 reduction of the per-CTA partial rows of the three kernels above: segment 1 = rows of the gy
 // kernel (grad post_conv.*), 2 = rows of the adjoint kernel (grad pre_conv.bias, gate matrices -> grad quantum_weights),
 // 3 = rows of the pre_conv^T kernel (grad pre_conv.weight).
-constexpr int kFFThreads = 1024;  // 32 warps per 32-column block: short dependent chains over the partial rows
-constexpr int kFFWarps = kFFThreads / 32;
+// 1 024 threads (32 warps per 32-column block: short dependent chains over the partial rows) for the plain finalize; 512 when
+// the gradient all-reduce rides in it, so the whole grid is resident in ONE wave (a CTA holds its SM slot while warp 0 waits
+// for the peers: with one 1 024-thread CTA per SM the 208 CTAs of conv2 paid the NVLink round trip twice)
 struct FastFinArgs {
   const float *part1, *part2, *part3, *qw;
   float *gw_pre, *gb_pre, *gqw, *gw_post, *gb_post;
   int G1, P1, G2, P2, G3, P3;
   int C, O, Lq;
   unsigned long long* tl;
+  FastDp dp;  // world <= 1: plain finalize
 };
 
+// Data-parallel training fuses the gradient all-reduce INTO this kernel ("fuse the intra-GPU reduction into that
+// kernel's epilogue so the all-reduce input is ready without an extra pass" -- here the all-reduce itself rides in the epilogue).
+// Warp 0 of every CTA holds the CTA's 32 reduced columns.  Each lane packs (epoch << 32 | float bits) into ONE 64-bit word and
+// stores it straight into slot [epoch parity][my rank][column] of EVERY peer's receive buffer over NVLink (posted P2P stores),
+// then polls its own buffer until the words of all ranks carry this epoch, and sums them in fixed rank order -- bitwise
+// identical on every rank.  Data and flag travel in the same atomic 8-byte store (the "LL" idea of NCCL's low-latency
+// protocol), so there is no fence, no separate flag and no remote read: one NVLink write latency per CTA.  Measured on 2 x
+// B200: the first version (data in my own buffer, __threadfence_system, release-store of a flag into the peers, acquire-spin,
+// remote loads) spent 3-6 us in EACH system-scope fence and 19 us per exchange in total.
+// The raw column sums are exchanged (gate-gradient matrices included: the (phi, theta, omega) chain rule is linear in them and
+// is applied after the sum).  The epoch lives in device memory (CUDA-graph capturable); parity double-buffering is enough
+// because a rank can only be one epoch ahead of its slowest reader.  A CTA only ever waits for the SAME CTA index of its peers
+// and the whole grid is resident, so there is no inter-CTA deadlock; a peer that never arrives trips a ~1 s bound, the local
+// gradient is kept and the status word set.
+__device__ __forceinline__ void dp_st_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long dp_ld_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// called by warp 0 (all 32 lanes); t = this lane's column sum; returns the mean over ranks
+__device__ __forceinline__ double dp_allreduce_columns(const FastDp& dp, double t, int lane) {
+  const int blk = blockIdx.x, nblk = gridDim.x;
+  unsigned* myflags = dp.flags[dp.rank];  // epoch[nblk], status
+  unsigned epoch = 0;
+  if (lane == 0) epoch = myflags[blk] + 1u;
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  const size_t slot_base = (size_t)(epoch & 1u) * dp.world;
+  const size_t col = (size_t)blk * 32 + lane;
+  const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint((float)t);
+#pragma unroll
+  for (int r = 0; r < kDpMaxWorld; ++r)
+    if (r < dp.world) dp_st_u64(reinterpret_cast<unsigned long long*>(dp.bufs[r]) + (slot_base + dp.rank) * dp.ncol + col, word);
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(dp.bufs[dp.rank]);
+  double sum = 0.0;
+  bool bad = false;
+  const long long t0 = clock64();
+  for (int r = 0; r < dp.world; ++r) {
+    const unsigned long long* src = mine + (slot_base + r) * dp.ncol + col;
+    unsigned long long v = dp_ld_u64(src);
+    while ((unsigned)(v >> 32) != epoch) {
+      if (clock64() - t0 > 2000000000LL) {  // ~1 s
+        bad = true;
+        break;
+      }
+      v = dp_ld_u64(src);
+    }
+    sum += (double)__uint_as_float((unsigned)v);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (bad) {
+    sum = t * dp.world;  // keep the local gradient; the status word tells the host
+    if (lane == 0) myflags[nblk] = 1u;
+  }
+  if (lane == 0) myflags[blk] = epoch;
+  return sum * (double)dp.scale;
+}
+
+template <int kFFThreads>
 __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFinArgs a) {
+  constexpr int kFFWarps = kFFThreads / 32;
   __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
   tl_begin(a.tl);
@@ -766,10 +830,11 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   red[warp][lane] = s;
   __syncthreads();
   if (warp != 0) return;
-  tl_end(a.tl);
   double t = 0.0;
 #pragma unroll
   for (int w = 0; w < kFFWarps; ++w) t += red[w][lane];
+  if (a.dp.world > 1) t = dp_allreduce_columns(a.dp, t, lane);
+  tl_end(a.tl);
   tot[lane] = t;
   __syncwarp();
   if (seg1) {
@@ -997,7 +1062,7 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
 
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
-                  unsigned char* ws, const ConvDims& d, cudaStream_t st) {
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp) {
   const FastPlan p = make_fast_plan(d);
   const size_t W = (size_t)d.B * d.Lout;
   float* gpre = reinterpret_cast<float*>(ws + p.off_gpre);
@@ -1040,11 +1105,16 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   // 4) finalize
   {
     FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridAdj, p.PA2,
-                  p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot()};
+                  p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot(), FastDp{}};
     const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
+    if (dp && dp->world > 1) {
+      a.dp = *dp;
+      a.dp.ncol = nblk * 32;
+    }
     {
       KernelTimer kt(kKBwdFinalize, st);
-      QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel, dim3(nblk), dim3(kFFThreads), 0, st, a));
+      if (a.dp.world > 1) QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel<512>, dim3(nblk), dim3(512), 0, st, a));
+      else QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel<1024>, dim3(nblk), dim3(1024), 0, st, a));
     }
     QW_CUDA_OK(cudaGetLastError());
   }

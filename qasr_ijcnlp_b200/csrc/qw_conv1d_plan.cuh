@@ -45,6 +45,17 @@ struct FastPlan {
 };
 constexpr int kHaloL = 8;    // gpre is stored halo-padded per utterance: [B][kHaloL + L_out + kHaloR][4]
 constexpr int kHaloR = 144;
+// data-parallel context of the fused finalize + gradient all-reduce (fast_finalize_kernel)
+constexpr int kDpMaxWorld = 8;
+struct FastDp {
+  float* bufs[kDpMaxWorld];      // peer r's receive buffer: [2 slots][world][ncol] 64-bit words (epoch << 32 | float bits)
+  unsigned* flags[kDpMaxWorld];  // only [rank] is used: epoch[cta], status (local bookkeeping)
+  int rank, world, ncol;
+  float scale;
+};
+inline int fast_dp_columns(const FastPlan& p) { return p.PA1 + p.PA2 + p.PB; }
+inline size_t fast_dp_buffer_bytes(const FastPlan& p, int world) { return (size_t)2 * world * fast_dp_columns(p) * 8; }
+inline size_t fast_dp_flag_bytes(const FastPlan& p) { return ((size_t)fast_dp_columns(p) / 32 + 1) * sizeof(unsigned); }
 struct FastAdjArgs {
   const float *pre_save, *gout, *qw;
   float *gpre_pad, *part;  // part: [grid][PA2] rows: [grad pre_conv.bias 4 + pad 28][Lq*32 gate-gradient matrices M]
@@ -59,7 +70,7 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
                  const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st);
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
-                  unsigned char* ws, const ConvDims& d, cudaStream_t st);
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp = nullptr);
 
 // fused inference stem (qw_stem.cu)
 size_t stem_workspace_bytes(int B, int L);

@@ -105,6 +105,64 @@ class _Pending:
         self.flat.mul_(1.0 / self.world)
 
 
+class FusedLayerGradAllReduce:
+    """Per-layer context of `qw_conv1d_backward_dp`: the mean over ranks of a QuantumConv1d layer's five parameter gradients is
+    taken INSIDE the backward's last kernel (every CTA of the finalize kernel stores (epoch, value) words straight into the peers'
+    receive buffers over NVLink and polls its own: one write latency, no fence, no separate collective, no bucket packing;
+    CUDA-graph capturable; bitwise identical on every rank).
+
+    Owns the layer's symmetric data / flag buffers (sizes depend on C, O, n_layers only).  torch symmetric memory does the
+    rendezvous.  world == 1 degenerates to the plain backward.  Attach to a module with `QuantumConv1d.fuse_grad_allreduce()`
+    or pass `.args()` to the raw entry point."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, stride: int, padding: int, n_qubits: int = 4,
+                 n_layers: int = 1, device=None, group=None):
+        import ctypes
+
+        from . import _lib
+
+        self._ctypes = ctypes
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        inited = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if inited else 1
+        self.rank = dist.get_rank(group) if inited else 0
+        dims = (1, in_channels, 64, kernel_size, stride, padding, out_channels, n_qubits, n_layers)
+        nbuf = self.lib.qw_conv1d_dp_buffer_bytes(*dims, self.world) // 4
+        nflag = self.lib.qw_conv1d_dp_flag_bytes(*dims, self.world) // 4
+        if nbuf == 0 or nflag == 0:
+            raise ValueError("the fused gradient all-reduce needs n_qubits == 4 and a valid layer geometry")
+        self.nbuf, self.nflag = nbuf, nflag
+        if self.world == 1:
+            self.buf = torch.zeros(nbuf, device=self.device, dtype=torch.float32)
+            self.flags = torch.zeros(nflag, device=self.device, dtype=torch.int32)
+            buf_ptrs, flag_ptrs = [self.buf.data_ptr()], [self.flags.data_ptr()]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            grp = group if group is not None else dist.group.WORLD
+            self.buf = symm_mem.empty(nbuf, dtype=torch.float32, device=self.device)
+            self.flags = symm_mem.empty(nflag, dtype=torch.int32, device=self.device)
+            self.buf.zero_()
+            self.flags.zero_()
+            self._hb = symm_mem.rendezvous(self.buf, grp)
+            self._hf = symm_mem.rendezvous(self.flags, grp)
+            buf_ptrs, flag_ptrs = list(self._hb.buffer_ptrs), list(self._hf.buffer_ptrs)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)  # every rank's flags are zero before anybody signals
+        P = ctypes.c_void_p
+        self._bufs = (P * self.world)(*[P(p) for p in buf_ptrs])
+        self._flags = (P * self.world)(*[P(p) for p in flag_ptrs])
+
+    def args(self):
+        """(peer_bufs, peer_flags, rank, world, scale) for qw_conv1d_backward_dp."""
+        return self._bufs, self._flags, self.rank, self.world, self._ctypes.c_float(1.0 / self.world)
+
+    def status(self) -> int:
+        """0 ok; 1 if some backward timed out waiting for a peer (synchronises)."""
+        return int(self.flags[self.nflag - 1].item())
+
+
 class P2PGradAllReduce:
     """One-shot NVLink peer-memory all-reduce (mean) of a small flat fp32 gradient bucket: `qw_grads_allreduce_p2p`.
 

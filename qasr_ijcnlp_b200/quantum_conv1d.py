@@ -35,7 +35,7 @@ def out_length(L: int, K: int, S: int, P: int) -> int:
 
 class _QuantumConv1dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w_pre, b_pre, qw, w_post, b_post, K, S, P, n_layers, emb):
+    def forward(ctx, x, w_pre, b_pre, qw, w_post, b_post, K, S, P, n_layers, emb, dpctx=None):
         lib = _lib.load()
         B, C, L = x.shape
         O, q = w_post.shape
@@ -57,6 +57,7 @@ class _QuantumConv1dFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(x, pre_save, *params)
             ctx.cfg = (B, C, L, K, S, P, O, q, n_layers, emb, f64)
+            ctx.dpctx = dpctx
         return y
 
     @staticmethod
@@ -74,17 +75,26 @@ class _QuantumConv1dFn(torch.autograd.Function):
         gb_post = torch.empty_like(b_post)
         nbytes = lib.qw_conv1d_workspace_bytes(B, C, L, K, S, P, O, q, n_layers, 8 if f64 else 4)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        fn = lib.qw_conv1d_backward_f64 if f64 else lib.qw_conv1d_backward
+        dpctx = getattr(ctx, "dpctx", None)
         with torch.cuda.device(dev):
-            st = fn(_ptr(gy), _ptr(x), _ptr(pre_save), _ptr(w_pre), _ptr(qw), _ptr(w_post), _ptr(gx), _ptr(gw_pre),
-                    _ptr(gb_pre), _ptr(gqw), _ptr(gw_post), _ptr(gb_post), _ptr(ws), nbytes,
-                    B, C, L, K, S, P, O, q, n_layers, emb, _stream())
+            if dpctx is not None and dpctx.world > 1:
+                if f64:
+                    raise RuntimeError("the fused gradient all-reduce is fp32 only")
+                # parameter gradients come back already averaged over the ranks (qw_conv1d_backward_dp); grad_x stays local
+                st = lib.qw_conv1d_backward_dp(_ptr(gy), _ptr(x), _ptr(pre_save), _ptr(w_pre), _ptr(qw), _ptr(w_post), _ptr(gx),
+                                               _ptr(gw_pre), _ptr(gb_pre), _ptr(gqw), _ptr(gw_post), _ptr(gb_post), _ptr(ws), nbytes,
+                                               B, C, L, K, S, P, O, q, n_layers, emb, *dpctx.args(), _stream())
+            else:
+                fn = lib.qw_conv1d_backward_f64 if f64 else lib.qw_conv1d_backward
+                st = fn(_ptr(gy), _ptr(x), _ptr(pre_save), _ptr(w_pre), _ptr(qw), _ptr(w_post), _ptr(gx), _ptr(gw_pre),
+                        _ptr(gb_pre), _ptr(gqw), _ptr(gw_post), _ptr(gb_post), _ptr(ws), nbytes,
+                        B, C, L, K, S, P, O, q, n_layers, emb, _stream())
         _lib.check(st, "qw_conv1d_backward")
-        return gx, gw_pre, gb_pre, gqw, gw_post, gb_post, None, None, None, None, None
+        return gx, gw_pre, gb_pre, gqw, gw_post, gb_post, None, None, None, None, None, None
 
 
 def quantum_conv1d(x, w_pre, b_pre, quantum_weights, w_post, b_post, kernel_size, stride=1, padding=0,
-                   n_layers=1, embedding="amplitude"):
+                   n_layers=1, embedding="amplitude", grad_allreduce=None):
     """Functional form.  x: (B, C, L) CUDA float32 (or float64 for the validation build)."""
     if x.dim() != 3:
         raise ValueError(f"expected input of shape (batch, channels, length), got {tuple(x.shape)}")
@@ -104,7 +114,7 @@ def quantum_conv1d(x, w_pre, b_pre, quantum_weights, w_post, b_post, kernel_size
     if quantum_weights.numel() != n_layers * q * 3:
         raise ValueError(f"quantum_weights has {quantum_weights.numel()} elements, expected {n_layers}*{q}*3")
     return _QuantumConv1dFn.apply(x, w_pre, b_pre, quantum_weights, w_post, b_post, int(kernel_size), int(stride),
-                                  int(padding), int(n_layers), EMBEDDINGS[embedding])
+                                  int(padding), int(n_layers), EMBEDDINGS[embedding], grad_allreduce)
 
 
 class QuantumConv1d(nn.Module):
@@ -130,6 +140,19 @@ class QuantumConv1d(nn.Module):
         self.post_conv = nn.Linear(self.n_qubits, out_channels)
         shape = (self.n_qubits, 3) if n_layers == 1 else (n_layers, self.n_qubits, 3)
         self.quantum_weights = nn.Parameter(torch.randn(*shape))
+        self._grad_allreduce = None  # dp.FusedLayerGradAllReduce: parameter gradients leave backward already averaged
+
+    def fuse_grad_allreduce(self, group=None):
+        """Data-parallel training: average this layer's parameter gradients over the process group INSIDE its backward
+        (`qw_conv1d_backward_dp`, one NVLink round trip in the last kernel) instead of in a separate collective.  Call once,
+        on every rank, after `.to(device)`.  The parameters must then be left out of any other gradient all-reduce.  Needs the
+        fast-path regime (n_qubits=4, amplitude embedding, k=3, stride 1|2, fp32)."""
+        from . import dp
+
+        self._grad_allreduce = dp.FusedLayerGradAllReduce(self.in_channels, self.out_channels, self.kernel_size, self.stride,
+                                                          self.padding, self.n_qubits, self.n_layers,
+                                                          device=self.pre_conv.weight.device, group=group)
+        return self
 
     def to(self, *args, **kwargs):  # the reference overrides .to(device) and returns self (:90-93)
         super().to(*args, **kwargs)
@@ -140,7 +163,7 @@ class QuantumConv1d(nn.Module):
             raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[1]}")
         return quantum_conv1d(x, self.pre_conv.weight, self.pre_conv.bias, self.quantum_weights,
                               self.post_conv.weight, self.post_conv.bias, self.kernel_size, self.stride,
-                              self.padding, self.n_layers, self.embedding)
+                              self.padding, self.n_layers, self.embedding, self._grad_allreduce)
 
     def extra_repr(self) -> str:
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "

@@ -105,3 +105,88 @@ def test_two_gpu_p2p_allreduce_matches_nccl():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def test_fused_backward_world1_equals_plain_backward(cuda):
+    """qw_conv1d_backward_dp with world == 1 is the plain backward (and the module hook is a no-op)."""
+    from qasr_ijcnlp_b200 import QuantumConv1d
+    torch.manual_seed(5)
+    m = QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(cuda)
+    x = torch.randn(2, 80, 256, device=cuda)
+    gy = torch.randn(2, 384, 256, device=cuda)
+    ref = torch.autograd.grad(m(x), list(m.parameters()), gy)
+    m.fuse_grad_allreduce()
+    got = torch.autograd.grad(m(x), list(m.parameters()), gy)
+    assert all(torch.equal(a, b) for a, b in zip(ref, got))
+
+
+def _worker_fused(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from qasr_ijcnlp_b200 import QuantumConv1d
+        ok = True
+        for (C, S, B, L) in ((80, 1, 4, 3000), (384, 2, 2, 3000), (8, 1, 1, 64)):
+            torch.manual_seed(11)  # same parameters on every rank
+            plain = QuantumConv1d(C, 384, 3, stride=S, padding=1, n_qubits=4).to(dev)
+            torch.manual_seed(11)
+            fused = QuantumConv1d(C, 384, 3, stride=S, padding=1, n_qubits=4).to(dev).fuse_grad_allreduce()
+            for it in range(3):  # both epoch parities
+                g = torch.Generator(device=dev).manual_seed(1000 * it + rank)  # different data per rank
+                x = torch.randn(B, C, L, device=dev, generator=g, requires_grad=True)
+                gy = torch.randn(B, 384, (L + 2 - 3) // S + 1, device=dev, generator=g)
+                ref = list(torch.autograd.grad(plain(x), [x] + list(plain.parameters()), gy))
+                for t in ref[1:]:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                    t /= world
+                got = torch.autograd.grad(fused(x), [x] + list(fused.parameters()), gy)
+                ok = ok and torch.equal(ref[0], got[0])  # grad_x stays local
+                for a, b in zip(ref[1:], got[1:]):
+                    # each rank's column sums are rounded to fp32 before the exchange: 1e-6 relative to the largest entry
+                    ok = ok and (a - b).abs().max().item() <= 1e-6 * max(1.0, a.abs().max().item())
+                    gathered = [torch.empty_like(b) for _ in range(world)]
+                    dist.all_gather(gathered, b.contiguous())
+                    ok = ok and all(torch.equal(gathered[0], t) for t in gathered)  # bitwise identical on every rank
+            ok = ok and fused._grad_allreduce.status() == 0
+        # inside a replayed CUDA graph
+        torch.manual_seed(11)
+        fused = QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(dev).fuse_grad_allreduce()
+        x = torch.full((2, 80, 256), float(rank + 1), device=dev) + torch.randn(2, 80, 256, device=dev)
+        gy = torch.randn(2, 384, 256, device=dev)
+        eager = torch.autograd.grad(fused(x), list(fused.parameters()), gy)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            captured = torch.autograd.grad(fused(x), list(fused.parameters()), gy)
+        torch.cuda.synchronize()
+        dist.barrier()
+        for _ in range(3):
+            graph.replay()
+            torch.cuda.synchronize()
+            ok = ok and all(torch.equal(a, b) for a, b in zip(eager, captured))
+        ok = ok and fused._grad_allreduce.status() == 0
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_fused_backward_allreduce_matches_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_fused, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}

@@ -23,9 +23,16 @@ def main():
     a = ap.parse_args()
     from qasr_ijcnlp_b200 import _lib
 
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    rank, world, local = bench.dist_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
     runner = bench.StemRunner(a.batch, dev, a.nsets)
+    if world > 1:  # torchrun: the all-reduce fused into every layer's finalize kernel (qw_conv1d_backward_dp)
+        from qasr_ijcnlp_b200 import dp
+
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        runner.fused_dp = {name: dp.FusedLayerGradAllReduce(cfg["C"], cfg["O"], cfg["K"], cfg["S"], cfg["P"], bench.Q, 1, device=dev)
+                           for name, cfg in bench.LAYERS.items()}
     lib = _lib.load()
     for i in range(2):
         n0 = _lib.launch_count()
@@ -61,6 +68,8 @@ def main():
     for r in range(a.reps):
         reset()
         torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
         graphs[r % a.nsets].replay()
         torch.cuda.synchronize()
         t = buf.cpu().tolist()
@@ -69,7 +78,10 @@ def main():
     # median over reps of span / gap, relative to the first kernel's start
     import statistics as st
 
-    print(f"# stem step, batch {a.batch}, {per_step} kernels per step, median of {a.reps} single graph replays (ns from %globaltimer)")
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
+    print(f"# stem step, batch {a.batch}, world {world}, {per_step} kernels per step, median of {a.reps} single graph replays (ns from %globaltimer)")
     print(f"# {'kernel':12s} {'start':>9s} {'end':>9s} {'span':>8s} {'gap_to_prev_end':>16s}")
     tot = []
     for k in range(nslots):
