@@ -132,13 +132,15 @@ int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* 
                         int n_samples, int n_mels, void* stream);
 
 /* ---- data-parallel training collective (the reference is single-process, train_quantum_whisper.py:195-214):
- * one-shot all-reduce of a small fp32 gradient bucket over NVLink peer memory, fused with the `scale` (1/world) multiply.
- * grads (n) is reduced in place.  peer_bufs / peer_flags are HOST arrays of `world` device pointers: rank r's symmetric data
- * buffer (qw_grads_allreduce_p2p_buffer_bytes(n) bytes) and flag array (qw_grads_allreduce_p2p_flag_bytes(world) bytes,
- * zero-initialised once), each mapped into this process (e.g. torch.distributed._symmetric_memory).  Every rank must
- * enqueue the call the same number of times; the kernel keeps its epoch in the flag array, so it is graph-capturable.
- * A peer that never arrives makes the kernel give up after ~1 s and set flag word [2*world+1] to 1 (no hang). */
-size_t qw_grads_allreduce_p2p_buffer_bytes(long long n);
+ * one-shot all-reduce of a small fp32 gradient bucket (n <= 2^20) over NVLink peer memory, fused with the `scale` (1/world)
+ * multiply.  grads (n) is reduced in place.  peer_bufs is a HOST array of `world` device pointers: rank r's receive buffer
+ * (qw_grads_allreduce_p2p_buffer_bytes(n, world) bytes, zero-initialised once, mapped into this process e.g. by
+ * torch.distributed._symmetric_memory); peer_flags[rank] is the caller's own zero-initialised bookkeeping array
+ * (qw_grads_allreduce_p2p_flag_bytes(world) bytes; the other entries are ignored).  Each rank stores (epoch, value) words
+ * straight into its peers' buffers (no fence, no remote read).  Every rank must enqueue the call the same number of times; the
+ * kernel keeps its epoch in the bookkeeping array, so it is graph-capturable.  A peer that never arrives makes the kernel give
+ * up after ~1 s and set the last bookkeeping word to 1 (no hang). */
+size_t qw_grads_allreduce_p2p_buffer_bytes(long long n, int world);
 size_t qw_grads_allreduce_p2p_flag_bytes(int world);
 int qw_grads_allreduce_p2p(float* grads, long long n, void* const* peer_bufs, void* const* peer_flags, int rank, int world,
                            float scale, void* stream);

@@ -52,7 +52,7 @@ _SIGNATURES = {
     "qw_log_mel_prep_bytes": (_SZ, [_I]),
     "qw_log_mel_prepare": (_I, [_P, _I, _P, _SZ, _P]),
     "qw_log_mel_prepared": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _P]),
-    "qw_grads_allreduce_p2p_buffer_bytes": (_SZ, [_LL]),
+    "qw_grads_allreduce_p2p_buffer_bytes": (_SZ, [_LL, _I]),
     "qw_grads_allreduce_p2p_flag_bytes": (_SZ, [_I]),
     "qw_grads_allreduce_p2p": (_I, [_P, _LL, ctypes.POINTER(_P), ctypes.POINTER(_P), _I, _I, ctypes.c_float, _P]),
 }

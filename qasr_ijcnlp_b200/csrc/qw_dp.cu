@@ -1,15 +1,18 @@
 // One-shot all-reduce of the (small) trainable-gradient bucket over NVLink peer memory, fused with the 1/world scaling:
 // the data-parallel collective of SURVEY.md 8e for the `freeze_non_quantum_layers` regime (9 440 floats for the two
-// quantum layers + a task head).  NCCL stays the path for large buckets (qasr_ijcnlp_b200.dp.GradBucket).
+// quantum layers + a task head).  NCCL stays the path for large buckets (qasr_ijcnlp_b200.dp.GradBucket); a QuantumConv1d
+// layer can also take the all-reduce into its own backward (qw_conv1d_backward_dp, qw_conv1d_fast.cu).
 //
-// Every rank owns a SYMMETRIC buffer (2 slots x n floats) and a flag array (2 x world uint32 + epoch + status), both
-// mapped into every peer's address space (torch symmetric memory does the rendezvous; the library only sees pointers).
-// The bucket is cut into <= 64 chunks, one CTA per chunk, each with its own flags (no grid-wide barrier needed):
-//   1. copy my chunk into my slot (epoch parity), __threadfence_system, store flag[slot][cta][my rank] = epoch into EVERY
-//      peer's flag array (P2P stores);
-//   2. spin until my own flag[slot][cta][r] >= epoch for every r (bounded: ~1 s, then status = 1);
-//   3. out[i] = scale * sum_r peer_slot_r[i] in fixed rank order, all peer loads of a float4 in flight at once, L1 bypassed
-//      -> bitwise identical on all ranks.
+// Every rank owns a RECEIVE buffer of [2 slots][world][n] 64-bit words mapped into every peer's address space (torch symmetric
+// memory does the rendezvous; the library only sees pointers) and a local bookkeeping array (epoch per CTA + status).
+// The bucket is cut into <= 64 chunks, one CTA per chunk:
+//   1. every thread packs (epoch << 32 | float bits) of its elements and stores the word straight into slot
+//      [epoch parity][my rank][i] of EVERY peer's buffer (posted P2P stores; data and flag in ONE atomic 8-byte store, the idea
+//      of NCCL's LL protocol: no fence, no separate flag, no remote read);
+//   2. it polls its own buffer until the word of every rank carries the epoch (bounded: ~1 s, then status = 1 and the local
+//      value is kept) and sums the payloads in fixed rank order -> bitwise identical on all ranks; out[i] = scale * sum.
+// First version (publish into my own buffer, __threadfence_system, st.release.sys flags into the peers, acquire-spin, remote
+// loads): each system-scope fence cost 3-6 us on B200 and the whole exchange ~19 us; this one is one NVLink write latency.
 // The epoch lives in device memory and is advanced by the kernel itself, so the launch is CUDA-graph capturable.
 // Double buffering by epoch parity is sufficient: a rank can only be one epoch ahead of the slowest reader.
 #include "../../include/qw.h"
@@ -20,32 +23,26 @@ namespace dp {
 
 constexpr int kMaxWorld = 8;
 constexpr int kThreadsAR = 256;
-constexpr int kMaxCtas = 64;  // the bucket is cut into <= 64 chunks, one CTA (and one set of flags) per chunk
+constexpr int kMaxCtas = 64;  // the bucket is cut into <= 64 chunks, one CTA (and one epoch word) per chunk
 
-// flag array (uint32): arrival[slot][cta][rank] at (slot * kMaxCtas + cta) * world + rank; epoch[cta] at 2 * kMaxCtas * world + cta;
-// status at 2 * kMaxCtas * world + kMaxCtas (the last word)
-__host__ __device__ inline int flag_words(int world) { return 2 * kMaxCtas * world + kMaxCtas + 1; }
+// bookkeeping words (uint32, local): epoch[cta] at cta; status at kMaxCtas (the last word)
+__host__ __device__ inline int flag_words(int) { return kMaxCtas + 1; }
 
 struct ARArgs {
-  float* grads;                 // (n) in / out, local
-  float* bufs[kMaxWorld];       // peer r's symmetric data buffer (2 * n4 * 4 floats)
-  unsigned* flags[kMaxWorld];   // peer r's flag array
-  long long n, n4;              // elements; float4 groups (ceil)
-  int rank, world, per_cta4;    // float4 groups per CTA
+  float* grads;                        // (n) in / out, local
+  unsigned long long* bufs[kMaxWorld]; // peer r's receive buffer: [2][world][n] words
+  unsigned* book;                      // my bookkeeping words
+  long long n;
+  int rank, world, per_cta;            // elements per CTA
   float scale;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_cv4(const float* p) {
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -53,71 +50,45 @@ __global__ void __launch_bounds__(kThreadsAR) grads_allreduce_p2p_kernel(const A
   __shared__ unsigned s_epoch;
   __shared__ int s_bad;
   const int tid = threadIdx.x, cta = blockIdx.x;
-  unsigned* myflags = a.flags[a.rank];
-  const int eidx = 2 * kMaxCtas * a.world + cta;
   if (tid == 0) {
-    s_epoch = myflags[eidx] + 1u;
+    s_epoch = a.book[cta] + 1u;
     s_bad = 0;
   }
   __syncthreads();
   const unsigned epoch = s_epoch;
-  const int slot = epoch & 1u;
-  const long long g0 = (long long)cta * a.per_cta4;
-  const long long g1 = (g0 + a.per_cta4 < a.n4) ? g0 + a.per_cta4 : a.n4;
-  const size_t slot_off = (size_t)slot * a.n4 * 4;
-  float* myslot = a.bufs[a.rank] + slot_off;
-  // 1. publish my chunk (the slot is padded to whole float4 groups; the ragged tail of `grads` is read element-wise)
-  for (long long g = g0 + tid; g < g1; g += kThreadsAR) {
-    float4 v;
-    if (4 * g + 3 < a.n) v = *reinterpret_cast<const float4*>(a.grads + 4 * g);
-    else {
-      v.x = 4 * g < a.n ? a.grads[4 * g] : 0.f;
-      v.y = 4 * g + 1 < a.n ? a.grads[4 * g + 1] : 0.f;
-      v.z = 4 * g + 2 < a.n ? a.grads[4 * g + 2] : 0.f;
-      v.w = 0.f;
-    }
-    *reinterpret_cast<float4*>(myslot + 4 * g) = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  const int fbase = (slot * kMaxCtas + cta) * a.world;
-  if (tid < a.world) {
-    st_release_sys(a.flags[tid] + fbase + a.rank, epoch);
-    // 2. wait for every rank's chunk (bounded: ~1 s, then give up instead of hanging the GPU)
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(myflags + fbase + tid) - epoch) < 0) {
-      if (clock64() - t0 > 2000000000LL) {
-        s_bad = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  if (s_bad) {
-    if (tid == 0) myflags[2 * kMaxCtas * a.world + kMaxCtas] = 1u;
-  } else {
-    // 3. fixed-order sum over ranks with L1-bypassing peer loads: bitwise identical on every rank
-    for (long long g = g0 + tid; g < g1; g += kThreadsAR) {
-      float4 v[kMaxWorld];
+  const size_t slot_base = (size_t)(epoch & 1u) * a.world;
+  const long long i0 = (long long)cta * a.per_cta;
+  const long long i1 = (i0 + a.per_cta < a.n) ? i0 + a.per_cta : a.n;
+  // 1. push my elements into every peer's receive buffer
+  for (long long i = i0 + tid; i < i1; i += kThreadsAR) {
+    const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(a.grads[i]);
 #pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r)
-        if (r < a.world) v[r] = ld_cv4(a.bufs[r] + slot_off + 4 * g);
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r)
-        if (r < a.world) {
-          s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w;
-        }
-      s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
-      if (4 * g + 3 < a.n) *reinterpret_cast<float4*>(a.grads + 4 * g) = s;
-      else {
-        if (4 * g < a.n) a.grads[4 * g] = s.x;
-        if (4 * g + 1 < a.n) a.grads[4 * g + 1] = s.y;
-        if (4 * g + 2 < a.n) a.grads[4 * g + 2] = s.z;
-      }
-    }
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < a.world) st_u64(a.bufs[r] + (slot_base + a.rank) * a.n + i, word);
   }
-  if (tid == 0) myflags[eidx] = epoch;
+  // 2. gather: poll my own buffer, fixed rank order
+  const unsigned long long* mine = a.bufs[a.rank];
+  const long long t0 = clock64();
+  bool bad = false;
+  for (long long i = i0 + tid; i < i1; i += kThreadsAR) {
+    float s = 0.f;
+    for (int r = 0; r < a.world; ++r) {
+      const unsigned long long* src = mine + (slot_base + r) * a.n + i;
+      unsigned long long v = ld_u64(src);
+      while ((unsigned)(v >> 32) != epoch && !bad) {
+        if (clock64() - t0 > 2000000000LL) bad = true;  // ~1 s: give up instead of hanging the GPU
+        else v = ld_u64(src);
+      }
+      s += __uint_as_float((unsigned)v);
+    }
+    if (!bad) a.grads[i] = s * a.scale;
+  }
+  if (bad) s_bad = 1;
+  __syncthreads();
+  if (tid == 0) {
+    if (s_bad) a.book[kMaxCtas] = 1u;
+    a.book[cta] = epoch;
+  }
 }
 
 }  // namespace dp
@@ -125,7 +96,9 @@ __global__ void __launch_bounds__(kThreadsAR) grads_allreduce_p2p_kernel(const A
 
 extern "C" {
 
-size_t qw_grads_allreduce_p2p_buffer_bytes(long long n) { return n > 0 ? (size_t)2 * ((n + 3) / 4) * 4 * sizeof(float) : 0; }
+size_t qw_grads_allreduce_p2p_buffer_bytes(long long n, int world) {
+  return (n > 0 && world > 0) ? (size_t)2 * world * n * sizeof(unsigned long long) : 0;
+}
 size_t qw_grads_allreduce_p2p_flag_bytes(int world) { return world > 0 ? (size_t)qw::dp::flag_words(world) * sizeof(unsigned) : 0; }
 
 int qw_grads_allreduce_p2p(float* grads, long long n, void* const* peer_bufs, void* const* peer_flags, int rank, int world,
@@ -135,20 +108,19 @@ int qw_grads_allreduce_p2p(float* grads, long long n, void* const* peer_bufs, vo
   QW_CHECK_ARG(grads && peer_bufs && peer_flags && n > 0, -1, "qw_grads_allreduce_p2p: null pointer or empty bucket");
   QW_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, -1, "qw_grads_allreduce_p2p: bad rank/world %d/%d (world <= %d)",
                rank, world, kMaxWorld);
-  QW_CHECK_ARG(n <= (1LL << 22), -2, "qw_grads_allreduce_p2p: bucket of %lld floats is too large for the one-shot kernel (use NCCL)", n);
+  QW_CHECK_ARG(n <= (1LL << 20), -2, "qw_grads_allreduce_p2p: bucket of %lld floats is too large for the one-shot kernel (use NCCL)", n);
   ARArgs a{};
   a.grads = grads;
   for (int r = 0; r < world; ++r) {
-    QW_CHECK_ARG(peer_bufs[r] && peer_flags[r], -1, "qw_grads_allreduce_p2p: null peer pointer for rank %d", r);
-    a.bufs[r] = (float*)peer_bufs[r];
-    a.flags[r] = (unsigned*)peer_flags[r];
+    QW_CHECK_ARG(peer_bufs[r], -1, "qw_grads_allreduce_p2p: null peer pointer for rank %d", r);
+    a.bufs[r] = (unsigned long long*)peer_bufs[r];
   }
-  QW_CHECK_ARG(((uintptr_t)grads & 15) == 0, -1, "qw_grads_allreduce_p2p: the bucket must be 16-byte aligned");
+  QW_CHECK_ARG(peer_flags[rank], -1, "qw_grads_allreduce_p2p: null bookkeeping pointer");
+  a.book = (unsigned*)peer_flags[rank];
   a.n = n;
-  a.n4 = (n + 3) / 4;
-  int ctas = (int)((a.n4 + kThreadsAR - 1) / kThreadsAR);
+  int ctas = (int)((n + 4 * kThreadsAR - 1) / (4 * kThreadsAR));
   ctas = ctas < 1 ? 1 : ctas > kMaxCtas ? kMaxCtas : ctas;
-  a.per_cta4 = (int)((a.n4 + ctas - 1) / ctas);
+  a.per_cta = (int)((n + ctas - 1) / ctas);
   a.rank = rank;
   a.world = world;
   a.scale = scale;

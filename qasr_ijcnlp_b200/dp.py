@@ -183,7 +183,7 @@ class P2PGradAllReduce:
         inited = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if inited else 1
         self.rank = dist.get_rank(group) if inited else 0
-        nbuf = self.lib.qw_grads_allreduce_p2p_buffer_bytes(self.numel) // 4
+        nbuf = self.lib.qw_grads_allreduce_p2p_buffer_bytes(self.numel, self.world) // 4
         nflag = self.lib.qw_grads_allreduce_p2p_flag_bytes(self.world) // 4
         self.nflag = nflag
         if self.world == 1:
