@@ -70,8 +70,11 @@ __host__ __device__ constexpr size_t fast_fwd_smem_bytes(int CK, int O, int Lq) 
 //                          tile n-1 (outs[(n-1)&1] -> y, 128-bit coalesced stores).
 //   warp  8   (circuit)  : tile n: part[n&1] -> bias, statevector circuit, <Z_i> -> outs[n&1] (+ pre_save/qout_save).
 // Hand-offs: pfull/pempty (part), ofull/oempty (outs).  No CTA-wide barrier inside the loop.
+// (Specialising this kernel for n_layers == 1 like the adjoint kernel -- 56 -> 48 KB of SASS, 96 -> 72 registers -- changed
+// nothing: 131.9 us per step either way.  Its circuit code is one warp's side job, not the whole kernel.)
 template <int S, int RC>
 __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const FastFwdArgs a) {
+  const int Lq = a.Lq;
   constexpr int XW = fwd_xw<S>();
   constexpr int STAGE_ELEMS = RC * XW;
   constexpr int ITS = RC / (4 * kFwdSW);  // kFwdSW warps x 4 rows per iteration
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
   float* bpost = wpost + (size_t)a.O * FQ;                          // [O]
   float* bpre = bpost + align_up(a.O, 4);                           // [4]
   float* gates = bpre + 4;                                          // [Lq][4][16]
-  float* part = gates + (size_t)a.Lq * FQ * kGateStride;            // [2][kFwdSW][32][4]
+  float* part = gates + (size_t)Lq * FQ * kGateStride;              // [2][kFwdSW][32][4]
   float* outs = part + 2 * kFwdSW * FTW * FQ;                       // [2][32][4]
   uint64_t* full = reinterpret_cast<uint64_t*>(outs + 2 * FTW * FQ);  // [kFwdStages]
   uint64_t* empty = full + kFwdStages;                              // [kFwdStages]
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
   for (int u = tid; u < a.O; u += kFwdSW * 32) st4(wpost + (size_t)u * FQ, ld4(a.w_post + (size_t)u * FQ));
   for (int idx = tid; idx < a.O; idx += kFwdSW * 32) bpost[idx] = a.b_post[idx];
   if (tid < FQ) bpre[tid] = a.b_pre[tid];
-  if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  if (tid < Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   }
   __syncthreads();
   pdl_wait();    // nothing global is written above
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       float out[FQ] = {0.f, 0.f, 0.f, 0.f};
       if (lane < a.tw && i < a.Lout) {
         float re[1 << FQ], im[1 << FQ];
-        circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+        circuit_forward_amp<float, FQ>(pre, gates, Lq, re, im, out);
         const size_t wi = (size_t)b * a.Lout + i;
         if (a.pre_save) st4(a.pre_save + wi * FQ, make_float4(pre[0], pre[1], pre[2], pre[3]));
         if (a.qout_save) st4(a.qout_save + wi * FQ, make_float4(out[0], out[1], out[2], out[3]));
@@ -505,14 +508,18 @@ __global__ void __launch_bounds__(32 * NW, 2) fast_bwd_gy2_kernel(const __grid_c
 // against the programmatically launched 1 024-thread finalize kernel, which costs 3-4 us per layer in the graph.
 constexpr int kAdjThreads = 128;
 
+// MULTI = false: the reference circuit (one layer); the n_layers loop of the circuit code folds away: 64 -> 35 KB of SASS,
+// 128 -> 96 registers, and the batch-16 step drops from 135.3 to 132.1 us (QW_ADJ_SPEC=0 selects the general kernel for A/B)
+template <bool MULTI>
 __global__ void __launch_bounds__(kAdjThreads, 4) fast_bwd_adj_kernel(const FastAdjArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  const int NE = FQ + a.Lq * 32;
+  const int Lq = MULTI ? a.Lq : 1;
+  const int NE = FQ + Lq * 32;
   float* gates = reinterpret_cast<float*>(smem_dyn);             // [Lq][4][16]
-  float* macc = gates + (size_t)a.Lq * FQ * kGateStride;         // [4 warps][NE][kGyMS]
+  float* macc = gates + (size_t)Lq * FQ * kGateStride;         // [4 warps][NE][kGyMS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   tl_begin(a.tl);
-  if (tid < a.Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  if (tid < Lq * FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
   for (int e = tid; e < 4 * NE * kGyMS; e += kAdjThreads) macc[e] = 0.f;
   __syncthreads();
   float* mymacc = macc + (size_t)warp * NE * kGyMS;
@@ -535,12 +542,12 @@ __global__ void __launch_bounds__(kAdjThreads, 4) fast_bwd_adj_kernel(const Fast
     const float4 pv = valid ? ld4(a.pre_save + (size_t)w * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
     const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
     float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
-    const float inv = circuit_forward_amp<float, FQ>(pre, gates, a.Lq, re, im, out);
+    const float inv = circuit_forward_amp<float, FQ>(pre, gates, Lq, re, im, out);
     wait_once();
     const float4 gv = valid ? ld4(a.gout + (size_t)w * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
     SmemGateAcc<float, FQ> acc{mymacc + (size_t)FQ * kGyMS + lane, kGyMS, 0};
-    circuit_backward_amp<float, FQ>(pre, inv, gates, a.Lq, re, im, gout, gpre, acc);
+    circuit_backward_amp<float, FQ>(pre, inv, gates, Lq, re, im, gout, gpre, acc);
     if (valid) {
       const int b = (int)(w / a.Lout), i = (int)(w - (long long)b * a.Lout);
       st4(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(kAdjThreads, 4) fast_bwd_adj_kernel(const Fast
   for (int e = warp; e < a.PA2; e += kAdjThreads / 32) {
     // e in [0,4): grad pre_conv.bias; [32, 32+Lq*32): gate matrices; everything else padding
     float v = 0.f;
-    const int src = e < FQ ? e : (e >= 32 && e < 32 + a.Lq * 32) ? FQ + (e - 32) : -1;
+    const int src = e < FQ ? e : (e >= 32 && e < 32 + Lq * 32) ? FQ + (e - 32) : -1;
     if (src >= 0) {
 #pragma unroll
       for (int wq = 0; wq < 4; ++wq) v += macc[((size_t)wq * NE + src) * kGyMS + lane];
@@ -1084,10 +1091,12 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   {
     FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W, timeline_next_slot()};
     const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
-    if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(fast_bwd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const int adj_spec = env_flag("QW_ADJ_SPEC", 1);
+    auto k = (d.Lq == 1 && adj_spec) ? fast_bwd_adj_kernel<false> : fast_bwd_adj_kernel<true>;
+    if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
       KernelTimer kt(kKBwdAdj, st);
-      QW_CUDA_OK(launch_pdl(p.small, fast_bwd_adj_kernel, dim3(p.gridAdj), dim3(kAdjThreads), smem, st, aa));
+      QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridAdj), dim3(kAdjThreads), smem, st, aa));
     }
     QW_CUDA_OK(cudaGetLastError());
   }
