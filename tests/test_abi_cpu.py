@@ -107,3 +107,24 @@ def test_cpu_input_fails_loudly():
         quantum_circuit(torch.randn(5, 4), torch.randn(4, 3))
     with pytest.raises(RuntimeError, match="no CPU path"):
         qa.log_mel_spectrogram(torch.randn(2, 16000))
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(lib):
+    """qw_stem_forward / qw_conv1d_backward_dp / the dp size queries: bad arguments come back as negative status before any
+    CUDA call; the size queries are pure host arithmetic."""
+    st = lib.qw_stem_forward(*([None] * 13), None, 0, 1, 80, 3000, 384, 384, 1, None)
+    assert st == -1 and b"null" in lib.qw_last_error()
+    assert lib.qw_stem_workspace_bytes(16, 3000) >= 2 * 16 * 3000 * 4 * 4 and lib.qw_stem_workspace_bytes(0, 3000) == 0
+    dims = (16, 384, 3000, 3, 2, 1, 384, 4, 1)
+    n2, n8 = lib.qw_conv1d_dp_buffer_bytes(*dims, 2), lib.qw_conv1d_dp_buffer_bytes(*dims, 8)
+    assert n2 > 0 and n8 == 4 * n2                                   # [2 slots][world][columns] 8-byte words
+    assert n2 == 2 * 2 * (1920 + 64 + 4608) * 8                       # columns: gy rows + adjoint rows + pre_conv^T rows
+    assert lib.qw_conv1d_dp_buffer_bytes(*dims, 9) == 0               # world <= 8
+    assert lib.qw_conv1d_dp_buffer_bytes(16, 384, 3000, 3, 2, 1, 384, 6, 1, 2) == 0   # fast path is n_qubits == 4
+    assert lib.qw_conv1d_dp_flag_bytes(*dims, 2) == ((1920 + 64 + 4608) // 32 + 1) * 4
+    P = ctypes.c_void_p
+    tbl = (P * 2)(P(0), P(0))
+    st = lib.qw_conv1d_backward_dp(*([None] * 12), None, 0, *dims, 0, tbl, tbl, 3, 2, ctypes.c_float(0.5), None)
+    assert st == -1 and b"rank/world" in lib.qw_last_error()
+    assert lib.qw_grads_allreduce_p2p_buffer_bytes(9440, 8) == 2 * 8 * 9440 * 8
+    assert lib.qw_timeline_set(None, 0) == 0
