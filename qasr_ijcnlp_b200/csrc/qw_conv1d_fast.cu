@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(kAdjThreads, 4) fast_bwd_adj_kernel(const Fast
     if (waited) return;
     waited = true;
     pdl_wait();
+    if (a.early_trigger) pdl_launch();
     // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance)
     const int per = (kHaloL + kHaloR) * FQ;
     for (long long idx = (long long)blockIdx.x * kAdjThreads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kAdjThreads) {
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(kAdjThreads, 4) fast_bwd_adj_kernel(const Fast
     for (int j = 0; j < FQ; ++j) mymacc[j * kGyMS + lane] += valid ? gpre[j] : 0.f;
   }
   wait_once();   // a CTA without windows still owes the halo zeroing
-  pdl_launch();  // late: an early trigger (measured: +0.3 us) lets the next kernel's CTAs crowd the SMs this latency-bound grid needs
+  if (!a.early_trigger) pdl_launch();  // late (QW_ADJ_TRIG=0): an early trigger (measured: +0.3 us) lets the next kernel's CTAs crowd the SMs this latency-bound grid needs
   __syncthreads();
   float* prow = a.part + (size_t)blockIdx.x * a.PA2;
   for (int e = warp; e < a.PA2; e += kAdjThreads / 32) {
@@ -745,6 +746,7 @@ struct FastFinArgs {
   int C, O, Lq;
   unsigned long long* tl;
   FastDp dp;  // world <= 1: plain finalize
+  int early12;
 };
 
 // Data-parallel training fuses the gradient all-reduce INTO this kernel ("fuse the intra-GPU reduction into that
@@ -813,12 +815,16 @@ __global__ void __launch_bounds__(kFFThreads) fast_finalize_kernel(const FastFin
   __shared__ double red[kFFWarps][33];
   __shared__ double tot[32];
   tl_begin(a.tl);
-  pdl_wait();
-  pdl_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb1 = a.P1 / 32, nb2 = a.P2 / 32;
   const bool seg1 = (int)blockIdx.x < nb1;
   const bool seg2 = !seg1 && (int)blockIdx.x < nb1 + nb2;
+  // Segments 1 and 2 reduce the rows of the gy and adjoint kernels.  Those grids completed before this kernel's immediate
+  // predecessor (pre_conv^T) passed ITS dependency wait, which is before it triggered this launch -- so their rows are final
+  // and visible already, and these CTAs (the lowest block indices: scheduled first, as pre_conv^T CTAs retire) do their whole
+  // job, all-reduce included, while pre_conv^T is still streaming.  Only segment 3 waits.
+  if (!(a.early12 && (seg1 || seg2))) pdl_wait();
+  pdl_launch();
   const int blk = seg1 ? blockIdx.x : seg2 ? blockIdx.x - nb1 : blockIdx.x - nb1 - nb2;
   const int G = seg1 ? a.G1 : seg2 ? a.G2 : a.G3;
   const int P = seg1 ? a.P1 : seg2 ? a.P2 : a.P3;
@@ -909,7 +915,12 @@ static int env_flag(const char* name, int dflt) {
 // Experiment switches (defaults = the measured winners on B200, batch-16 stem step):
 //   QW_FWD_ETMA  1: the forward kernel requests its first x tiles before staging its parameters        (-1.0 us / step)
 //   QW_PRE_EX    1: the pre_conv^T kernel requests its first x tiles before the dependency wait        (-1.7 us)
+//   QW_FIN_EARLY 1: finalize segments 1-2 (rows of the gy / adjoint kernels) run before the dependency wait  (-2.6 us)
+//   QW_ADJ_TRIG  1: the adjoint kernel triggers its dependent right after its wait, so pre_conv^T CTAs come in and request
+//                   their x tiles while it runs (+0.3 us with the 128-register adjoint kernel, -1.4 us with the 96-register one)
 static int flag_fwd_etma() { static const int v = env_flag("QW_FWD_ETMA", 1); return v; }
+static int flag_fin_early() { static const int v = env_flag("QW_FIN_EARLY", 1); return v; }
+static int flag_adj_trig() { static const int v = env_flag("QW_ADJ_TRIG", 1); return v; }
 static int flag_pre_ex() { static const int v = env_flag("QW_PRE_EX", 1); return v; }
 static bool g_fast_enabled = true;
 void set_fast_path(bool on) { g_fast_enabled = on; }
@@ -970,7 +981,9 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.num_ptiles = d.B * p.ptiles_per_utt;
   p.nchunks = (d.C + 31) / 32;
   p.Cpad = p.nchunks * 32;
-  int cap = 3 * sms / p.nchunks;
+  // CTAs per SM of the pre_conv^T kernel: 4 x 52 KB of shared memory fit; measured at batch 16: 2 -> 133.0, 3 -> 127.9, 4 -> 126.9 us
+  static const int pre_ctas = env_flag("QW_PRE_CTAS", 4);
+  int cap = pre_ctas * sms / p.nchunks;
   if (cap < 1) cap = 1;
   p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
   p.PB = p.Cpad * 12;
@@ -1089,7 +1102,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   }
   // 2) adjoint differentiation of the circuit, one window per thread
   {
-    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W, timeline_next_slot()};
+    FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W, flag_adj_trig(), timeline_next_slot()};
     const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
     static const int adj_spec = env_flag("QW_ADJ_SPEC", 1);
     auto k = (d.Lq == 1 && adj_spec) ? fast_bwd_adj_kernel<false> : fast_bwd_adj_kernel<true>;
@@ -1114,7 +1127,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   // 4) finalize
   {
     FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridAdj, p.PA2,
-                  p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot(), FastDp{}};
+                  p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot(), FastDp{}, flag_fin_early()};
     const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
     if (dp && dp->world > 1) {
       a.dp = *dp;

@@ -61,6 +61,7 @@ struct FastAdjArgs {
   float *gpre_pad, *part;  // part: [grid][PA2] rows: [grad pre_conv.bias 4 + pad 28][Lq*32 gate-gradient matrices M]
   int B, Lout, LP, Lq, PA2;
   long long W;
+  int early_trigger;  // experiment switch QW_ADJ_TRIG: trigger the dependent launch right after the wait
   unsigned long long* tl;
 };
 void set_fast_path(bool on);
