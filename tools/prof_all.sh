@@ -8,4 +8,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/prof_step.py --steps 1 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -o gpurun_out/final_prof_step python tools/prof_step.py --steps 1 > gpurun_out/ncu_step2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:stem2 -c 1 -o gpurun_out/final_prof_stem2 python tools/bench_stem.py --batches 64 --reps 3 > gpurun_out/ncu_stem2b.log 2>&1
-tail -2 gpurun_out/final_bench.err gpurun_out/ncu_step2.log gpurun_out/ncu_stem2b.log
+for f in gpurun_out/final_bench.err gpurun_out/ncu_step2.log gpurun_out/ncu_stem2b.log; do tail -n 2 $f; done
