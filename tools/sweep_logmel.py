@@ -1,6 +1,6 @@
 """BASELINE.json config 5: fused log-mel + QuantumConv1d stem forward, batch sweep over 30 s synthetic audio.
-One JSON line per batch size: kernel times (in-library CUDA events), utt/s of log-mel alone and of mel -> conv1 -> GELU ->
-conv2, HBM fraction of the log-mel kernels (algorithmic bytes 4*(n + 3*80*3000) per utterance).
+One JSON line per batch size: kernel times (in-library CUDA events), utt/s of log-mel alone, of mel -> conv1 -> GELU ->
+conv2 (operator by operator) and of mel -> fused stem (conv1, GELU, conv2, GELU, permute, positional embedding), HBM fraction of the log-mel kernels (algorithmic bytes 4*(n + 3*80*3000) per utterance).
 
     python tools/sweep_logmel.py [--out profiles/r1_config5_sweep.jsonl] [--max-batch 512]
 """
@@ -8,8 +8,9 @@ import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-from qasr_ijcnlp_b200 import QuantumConv1d, _lib
+from qasr_ijcnlp_b200 import QuantumConv1d, _lib, fused_stem_forward
 from qasr_ijcnlp_b200 import audio as qa
+from qasr_ijcnlp_b200.encoder import sinusoids
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
@@ -23,6 +24,7 @@ HBM = (json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0) * 1e9
 torch.manual_seed(0)
 conv1 = QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(dev)
 conv2 = QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(dev)
+pos = sinusoids(1500, 384).to(dev)
 rows = []
 B = 1
 while B <= a.max_batch:
@@ -46,12 +48,22 @@ while B <= a.max_batch:
     for _ in range(a.iters): stem()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
+    # the whole encoder front (model.py:193-198 incl. the second GELU, permute, positional embedding) through the fused stem
+    def front_fused():
+        return fused_stem_forward(conv1, conv2, qa.log_mel_spectrogram(audio), pos)
+    for _ in range(2): front_fused()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.iters): front_fused()
+    e1.record(); torch.cuda.synchronize()
+    ms_fused = e0.elapsed_time(e1) / a.iters
     t_mel = prof["logmel_stft_kernel"] + prof["logmel_finish_kernel"]
     bytes_mel = B * 4.0 * (480000 + 3 * 80 * 3000)
     row = {"config": 5, "batch": B, "logmel_stft_ms": round(prof["logmel_stft_kernel"], 4),
            "logmel_finish_ms": round(prof["logmel_finish_kernel"], 4), "conv_fwd_ms_per_launch": round(prof["qconv_fwd_kernel"], 4),
            "logmel_utt_per_s": round(B / (t_mel * 1e-3), 1), "logmel_hbm_frac": round(bytes_mel / (t_mel * 1e-3) / HBM, 4),
-           "stem_ms": round(ms, 4), "stem_utt_per_s": round(B / (ms * 1e-3), 1)}
+           "stem_ms": round(ms, 4), "stem_utt_per_s": round(B / (ms * 1e-3), 1),
+           "fused_front_ms": round(ms_fused, 4), "fused_front_utt_per_s": round(B / (ms_fused * 1e-3), 1)}
     rows.append(row)
     print(json.dumps(row), flush=True)
     del audio
