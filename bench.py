@@ -471,6 +471,14 @@ def run_b200(args):
     step_bytes = B * (3000 * 3712 + 1500 * 12288)
     step_frac = step_bytes / (ms / K * 1e-3) / 1e9 / peak
 
+    # ---- where the step goes INSIDE the replayed graph (CUDA events cannot see there): %globaltimer stamps per kernel
+    in_graph = None
+    if world == 1:
+        try:
+            in_graph = in_graph_timeline(runner, nsets, dev, B, peak)
+        except Exception as e:
+            in_graph = {"error": repr(e)[:200]}
+
     # ---- e2e through the nn.Module API with host buffers
     e2e = run_e2e(runner, B, K, Wm, world, dev, graphed=not args.e2e_eager)
 
@@ -524,13 +532,72 @@ def run_b200(args):
                 "parallelism": f"dp{world} (batch shard; forward: no collective; gradients: {collective})",
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
-            "step_roofline_frac": round(step_frac, 4), "kernels": kernels,
+            "step_roofline_frac": round(step_frac, 4), "kernels": kernels, "in_graph": in_graph,
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
             "stem_infer": stem_inf, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
         }
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def in_graph_timeline(runner, nsets, dev, B, peak, reps=20):
+    """Per-kernel critical-path times inside the replayed step graph (qw_timeline_set: every kernel records min(CTA start) /
+    max(CTA end) of %globaltimer).  delta = end of the kernel - end of its predecessor, i.e. what the kernel adds to the step
+    with the programmatic-dependent-launch overlap it really has; median over `reps` single replays.  Explains `value`; the
+    `roofline` object stays on the conservative per-launch event brackets."""
+    from qasr_ijcnlp_b200 import _lib
+
+    lib = _lib.load()
+    n0 = _lib.launch_count()
+    runner.step(0)
+    per_step = _lib.launch_count() - n0
+    torch.cuda.synchronize()
+    buf = torch.zeros(2 * per_step, dtype=torch.int64, device=dev)
+    side = torch.cuda.Stream()
+    graphs = []
+    try:
+        for s_ in range(nsets):
+            _lib.check(lib.qw_timeline_set(ctypes.c_void_p(buf.data_ptr()), per_step), "qw_timeline_set")  # slot counter -> 0
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                runner.step(s_)
+            graphs.append(g)
+        torch.cuda.synchronize()
+        for i in range(2 * nsets):
+            graphs[i % nsets].replay()
+        rows = []
+        for r in range(reps):
+            buf[0::2] = torch.iinfo(torch.int64).max
+            buf[1::2] = 0
+            torch.cuda.synchronize()
+            graphs[r % nsets].replay()
+            torch.cuda.synchronize()
+            t = buf.cpu().tolist()
+            rows.append([(t[2 * k], t[2 * k + 1]) for k in range(per_step)])
+    finally:
+        lib.qw_timeline_set(None, 0)
+    names = ["conv1.fwd", "conv2.fwd", "conv2.bwd_post(gy)", "conv2.bwd_adj", "conv2.bwd_pre", "conv2.bwd_finalize",
+             "conv1.bwd_post(gy)", "conv1.bwd_adj", "conv1.bwd_pre", "conv1.bwd_finalize"]
+    if per_step != len(names):
+        names = [f"k{k}" for k in range(per_step)]
+    algo = {"conv1.fwd": algorithmic_bytes("qconv_fwd_kernel", "conv1", B), "conv2.fwd": algorithmic_bytes("qconv_fwd_kernel", "conv2", B),
+            "conv2.bwd_post(gy)": algorithmic_bytes("qconv_bwd_post_kernel", "conv2", B),
+            "conv1.bwd_post(gy)": algorithmic_bytes("qconv_bwd_post_kernel", "conv1", B),
+            "conv2.bwd_pre": algorithmic_bytes("qconv_bwd_pre_kernel", "conv2", B),
+            "conv1.bwd_pre": algorithmic_bytes("qconv_bwd_pre_kernel", "conv1", B)}
+    out = {}
+    for k in range(per_step):
+        d = statistics.median((r[k][1] - (r[k - 1][1] if k else r[0][0])) for r in rows) / 1e3
+        ent = {"us": round(d, 2)}
+        ab = algo.get(names[k])
+        if ab and d > 0:
+            ent["frac"] = round(ab / (d * 1e-6) / 1e9 / peak, 4)
+        out[names[k]] = ent
+    total = statistics.median(max(e for _, e in r) - r[0][0] for r in rows) / 1e3
+    return {"step_us": round(total, 2), "kernels": out,
+            "how": "median of %d single graph replays; us a kernel adds to the step = its last CTA end - its predecessor's last CTA "
+                   "end (%%globaltimer); frac = algorithmic bytes / that time / HBM peak" % reps}
 
 
 def runner_bytes(B):
