@@ -106,7 +106,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // QW_PDL: 0 = never, 2 = always, unset / 1 = when the caller says the launch is latency-dominated (`small`): measured on B200,
-// PDL gains 4 % on the batch-16 stem step (5 tiles per CTA) and loses 4 % at batch 64 (20 tiles per CTA).
+// PDL gains 4 % on the batch-16 stem step (5 tiles per CTA), 2.8 % at batch 64 (20 tiles) and loses 2.3 % at batch 256 (80 tiles).
 int pdl_mode();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(bool small, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

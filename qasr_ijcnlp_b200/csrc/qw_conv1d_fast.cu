@@ -965,7 +965,9 @@ FastPlan make_fast_plan(const ConvDims& d) {
     p.gridF = p.num_tiles < per_sm * sms ? p.num_tiles : per_sm * sms;
   }
   p.gridGy = p.num_tiles < 2 * sms ? p.num_tiles : 2 * sms;
-  p.small = p.num_tiles <= 6 * 2 * sms;   // <= 6 tiles per CTA: launch / ramp latency matters more than steady-state streaming
+  // programmatic dependent launch while a CTA sees <= 24 tiles: launch / ramp latency still matters (measured with the pre-wait
+  // work of this round: batch 16 / 32 / 64 gain 4 / 2.5 / 2.8 %, batch 256 -- 80 tiles per CTA -- loses 2.3 %)
+  p.small = p.num_tiles <= 24 * 2 * sms;
   p.PA1 = gy_plen(d.O);
   const long long W = (long long)d.B * d.Lout;
   {
