@@ -1,4 +1,5 @@
-import json, sys
+import json, signal, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # quiet under `| head`
 d = json.load(open(sys.argv[1]))
 print("value %.4g %s  ms/step %.5f  step_frac %.4f  e2e %.4g (%.4f ms)" % (d["value"], d["unit"], d["ms_per_step"], d["step_roofline_frac"], d["e2e"]["value"], d["e2e"]["ms_per_step"]))
 print("roofline", {k: d["roofline"][k] for k in ("kernel", "achieved", "frac", "kernel_ms", "kernel_share_of_step", "traffic")})
