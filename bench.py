@@ -301,6 +301,8 @@ def algorithmic_bytes(kernel, layer, B):
         return W * y_per_win  # reads gy once
     if kernel == "qconv_bwd_pre_kernel":
         return W * x_per_win * (2.0 if cfg["need_gx"] else 1.0)  # re-read x (+ write grad_x)
+    if kernel == "qconv_bwd_fused_kernel":
+        return W * (y_per_win + x_per_win * (2.0 if cfg["need_gx"] else 1.0))  # the whole backward of the layer
     return 0.0
 
 
@@ -541,6 +543,29 @@ def run_b200(args):
         torch.distributed.destroy_process_group()
 
 
+def step_kernel_names(runner):
+    """Kernel labels of one step in launch order, from the launch count of each C-ABI call (a layer's backward is either
+    gy / adjoint / pre_conv^T / finalize or, for a small-batch data layer, fused / finalize)."""
+    from qasr_ijcnlp_b200 import _lib
+
+    names = []
+    for layer, what in (("conv1", "fwd"), ("conv2", "fwd"), ("conv2", "bwd"), ("conv1", "bwd")):
+        n0 = _lib.launch_count()
+        (runner.fwd if what == "fwd" else runner.bwd)(layer, 0)
+        n = _lib.launch_count() - n0
+        if what == "fwd":
+            kinds = ["fwd"] * n
+        elif n == 4:
+            kinds = ["bwd_post(gy)", "bwd_adj", "bwd_pre", "bwd_finalize"]
+        elif n == 2:
+            kinds = ["bwd_fused", "bwd_finalize"]
+        else:
+            kinds = [f"bwd_k{i}" for i in range(n)]
+        names += [f"{layer}.{k}" for k in kinds]
+    torch.cuda.synchronize()
+    return names
+
+
 def in_graph_timeline(runner, nsets, dev, B, peak, reps=20):
     """Per-kernel critical-path times inside the replayed step graph (qw_timeline_set: every kernel records min(CTA start) /
     max(CTA end) of %globaltimer).  delta = end of the kernel - end of its predecessor, i.e. what the kernel adds to the step
@@ -577,15 +602,15 @@ def in_graph_timeline(runner, nsets, dev, B, peak, reps=20):
             rows.append([(t[2 * k], t[2 * k + 1]) for k in range(per_step)])
     finally:
         lib.qw_timeline_set(None, 0)
-    names = ["conv1.fwd", "conv2.fwd", "conv2.bwd_post(gy)", "conv2.bwd_adj", "conv2.bwd_pre", "conv2.bwd_finalize",
-             "conv1.bwd_post(gy)", "conv1.bwd_adj", "conv1.bwd_pre", "conv1.bwd_finalize"]
+    names = step_kernel_names(runner)
     if per_step != len(names):
         names = [f"k{k}" for k in range(per_step)]
-    algo = {"conv1.fwd": algorithmic_bytes("qconv_fwd_kernel", "conv1", B), "conv2.fwd": algorithmic_bytes("qconv_fwd_kernel", "conv2", B),
-            "conv2.bwd_post(gy)": algorithmic_bytes("qconv_bwd_post_kernel", "conv2", B),
-            "conv1.bwd_post(gy)": algorithmic_bytes("qconv_bwd_post_kernel", "conv1", B),
-            "conv2.bwd_pre": algorithmic_bytes("qconv_bwd_pre_kernel", "conv2", B),
-            "conv1.bwd_pre": algorithmic_bytes("qconv_bwd_pre_kernel", "conv1", B)}
+    algo = {}
+    for layer in ("conv1", "conv2"):
+        algo[f"{layer}.fwd"] = algorithmic_bytes("qconv_fwd_kernel", layer, B)
+        algo[f"{layer}.bwd_post(gy)"] = algorithmic_bytes("qconv_bwd_post_kernel", layer, B)
+        algo[f"{layer}.bwd_pre"] = algorithmic_bytes("qconv_bwd_pre_kernel", layer, B)
+        algo[f"{layer}.bwd_fused"] = algorithmic_bytes("qconv_bwd_fused_kernel", layer, B)
     out = {}
     for k in range(per_step):
         d = statistics.median((r[k][1] - (r[k - 1][1] if k else r[0][0])) for r in rows) / 1e3

@@ -31,6 +31,9 @@ extern "C" {
 
 /* ABI version / build info. */
 int qw_abi_version(void);
+/* Hash of the sources (csrc/, include/, compile flags) this library was built from; the Python loader compares it with the tree
+ * next to it so that a stale prebuilt .so is rebuilt (or refused) instead of silently running old kernels. */
+const char* qw_build_stamp(void);
 const char* qw_last_error(void);
 /* Number of kernels this library has launched from the calling process since load (for bench gpu_launches). */
 long long qw_launch_count(void);
@@ -47,6 +50,11 @@ int qw_timeline_set(unsigned long long* dev_buf, int nslots);
 /* 1 (default): use the TMA fast path when the shape qualifies (fp32, q=4, K=3, stride 1|2, L%4==0, L_out%4==0,
  * O%4==0, O<=576, 16-byte aligned tensors; the forward additionally needs padding==1); 0: always use the generic kernels (used by the parity tests). */
 void qw_set_fast_path(int enable);
+/* Kernel-selection switches (A/B experiments and parity tests ONLY: they choose between equivalent kernels and are not part of
+ * the reference-facing contract).  name = "FAST_PATH", "GY_MMA", "BWD_FUSED", "FWD_MMA", ... (csrc/qw_common.cuh, enum Option); each
+ * is initialised from the environment variable QW_<name> on first use.  Process-global and NOT re-entrant: do not change an
+ * option while another thread is inside a qw_* call.  Returns 0, or -1 for an unknown name. */
+int qw_set_option(const char* name, int value);
 
 /* ---- QuantumConv1d.forward  (quantum_whisper.py:95-128; circuit :64-85; params :58-59,88)
  * x (B,C,L) -> y (B,O,L_out), L_out = (L+2P-K)/S+1 (:103).  w_pre (q, C*K) with column c*K+k (:58,:111),

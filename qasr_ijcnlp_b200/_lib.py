@@ -25,6 +25,7 @@ _CONV_DIMS = [_I] * 10  # B C L K S P O q n_layers embedding
 
 _SIGNATURES = {
     "qw_abi_version": (_I, []),
+    "qw_build_stamp": (ctypes.c_char_p, []),
     "qw_last_error": (ctypes.c_char_p, []),
     "qw_launch_count": (_LL, []),
     "qw_profile_enable": (None, [_I]),
@@ -32,6 +33,7 @@ _SIGNATURES = {
     "qw_kernel_name": (ctypes.c_char_p, [_I]),
     "qw_timeline_set": (_I, [_P, _I]),
     "qw_set_fast_path": (None, [_I]),
+    "qw_set_option": (_I, [ctypes.c_char_p, _I]),
     "qw_conv1d_forward": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_forward_f64": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_workspace_bytes": (_SZ, [_I] * 10),
@@ -77,6 +79,7 @@ def load(build_if_missing: bool = True):
 
             _build.build()
         lib = ctypes.CDLL(LIB_PATH)
+        lib = _refresh_if_stale(lib, build_if_missing)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export it
             fn.restype = res
@@ -85,6 +88,41 @@ def load(build_if_missing: bool = True):
             raise QwError("libqw_b200.so ABI version mismatch; rebuild with `python -m qasr_ijcnlp_b200.build --force`")
         _lib = lib
         return lib
+
+
+def _refresh_if_stale(lib, may_build: bool):
+    """The .so is git-ignored but travels with the tree: make sure it was built from THESE sources.  A library
+    whose embedded source hash differs from the tree is rebuilt in-tree; if that is impossible the load fails loudly."""
+    from . import build as _build
+
+    want = _build._source_hash()
+    try:
+        fn = lib.qw_build_stamp
+        fn.restype = ctypes.c_char_p
+        have = fn().decode()
+    except AttributeError:
+        have = "missing"
+    if have == want or os.environ.get("QW_ALLOW_STALE_LIB") == "1":
+        return lib
+    if not may_build:
+        raise QwError(f"{LIB_PATH} was built from other sources (stamp {have}, tree {want}); run `python -m qasr_ijcnlp_b200.build`")
+    # dlclose is not reliable through ctypes: build under a fresh name is not needed -- the process has not called into the old
+    # mapping yet, so rebuild in place and map the new file
+    handle = lib._handle
+    del lib
+    try:
+        import _ctypes
+
+        _ctypes.dlclose(handle)
+    except Exception:
+        pass
+    _build.build(force=False)
+    lib = ctypes.CDLL(LIB_PATH)
+    fn = lib.qw_build_stamp
+    fn.restype = ctypes.c_char_p
+    if fn().decode() != want:
+        raise QwError(f"{LIB_PATH} is stale (stamp {fn().decode()}, tree {want}) and could not be rebuilt")
+    return lib
 
 
 def check(status: int, what: str) -> None:

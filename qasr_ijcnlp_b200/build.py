@@ -36,7 +36,7 @@ def _nvcc() -> str:
 
 def _units():
     """(object name, source, extra flags)"""
-    units = [("qw_api.o", "qw_api.cu", []), ("qw_conv1d.o", "qw_conv1d.cu", []), ("qw_logmel.o", "qw_logmel.cu", []),
+    units = [("qw_api.o", "qw_api.cu", [f'-DQW_BUILD_STAMP="{_source_hash()}"']), ("qw_conv1d.o", "qw_conv1d.cu", []), ("qw_logmel.o", "qw_logmel.cu", []),
              ("qw_conv1d_fast.o", "qw_conv1d_fast.cu", []), ("qw_conv1d_general.o", "qw_conv1d_general.cu", []), ("qw_dp.o", "qw_dp.cu", []),
              ("qw_stem.o", "qw_stem.cu", [])]
     for tname, t in (("f32", "float"), ("f64", "double")):
@@ -62,6 +62,26 @@ def _source_hash() -> str:
     return h.hexdigest()[:16]
 
 
+def _unit_hash(src: str, extra) -> str:
+    """Hash of what one object depends on: its own .cu, every header of the tree, the flags."""
+    h = hashlib.sha256()
+    deps = [os.path.join(CSRC, src)]
+    deps += sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    deps += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + list(extra)).encode())
+    return h.hexdigest()[:16]
+
+
+def is_stale() -> bool:
+    """True when libqw_b200.so does not match the sources next to it (or is missing)."""
+    stamp = os.path.join(BUILD, "stamp.txt")
+    return not (os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == _source_hash())
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp.txt")
@@ -73,11 +93,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(u):
         obj, src, extra = u
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+        out = os.path.join(BUILD, obj)
+        hfile = out + ".hash"
+        uh = _unit_hash(src, extra)
+        if not force and not verbose and os.path.exists(out) and os.path.exists(hfile) and open(hfile).read().strip() == uh:
+            return obj, 0, ""  # object is current: only the units whose sources changed recompile
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", out]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            with open(hfile, "w") as fh:
+                fh.write(uh)
         return obj, r.returncode, r.stdout + r.stderr
 
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/qw.h"
 #include "qw_common.cuh"
@@ -26,6 +27,39 @@ int pdl_mode() {
     return (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;
   }();
   return v;
+}
+
+// ---- option table
+struct OptDef {
+  const char* name;
+  int dflt;
+};
+static const OptDef kOptDefs[kOptCount] = {{"FAST_PATH", 1}, {"GY_MMA", 1}, {"BWD_FUSED", 1}, {"FWD_MMA", 1}, {"FWD_ETMA", 1}, {"FIN_EARLY", 1},
+                                           {"ADJ_TRIG", 1}, {"PRE_EX", 1}, {"ADJ_SPEC", 1}, {"PRE_CTAS", 4}, {"GY_WARPS", 0}};
+static std::atomic<int> g_opt[kOptCount];
+static std::once_flag g_opt_once;
+static void opt_init() {
+  for (int i = 0; i < kOptCount; ++i) {
+    char env[64];
+    snprintf(env, sizeof(env), "QW_%s", kOptDefs[i].name);
+    const char* e = getenv(env);
+    g_opt[i].store(e ? atoi(e) : kOptDefs[i].dflt, std::memory_order_relaxed);
+  }
+}
+int option(Option o) {
+  std::call_once(g_opt_once, opt_init);
+  return g_opt[o].load(std::memory_order_relaxed);
+}
+int set_option(const char* name, int value) {
+  std::call_once(g_opt_once, opt_init);
+  if (!name) return -1;
+  if (strncmp(name, "QW_", 3) == 0) name += 3;
+  for (int i = 0; i < kOptCount; ++i)
+    if (strcmp(name, kOptDefs[i].name) == 0) {
+      g_opt[i].store(value, std::memory_order_relaxed);
+      return 0;
+    }
+  return -1;
 }
 
 // ---- debug timeline: caller-owned device buffer of 2 x nslots u64 (start, end) pairs
@@ -67,7 +101,17 @@ void profile_end(int id, cudaStream_t st) {
 }  // namespace qw
 
 extern "C" {
+#ifndef QW_BUILD_STAMP
+#define QW_BUILD_STAMP "unstamped"
+#endif
+const char* qw_build_stamp(void) { return QW_BUILD_STAMP; }
 int qw_abi_version(void) { return QW_ABI_VERSION; }
+int qw_set_option(const char* name, int value) {
+  const int r = qw::set_option(name, value);
+  if (r != 0) qw::set_error("qw_set_option: unknown option '%s'", name ? name : "(null)");
+  return r;
+}
+void qw_set_fast_path(int enable) { qw::set_option("FAST_PATH", enable != 0); }
 const char* qw_last_error(void) { return qw::g_err; }
 long long qw_launch_count(void) { return qw::g_launches.load(std::memory_order_relaxed); }
 
@@ -109,7 +153,7 @@ int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset
 const char* qw_kernel_name(int kernel_id) {
   static const char* names[] = {"qconv_fwd_kernel", "qconv_bwd_post_kernel", "qconv_bwd_pre_kernel", "qconv_bwd_finalize_kernel",
                                 "circuit_fwd_kernel", "circuit_bwd_kernel", "circuit_finalize_kernel", "logmel_stft_kernel",
-                                "logmel_finish_kernel", "qconv_bwd_adj_kernel", "logmel_prep_kernel", "grads_allreduce_p2p_kernel", "stem2_kernel"};
+                                "logmel_finish_kernel", "qconv_bwd_adj_kernel", "logmel_prep_kernel", "grads_allreduce_p2p_kernel", "stem2_kernel", "qconv_bwd_fused_kernel"};
   return (kernel_id >= 0 && kernel_id < qw::kKCount) ? names[kernel_id] : "";
 }
 }

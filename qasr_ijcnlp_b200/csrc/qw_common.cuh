@@ -7,13 +7,33 @@
 
 namespace qw {
 
+// ---- kernel-selection options (A/B switches).  Process-global, read from the environment (QW_<NAME>) on first use and settable through
+// qw_set_option(): TEST / EXPERIMENT ONLY -- they pick between equivalent kernels, are not part of the reference-facing contract, and
+// changing them while another thread is inside a qw_* call is not supported.
+enum Option {
+  kOptFastPath = 0,  // FAST_PATH  1: TMA fast path when the shape qualifies; 0: generic kernels
+  kOptGyMma,         // GY_MMA     1: gy pass on the tensor pipe (mma.sync 3xTF32); 0: FFMA form
+  kOptBwdFused,      // BWD_FUSED  1: one backward kernel for small-batch data layers; 0: gy / adjoint / pre_conv^T kernels
+  kOptFwdMma,        // FWD_MMA    1: post_conv of the forward kernel on the tensor pipe; 0: FFMA form
+  kOptFwdEtma,       // FWD_ETMA   1: forward requests its first x tiles before staging parameters
+  kOptFinEarly,      // FIN_EARLY  1: finalize segments 1-2 run before the dependency wait (split backward only)
+  kOptAdjTrig,       // ADJ_TRIG   1: adjoint kernel triggers its dependent right after its wait
+  kOptPreEx,         // PRE_EX     1: pre_conv^T requests its first x tiles before the dependency wait
+  kOptAdjSpec,       // ADJ_SPEC   1: single-layer specialisation of the adjoint kernel
+  kOptPreCtas,       // PRE_CTAS   CTAs per SM of the pre_conv^T kernel (default 4)
+  kOptGyWarps,       // GY_WARPS   12: wide FFMA gy kernel (only with GY_MMA=0)
+  kOptCount
+};
+int option(Option o);
+int set_option(const char* name, int value);  // 0, or -1 for an unknown name
+
 // ---- error text (thread local) and launch counter
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
 
 // Optional per-kernel CUDA-event timing (qw_profile_enable): KernelTimer brackets one launch on `st`.
-enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKGradAllReduce, kKStem2, kKCount };
+enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKGradAllReduce, kKStem2, kKBwdFused, kKCount };
 bool profiling_enabled();
 void profile_begin(int id, cudaStream_t st);
 void profile_end(int id, cudaStream_t st);

@@ -196,7 +196,6 @@ using qw::ConvDims;
 
 extern "C" {
 
-void qw_set_fast_path(int enable) { qw::set_fast_path(enable != 0); }
 
 int qw_conv1d_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
                       const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O, int q,

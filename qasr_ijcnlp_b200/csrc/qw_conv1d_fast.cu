@@ -9,9 +9,9 @@
 //   fast_fwd_kernel<S,RC>   x tile ring (3-D tensor map, zero padding by OOB fill) -> pre_conv partials with a
 //                           "4 rows x 8 lanes x 4 adjacent windows" lane layout -> circuit (thread/window) ->
 //                           post_conv with 128-bit coalesced stores.
-//   fast_bwd_gy_kernel<RPT> streams gy once (SWIZZLE_128B tiles, conflict-free in both orientations):
-//                           gout = post_conv^T gy (time-major lanes) and grad post_conv.{weight,bias}
-//                           (channel-major lanes, register accumulators for the whole CTA lifetime).
+//   fast_bwd_gy3_kernel     streams gy once (SWIZZLE_128B tiles): gout = post_conv^T gy and grad post_conv.{weight,bias} on the
+//                           tensor pipe (mma.sync 3xTF32); its FUSED form carries a small-batch data layer through the adjoint
+//                           and pre_conv^T as well.  fast_bwd_gy2_kernel is the FFMA form (A/B switch GY_MMA=0).
 //   fast_bwd_adj_kernel     adjoint differentiation of the circuit, one thread per window -> gpre (halo-padded).
 //   fast_bwd_pre_kernel<S,PAR,GX>  x tile ring in, grad_x written in place and stored back by TMA; lanes along
 //                           channels hold pre_conv weights and their gradient accumulators in registers.
@@ -26,10 +26,7 @@ namespace qw {
 
 constexpr int FQ = 4;     // n_qubits on the fast path
 constexpr int FTW = 32;   // windows a tile's shared-memory boxes cover (forward, gy streaming)
-// Tiles ADVANCE by a run-time stride tw <= FTW (a multiple of 4; default FTW, QW_TW=16..28 for experiments).  The idea was to
-// even out the rounds of the persistent grid (batch 16: 1 504 / 752 tiles of 32 windows for 296 CTAs = 5.08 / 2.54 tiles per
-// CTA, i.e. 6 / 3 rounds of which the last is nearly empty; a stride of 28 makes 6 / 3 rounds of 28 windows).  Measured: no gain
-// (see make_fast_plan).  The TMA boxes keep their size (the columns past tw are the neighbour tile's), lanes past tw do not store.
+// (The kernels still carry a run-time tile stride `tw`; it is always FTW -- see make_fast_plan.)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -493,6 +490,424 @@ __global__ void __launch_bounds__(32 * NW, 2) fast_bwd_gy2_kernel(const __grid_c
   tl_end(a.tl);
 }
 
+// =============================================================================================== backward: gy streaming on the tensor pipe
+// fast_bwd_gy2_kernel is bound by instruction issue, not by HBM: 7 500 warp-instructions per 48 KB tile (ncu, round 1: FFMA 40 %,
+// issue slots 41 % busy at 3 warps per scheduler), i.e. 3.2 us per round of 296 tiles against 2.2 us of HBM time.  Both of its
+// contractions are rank-4 products of the streamed tile with a small matrix:
+//     grad post_conv.weight[o][j] += sum_w gy[o][w] * <Z_j>[w]        (K = windows,  N = 4)
+//     gout[w][j]                   = sum_o gy[o][w] * W_post[o][j]    (K = channels, N = 4)
+// so they fit the warp-level tensor-core instruction mma.sync.m16n8k8 (TF32 in, fp32 accumulate; SASS HMMA.1688.F32.TF32,
+// measured 8.7 clk per sub-partition on B200, tools/probe/mma_probe.cu = 4.6 x the FFMA pipe per MAC and ONE issue slot per
+// 1 024 MACs) with the N = 8 columns holding [hi | lo] of the small matrix: a "3 x TF32" product.  The streamed operand is
+// split in registers, v = hi + lo with hi = v & 0xffffe000 (exact) and lo = v - hi (exact in fp32, <= 13 significant bits, the
+// tensor core keeps 11 of them), and both halves are multiplied with [hi | lo]: the dropped terms are 2^-21 relative, the
+// accumulation is fp32 -- inside the 1e-5 budget (tests: same tolerances as the FFMA kernel).  Per 128 elements of the tile
+// and contraction: 2 LDS.64 + 8 split ops + 2-4 MMA instead of ~46 LDS/FFMA/FADD: ~3 000 instructions per tile.
+//
+// Fragment <-> tile mapping (g = lane >> 2, t = lane & 3; the tile is SWIZZLE_128B, rows = channels, 32 windows per row):
+//   weight gradient (computed transposed, the streamed tile is the B operand): B[k][n] = gy[8 ob + n][w(k)],
+//                    w(t) = 4 kb + 2 (t & 1) + 16 (t >> 1), w(t + 4) = w(t) + 1, so b0/b1 are ONE conflict-free LDS.64 and need no
+//                    register shuffling; A[m][k] = rows 0-3 hi(<Z_m>[w(k)]), rows 4-7 lo(<Z_{m-4}>[w(k)]), row 8 = 1 (the bias
+//                    gradient rides along for free), rows 9-15 = 0.
+//   gout:            A[m][k] = gy[8 kb + r(k)][16 mb + w(m)], r(t) = 2 t, r(t + 4) = 2 t + 1, w(g) = 2 g, w(g + 8) = 2 g + 1
+//                    (again two conflict-free LDS.64); B[k][n] = [hi | lo] of W_post[8 kb + r(k)][n & 3], held in registers for the
+//                    CTA lifetime (each warp owns 4 of the 24 channel blocks of a stage; partial sums of the 6 warps meet in
+//                    shared memory, double-buffered, one __syncthreads per tile).
+constexpr int kGy3Warps = 6, kGy3Threads = 32 * kGy3Warps, kGy3Rows = 32 * kGy3Warps, kGy3Stages = 3;
+__host__ __device__ constexpr size_t fast_gy3_smem_bytes() {
+  return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 + 2 * kGy3Stages * 8;
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
+// ---- fused small-batch form (FUSED = true): gy pass + adjoint + pre_conv^T of a data layer (no grad_x) in ONE kernel.
+// At batch 16 a CTA of the persistent grid sees only 5-6 tiles, the three backward kernels of a layer run 5-20 us each, and a
+// zero-compute TMA streaming kernel of the same footprint needs ~15 us for the 74 MB of gy (tools/probe/stream_probe.cu): launch
+// ramp, the ragged last round and the drain of every kernel boundary cost as much as the bytes.  Here every CTA owns a CONTIGUOUS
+// range of <= kFbMaxTiles tiles and carries them through all three phases on its own, so nothing waits for a grid-wide boundary:
+//   phase 1  the tensor-pipe gy pass above; gout stays in shared memory (never written to HBM), <Z> and pre_conv outputs of the
+//            tile's windows arrive by TMA next to its first stage;
+//   phase 2  adjoint differentiation, one window per thread over ALL warps at once (the round-1 fused attempt specialised two
+//            warps per CTA and serialised ~3 000 dependent instructions per tile on them); gate-gradient matrices are reduced
+//            with a transposing warp reduction (31 shuffles for 32 values) -- one window per thread needs no accumulators;
+//            the x tiles of phase 3 are requested before it starts and land while it runs;
+//   phase 3  grad pre_conv.weight[j][c][k] += gpre[w][j] x[c][w + k - 1]: threads = (c, k) pairs, register accumulators.
+// CTAs that own one tile fewer than their neighbours run phases 2-3 while the others still stream.  One partial row per CTA
+// and phase, reduced by the finalize kernel as before.
+constexpr int kFbMaxTiles = 6;   // 6 tiles x 32 windows = one window per thread in phase 2
+constexpr int kFbXW = 40;        // x tile columns (as the forward kernel: tap k of local window w = column 3 + w + k)
+constexpr int kFbXRows = 96;     // x tile rows (channels; C <= 96)
+__host__ __device__ constexpr size_t fast_gy3_fused_smem_bytes() {
+  return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)4 * kFbMaxTiles * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 +
+         (size_t)FQ * kGateStride * 4 + (size_t)kGy3Warps * 40 * 4 + (2 * kGy3Stages + kGy3Stages) * 8;
+}
+struct FastGy3Args {
+  const float *w_post, *qw;
+  float *gout, *part;       // plain: gout [B*Lout][4]; part: [grid][PA1]
+  float *part2, *part3;     // fused: [grid][PA2], [grid][PB]
+  int B, C, O, Lout, tiles_per_utt, num_tiles, PA1, PA2, PB;
+  unsigned long long* tl;
+};
+struct RegGateAcc {
+  float m[FQ][8];
+  __device__ __forceinline__ void set_layer(int) {}
+  __device__ __forceinline__ void add(int wire, const float (&mm)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[wire][e] += mm[e];
+  }
+};
+// v[32] per lane -> lane L returns sum over the warp of v[L]  (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < ofs; ++i) {
+      const float send = up ? v[i] : v[i + ofs];
+      const float keep = up ? v[i + ofs] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  return v[0];
+}
+
+template <int NHALF, bool FUSED>
+__global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __grid_constant__ CUtensorMap tm_gy,
+                                                                       const __grid_constant__ CUtensorMap tm_qout,
+                                                                       const __grid_constant__ CUtensorMap tm_pre,
+                                                                       const __grid_constant__ CUtensorMap tm_x, const FastGy3Args a) {
+  constexpr int SE = kGy3Rows * 32;  // floats per stage
+  constexpr int NQT = FUSED ? kFbMaxTiles : 3;  // <Z> tiles kept (fused: all of the CTA's tiles)
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* base = align1024(smem_dyn);
+  float* stages = reinterpret_cast<float*>(base);                      // [kGy3Stages][192][32] swizzled
+  float* outs = stages + (size_t)kGy3Stages * SE;                      // [NQT][32][4]   <Z> of the tiles' windows
+  float* pre_s = outs + NQT * FTW * FQ;                                // fused: [kFbMaxTiles][32][4] pre_conv outputs
+  float* gout_s = pre_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);        // fused: [kFbMaxTiles][32][4]
+  float* gpre_s = gout_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);       // fused: [kFbMaxTiles][32][4]
+  float* gred = gpre_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);         // [2][6 warps][32 windows][8]
+  float* gates = gred + 2 * kGy3Warps * FTW * 8;                       // fused: [4][16]
+  float* red2 = gates + (FUSED ? FQ * kGateStride : 0);                // fused: [6 warps][40]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red2 + (FUSED ? kGy3Warps * 40 : 0));
+  uint64_t* empty = full + kGy3Stages;
+  uint64_t* xfull = empty + kGy3Stages;                                // fused: [kGy3Stages] x tiles of phase 3
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  tl_begin(a.tl);
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_gy);
+    tma_prefetch_desc(&tm_qout);
+    if (FUSED) {
+      tma_prefetch_desc(&tm_pre);
+      tma_prefetch_desc(&tm_x);
+    }
+    for (int s = 0; s < kGy3Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGy3Warps);
+      if (FUSED) mbar_init(&xfull[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (FUSED && tid < FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+  // B fragments of the gout contraction (parameters: readable before the dependency wait)
+  uint32_t bw[NHALF][4][2];
+#pragma unroll
+  for (int h = 0; h < NHALF; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int o = h * kGy3Rows + (warp * 4 + i) * 8 + 2 * t + e;
+        const float v = (o < a.O) ? __ldg(a.w_post + (size_t)o * FQ + (g & 3)) : 0.f;
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        bw[h][i][e] = g < 4 ? hi : lo;
+      }
+  // lane offsets (floats) inside a stage
+  int off1[4], off2[2][2];
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) off1[kb] = g * 32 + (((kb + 4 * (t >> 1)) ^ g) << 2) + 2 * (t & 1);
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) off2[m][e] = (2 * t + e) * 32 + (((4 * m + (g >> 1)) ^ (2 * t + e)) << 2) + 2 * (g & 1);
+  __syncthreads();
+  pdl_wait();
+  pdl_launch();
+
+  // plain: round-robin tiles (neighbouring CTAs stream neighbouring row segments); fused: a contiguous range per CTA
+  int tile0, tstep, my_tiles;
+  if (FUSED) {
+    tile0 = (int)(((long long)blockIdx.x * a.num_tiles) / gridDim.x);
+    my_tiles = (int)(((long long)(blockIdx.x + 1) * a.num_tiles) / gridDim.x) - tile0;
+    tstep = 1;
+  } else {
+    tile0 = blockIdx.x;
+    tstep = gridDim.x;
+    my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  }
+  const int total_stages = my_tiles * NHALF;
+  float d1[NHALF * 4][4];  // [8-channel block][fragment]: rows = hi/lo of <Z_j> (and the ones row), columns = channels
+#pragma unroll
+  for (int m = 0; m < NHALF * 4; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d1[m][j] = 0.f;
+  const uint32_t one_g0 = (g == 0) ? 0x3f800000u : 0u;  // A rows 8..15: row 8 (lanes g == 0) = 1.0f
+
+  auto issue = [&](int gs) {
+    const int n = gs / NHALF, h = gs - n * NHALF;
+    const int tile = tile0 + n * tstep;
+    const int b = tile / a.tiles_per_utt;
+    const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+    const int s = gs % kGy3Stages;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(SE + (h == 0 ? (FUSED ? 2 : 1) * FTW * FQ : 0)) * 4);
+#pragma unroll
+    for (int bx = 0; bx < kGy3Rows / 64; ++bx)
+      tma_load_3d(stages + (size_t)s * SE + bx * 64 * 32, &tm_gy, i0, h * kGy3Rows + bx * 64, b, &full[s]);
+    if (h == 0) {
+      tma_load_3d(outs + (n % NQT) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
+      if (FUSED) tma_load_3d(pre_s + n * FTW * FQ, &tm_pre, 0, i0, b, &full[s]);
+    }
+  };
+  if (tid == 0)
+    for (int gs = 0; gs < kGy3Stages - 1 && gs < total_stages; ++gs) issue(gs);
+
+  int gs = 0;
+  for (int n = 0; n < my_tiles; ++n) {
+    float d2[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d2[m][j] = 0.f;
+    uint32_t aq[4][4];
+    const float* os = outs + (n % NQT) * FTW * FQ;
+#pragma unroll
+    for (int h = 0; h < NHALF; ++h, ++gs) {
+      if (tid == 0) {
+        const int gn = gs + kGy3Stages - 1;
+        if (gn < total_stages) {
+          if (gn >= kGy3Stages) mbar_wait(&empty[gn % kGy3Stages], ((gn / kGy3Stages) - 1) & 1);
+          issue(gn);
+        }
+      }
+      const int s = gs % kGy3Stages;
+      mbar_wait(&full[s], (gs / kGy3Stages) & 1);
+      const float* gsm = stages + (size_t)s * SE;
+      if (h == 0) {
+        // A fragments of the weight-gradient contraction from this tile's <Z> (they arrived with the tile's first stage)
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const int w0 = 4 * kb + 2 * (t & 1) + 16 * (t >> 1);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            uint32_t hi, lo;
+            split_tf32(os[(w0 + e) * FQ + (g & 3)], hi, lo);
+            aq[kb][2 * e] = g < 4 ? hi : lo;
+            aq[kb][2 * e + 1] = one_g0;
+          }
+        }
+      }
+      // ---- grad post_conv.{weight,bias}: this warp's four 8-channel blocks of the stage, K = the tile's 32 windows
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* rp = gsm + (warp * 4 + i) * 256;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const float2 u = ld2(rp + off1[kb]);
+          uint32_t bh[2], bl[2];
+          split_tf32(u.x, bh[0], bl[0]);
+          split_tf32(u.y, bh[1], bl[1]);
+          mma_tf32(d1[h * 4 + i], aq[kb], bh[0], bh[1]);
+          mma_tf32(d1[h * 4 + i], aq[kb], bl[0], bl[1]);
+        }
+      }
+      // ---- gout partials: this warp's four 8-channel blocks of the stage, both 16-window halves of the tile
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* rp = gsm + (warp * 4 + i) * 256;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float2 u = ld2(rp + off2[m][0]), v = ld2(rp + off2[m][1]);
+          uint32_t ah[4], al[4];
+          split_tf32(u.x, ah[0], al[0]);
+          split_tf32(u.y, ah[1], al[1]);
+          split_tf32(v.x, ah[2], al[2]);
+          split_tf32(v.y, ah[3], al[3]);
+          mma_tf32(d2[m], ah, bw[h][i][0], bw[h][i][1]);
+          mma_tf32(d2[m], al, bw[h][i][0], bw[h][i][1]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // ---- the 6 warps' partial gout rows meet in shared memory; warp n % 6 sums and stores the tile's gout.  Double-buffered:
+    // a warp can only be writing buffer (n + 2) & 1 after the barrier of tile n + 1, which the summing warp of tile n reaches
+    // after its reads.
+    float* gr = gred + (size_t)(n & 1) * kGy3Warps * FTW * 8 + (size_t)warp * FTW * 8;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      st2(gr + (16 * m + 2 * g) * 8 + 2 * t, make_float2(d2[m][0], d2[m][1]));
+      st2(gr + (16 * m + 2 * g + 1) * 8 + 2 * t, make_float2(d2[m][2], d2[m][3]));
+    }
+    __syncthreads();
+    if (warp == n % kGy3Warps) {
+      const float* gq = gred + (size_t)(n & 1) * kGy3Warps * FTW * 8 + (size_t)lane * 8;
+      float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < kGy3Warps; ++w) {
+        const float4 p0 = ld4(gq + (size_t)w * FTW * 8), p1 = ld4(gq + (size_t)w * FTW * 8 + 4);
+        sacc.x += p0.x + p1.x; sacc.y += p0.y + p1.y; sacc.z += p0.z + p1.z; sacc.w += p0.w + p1.w;
+      }
+      if (FUSED) {
+        st4(gout_s + ((size_t)n * FTW + lane) * FQ, sacc);
+      } else {
+        const int tile = tile0 + n * tstep;
+        const int b = tile / a.tiles_per_utt;
+        const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+        if (i < a.Lout) st4(a.gout + ((size_t)b * a.Lout + i) * FQ, sacc);
+      }
+    }
+  }
+  // ---- partial row of this CTA: [O*4 grad post_conv.weight][O grad post_conv.bias][pad]
+  {
+    float* prow = a.part + (size_t)blockIdx.x * a.PA1;
+#pragma unroll
+    for (int m = 0; m < NHALF * 4; ++m) {
+      const int h = m >> 2, i = m & 3;
+      const int o = h * kGy3Rows + (warp * 4 + i) * 8 + 2 * t;  // this lane's two channels: o, o + 1
+      // rows j (hi half of <Z_j>) and j + 4 (lo half) live in lanes g and g + 4
+      const float c0 = d1[m][0] + __shfl_xor_sync(0xffffffffu, d1[m][0], 16);
+      const float c1 = d1[m][1] + __shfl_xor_sync(0xffffffffu, d1[m][1], 16);
+      if (g < 4) {
+        if (o < a.O) prow[(size_t)o * FQ + g] = c0;
+        if (o + 1 < a.O) prow[(size_t)(o + 1) * FQ + g] = c1;
+      }
+      if (g == 0) {  // row 8 = the ones row: grad post_conv.bias
+        if (o < a.O) prow[a.O * FQ + o] = d1[m][2];
+        if (o + 1 < a.O) prow[a.O * FQ + o + 1] = d1[m][3];
+      }
+    }
+    for (int e = a.O * (FQ + 1) + tid; e < a.PA1; e += kGy3Threads) prow[e] = 0.f;
+  }
+  if constexpr (FUSED) {
+    // =========================================================================== phase 2: adjoint, one window per thread
+    __syncthreads();  // gout_s complete; every warp is done with the gy ring
+    const int xtile_elems = kFbXRows * kFbXW;
+    auto issue_x = [&](int n) {
+      const int tile = tile0 + n;
+      const int b = tile / a.tiles_per_utt;
+      const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+      const int s = n % kGy3Stages;
+      mbar_arrive_expect_tx(&xfull[s], (uint32_t)xtile_elems * 4);
+      tma_load_3d(stages + (size_t)s * SE, &tm_x, i0 - 4, 0, b, &xfull[s]);
+    };
+    if (tid == 0)
+      for (int n = 0; n < kGy3Stages && n < my_tiles; ++n) issue_x(n);
+    {
+      const int n = tid >> 5;  // tile of this thread's window (warp <-> tile), window = lane
+      bool valid = false;
+      if (n < my_tiles) {
+        const int tile = tile0 + n;
+        const int b = tile / a.tiles_per_utt;
+        valid = (tile - b * a.tiles_per_utt) * FTW + lane < a.Lout;
+      }
+      if (n < my_tiles) {  // warp-uniform: a warp whose tile does not exist only clears its row
+        const float4 pv = valid ? ld4(pre_s + ((size_t)n * FTW + lane) * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+        const float4 gv = valid ? ld4(gout_s + ((size_t)n * FTW + lane) * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
+        const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
+        float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
+        const float inv = circuit_forward_amp<float, FQ>(pre, gates, 1, re, im, out);
+        RegGateAcc acc;
+#pragma unroll
+        for (int w = 0; w < FQ; ++w)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc.m[w][e] = 0.f;
+        circuit_backward_amp<float, FQ>(pre, inv, gates, 1, re, im, gout, gpre, acc);
+        st4(gpre_s + ((size_t)n * FTW + lane) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
+        // warp totals: 32 gate-matrix entries (transposing reduction) + 4 grad pre_conv.bias entries
+        float mv[32];
+#pragma unroll
+        for (int w = 0; w < FQ; ++w)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mv[w * 8 + e] = acc.m[w][e];
+        const float msum = warp_transpose_sum32(mv, lane);
+        red2[warp * 40 + lane] = msum;
+#pragma unroll
+        for (int j = 0; j < FQ; ++j) {
+          const float bsum = warp_sum(gpre[j]);
+          if (lane == 0) red2[warp * 40 + 32 + j] = bsum;
+        }
+      } else {
+        red2[warp * 40 + lane] = 0.f;
+        if (lane < FQ) red2[warp * 40 + 32 + lane] = 0.f;
+      }
+    }
+    __syncthreads();  // gpre_s, red2 complete
+    {
+      float* prow2 = a.part2 + (size_t)blockIdx.x * a.PA2;
+      for (int e = tid; e < a.PA2; e += kGy3Threads) {
+        // row layout: [0,4) grad pre_conv.bias, [32, 64) gate-gradient matrices, everything else padding
+        const int src = e < FQ ? 32 + e : (e >= 32 && e < 64) ? e - 32 : -1;
+        float v = 0.f;
+        if (src >= 0)
+#pragma unroll
+          for (int w = 0; w < kGy3Warps; ++w) v += red2[w * 40 + src];
+        prow2[e] = v;
+      }
+    }
+    // =========================================================================== phase 3: grad pre_conv.weight
+    // thread <-> (channel c, tap k): p = c * 3 + k; slot 1 covers p >= 192 (C <= 96: at most 288 pairs)
+    const int nck = a.C * 3;
+    const int p0 = tid, p1 = tid + kGy3Threads;
+    const int c0 = p0 / 3, k0 = p0 - 3 * c0, c1 = p1 / 3, k1 = p1 - 3 * c1;
+    const bool v0 = p0 < nck, v1 = p1 < nck;
+    float acc0[FQ] = {0.f, 0.f, 0.f, 0.f}, acc1[FQ] = {0.f, 0.f, 0.f, 0.f};
+    for (int n = 0; n < my_tiles; ++n) {
+      const int s = n % kGy3Stages;
+      mbar_wait(&xfull[s], (n / kGy3Stages) & 1);
+      const float* xs = stages + (size_t)s * SE;
+      const float* x0 = xs + (v0 ? c0 * kFbXW + 3 + k0 : 0);
+      const float* x1 = xs + (v1 ? c1 * kFbXW + 3 + k1 : 0);
+      const float* gp = gpre_s + (size_t)n * FTW * FQ;
+#pragma unroll 8
+      for (int w = 0; w < FTW; ++w) {
+        const float4 gq = ld4(gp + w * FQ);
+        const float xa = x0[w], xb = x1[w];
+        acc0[0] = fmaf(gq.x, xa, acc0[0]); acc0[1] = fmaf(gq.y, xa, acc0[1]);
+        acc0[2] = fmaf(gq.z, xa, acc0[2]); acc0[3] = fmaf(gq.w, xa, acc0[3]);
+        acc1[0] = fmaf(gq.x, xb, acc1[0]); acc1[1] = fmaf(gq.y, xb, acc1[1]);
+        acc1[2] = fmaf(gq.z, xb, acc1[2]); acc1[3] = fmaf(gq.w, xb, acc1[3]);
+      }
+      if (n + kGy3Stages < my_tiles) {
+        __syncthreads();  // every thread is done with slot s
+        if (tid == 0) issue_x(n + kGy3Stages);
+      }
+    }
+    float* prow3 = a.part3 + (size_t)blockIdx.x * a.PB;
+    if (v0) {
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) prow3[c0 * 12 + j * 3 + k0] = acc0[j];
+    }
+    if (v1) {
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) prow3[c1 * 12 + j * 3 + k1] = acc1[j];
+    }
+    for (int e = nck * FQ + tid; e < a.PB; e += kGy3Threads) prow3[e] = 0.f;
+  }
+  tl_end(a.tl);
+}
+
 // adjoint differentiation of the circuit, one window per thread; partial row per CTA: [gb_pre 4 + pad 28][Lq*32 gate matrices]
 //
 // The forward recomputation of a window needs only pre_save (written by the forward kernel, at least two launches back in the
@@ -681,8 +1096,6 @@ __global__ void __launch_bounds__(kThreads) fast_bwd_pre_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           // window index relative to wb: stride 1: p - k + 2; stride 2: (p + PAR - k)/2 + 1 when even
-          constexpr int dummy = 0;
-          (void)dummy;
           const int num = p + PAR - k;
           const bool valid = (S == 1) || ((num & 1) == 0);
           if (valid) {
@@ -908,27 +1321,18 @@ int make_tmap_3d_f32(CUtensorMap* tm, const void* base, unsigned long long d0, u
   return 0;
 }
 
-static int env_flag(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-// Experiment switches (defaults = the measured winners on B200, batch-16 stem step):
-//   QW_FWD_ETMA  1: the forward kernel requests its first x tiles before staging its parameters        (-1.0 us / step)
-//   QW_PRE_EX    1: the pre_conv^T kernel requests its first x tiles before the dependency wait        (-1.7 us)
-//   QW_FIN_EARLY 1: finalize segments 1-2 (rows of the gy / adjoint kernels) run before the dependency wait  (-2.6 us)
-//   QW_ADJ_TRIG  1: the adjoint kernel triggers its dependent right after its wait, so pre_conv^T CTAs come in and request
-//                   their x tiles while it runs (+0.3 us with the 128-register adjoint kernel, -1.4 us with the 96-register one)
-static int flag_fwd_etma() { static const int v = env_flag("QW_FWD_ETMA", 1); return v; }
-static int flag_fin_early() { static const int v = env_flag("QW_FIN_EARLY", 1); return v; }
-static int flag_adj_trig() { static const int v = env_flag("QW_ADJ_TRIG", 1); return v; }
-static int flag_pre_ex() { static const int v = env_flag("QW_PRE_EX", 1); return v; }
-static bool g_fast_enabled = true;
-void set_fast_path(bool on) { g_fast_enabled = on; }
+// A/B switches: qw::option() (qw_common.cuh; defaults = the measured winners on B200, batch-16 stem step)
+static int flag_fwd_etma() { return option(kOptFwdEtma); }
+static int flag_fin_early() { return option(kOptFinEarly); }
+static int flag_adj_trig() { return option(kOptAdjTrig); }
+static int flag_pre_ex() { return option(kOptPreEx); }
+static int flag_gy_mma() { return option(kOptGyMma); }
+static int flag_bwd_fused() { return option(kOptBwdFused); }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd) {
-  return g_fast_enabled && (!fwd || d.P == 1) && d.Q == 4 && d.K == 3 && (d.S == 1 || d.S == 2) && d.emb == kEmbAmplitude && d.L % 4 == 0 &&
+  return option(kOptFastPath) && (!fwd || d.P == 1) && d.Q == 4 && d.K == 3 && (d.S == 1 || d.S == 2) && d.emb == kEmbAmplitude && d.L % 4 == 0 &&
          d.Lout % 4 == 0 && d.O % 4 == 0 && d.O <= 576 && d.Lq <= 4 && d.C * 3 * FQ * 4 <= 96 * 1024 && aligned16(x) && aligned16(y_or_gy) &&
          aligned16(gx) && tmap_encode_fn() != nullptr;
 }
@@ -944,15 +1348,9 @@ bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const 
 FastPlan make_fast_plan(const ConvDims& d) {
   FastPlan p{};
   const int sms = num_sms();
-  {
-    // tile stride: FTW unless QW_TW forces 16..32 (A/B switch).  Measured on B200 at batch 16 (stem step, same box):
-    // stride 32: 140.1 us, 28: 140.2 us, 24: 154.4 us -- the rounds are bound by per-tile latency (TMA round trip + the
-    // circuit warp's dependent chain + the hand-offs), not by the bytes of a tile, so narrower tiles only add tiles.
-    static const int forced = env_flag("QW_TW", 0);
-    for (int tw = FTW; tw >= 16; tw -= 4)
-      if (tw == forced) p.tw = tw;
-    if (p.tw == 0) p.tw = FTW;
-  }
+  // tile stride = tile width.  (Round 1 measured narrower strides with the same 32-window boxes: 32 -> 140.1 us, 28 -> 140.2, 24 -> 154.4
+  // per step: the bytes of a round do not shrink with the stride, so the experiment switch is gone.)
+  p.tw = FTW;
   p.tiles_per_utt = (d.Lout + p.tw - 1) / p.tw;
   p.num_tiles = d.B * p.tiles_per_utt;
   p.rc = d.C <= 128 ? (int)align_up(d.C, 32) : 64;  // small C: the whole channel range is one TMA box per tile
@@ -984,7 +1382,7 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.nchunks = (d.C + 31) / 32;
   p.Cpad = p.nchunks * 32;
   // CTAs per SM of the pre_conv^T kernel: 4 x 52 KB of shared memory fit; measured at batch 16: 2 -> 133.0, 3 -> 127.9, 4 -> 126.9 us
-  static const int pre_ctas = env_flag("QW_PRE_CTAS", 4);
+  const int pre_ctas = option(kOptPreCtas) > 0 ? option(kOptPreCtas) : 4;
   int cap = pre_ctas * sms / p.nchunks;
   if (cap < 1) cap = 1;
   p.gridPx = p.num_ptiles < cap ? p.num_ptiles : cap;
@@ -994,7 +1392,7 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
   p.off_p1 = o;   o = align_up(o + (size_t)p.gridGy * p.PA1 * 4, 256);
   p.off_p2 = o;   o = align_up(o + (size_t)p.gridAdj * p.PA2 * 4, 256);
-  p.off_p3 = o;   o = align_up(o + (size_t)p.gridPx * p.PB * 4, 256);
+  p.off_p3 = o;   o = align_up(o + (size_t)(p.gridPx > p.gridGy ? p.gridPx : p.gridGy) * p.PB * 4, 256);  // fused backward: one row per gy CTA
   p.ws_bytes = o;
   return p;
 }
@@ -1056,8 +1454,34 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
 // gy 14.7 / 23.2 vs 12.9 / 21.8 us) -- the extra warps do not raise the issue rate of the two contractions, the 2-deep ring
 // loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.  Also measured and dropped:
 // 3 CTAs per SM of the 6-warp form with a 2-deep ring (444 CTAs): 139.2 us.
+template <int NHALF, bool FUSED>
+static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
+                           const FastPlan& p, cudaStream_t st) {
+  const size_t smem = FUSED ? fast_gy3_fused_smem_bytes() : fast_gy3_smem_bytes();
+  auto k = fast_bwd_gy3_kernel<NHALF, FUSED>;
+  QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    KernelTimer kt(FUSED ? kKBwdFused : kKBwdPost, st);
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(kGy3Threads), smem, st, tg, tq, tp, tx, a));
+  }
+  QW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <bool FUSED>
+static int launch_fast_gy3_any(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
+                               const FastPlan& p, cudaStream_t st) {
+  const int nhalf = (a.O + kGy3Rows - 1) / kGy3Rows;
+  return nhalf == 1 ? launch_fast_gy3<1, FUSED>(tg, tq, tp, tx, a, p, st)
+       : nhalf == 2 ? launch_fast_gy3<2, FUSED>(tg, tq, tp, tx, a, p, st)
+                    : launch_fast_gy3<3, FUSED>(tg, tq, tp, tx, a, p, st);
+}
 static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
-  static const int forced = env_flag("QW_GY_WARPS", 0);
+  // default: the tensor-pipe form (fast_bwd_gy3_kernel); QW_GY_MMA=0 selects the FFMA form for A/B
+  if (flag_gy_mma() && p.tw == FTW) {
+    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, a.B, 0, a.O, a.Lout, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl};
+    return launch_fast_gy3_any<false>(tg, tq, tq, tq, a3, p, st);
+  }
+  const int forced = option(kOptGyWarps);
   const bool wide = forced == 12;
   if (wide) {
     const int nhalf = (a.O + 383) / 384;
@@ -1097,6 +1521,31 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
   float* gout = reinterpret_cast<float*>(ws + p.off_gout);
   float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
+  // small-batch data layer (no grad_x): gy pass + adjoint + pre_conv^T in one kernel (see fast_bwd_gy3_kernel<.., true>)
+  const bool fused = flag_bwd_fused() && flag_gy_mma() && gx == nullptr && d.S == 1 && d.P == 1 && d.Lq == 1 && d.C <= kFbXRows && p.tw == FTW &&
+                     (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy;
+  if (fused) {
+    alignas(64) CUtensorMap tm_pre, tm_xf;
+    if (int e = make_tmap_3d_f32(&tm_pre, pre_save, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
+    if (int e = make_tmap_3d_f32(&tm_xf, x, d.L, d.C, d.B, kFbXW, kFbXRows, false)) return e;
+    FastGy3Args a{w_post, qwts, nullptr, part1, part2, part3, d.B, d.C, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.PA2, p.PB,
+                  timeline_next_slot()};
+    if (int e = launch_fast_gy3_any<true>(tm_gy, tm_qout, tm_pre, tm_xf, a, p, st)) return e;
+    FastFinArgs f{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridGy, p.PA2,
+                  p.gridGy, p.PB, d.C, d.O, d.Lq, timeline_next_slot(), FastDp{}, 0};
+    const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
+    if (dp && dp->world > 1) {
+      f.dp = *dp;
+      f.dp.ncol = nblk * 32;
+    }
+    {
+      KernelTimer kt(kKBwdFinalize, st);
+      if (f.dp.world > 1) QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel<512>, dim3(nblk), dim3(512), 0, st, f));
+      else QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel<1024>, dim3(nblk), dim3(1024), 0, st, f));
+    }
+    QW_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
   {
     FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot()};
@@ -1106,7 +1555,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   {
     FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W, flag_adj_trig(), timeline_next_slot()};
     const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
-    static const int adj_spec = env_flag("QW_ADJ_SPEC", 1);
+    const int adj_spec = option(kOptAdjSpec);
     auto k = (d.Lq == 1 && adj_spec) ? fast_bwd_adj_kernel<false> : fast_bwd_adj_kernel<true>;
     if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {

@@ -64,7 +64,6 @@ struct FastAdjArgs {
   int early_trigger;  // experiment switch QW_ADJ_TRIG: trigger the dependent launch right after the wait
   unsigned long long* tl;
 };
-void set_fast_path(bool on);
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd);
 FastPlan make_fast_plan(const ConvDims& d);
 int fast_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,

@@ -194,6 +194,63 @@ def test_fast_and_generic_agree_full_size(cuda):
             assert (a - b).abs().max().item() <= tol, i
 
 
+def _set_opt(lib, name, value):
+    assert lib.qw_set_option(name.encode(), value) == 0, name
+
+
+@pytest.mark.parametrize("B,C,L,O", [(16, 80, 3000, 384), (2, 80, 3000, 384), (3, 80, 260, 384), (1, 40, 1028, 8), (5, 96, 72, 200),
+                                     (7, 33, 64, 64)])
+def test_fused_backward_data_layer(cuda, B, C, L, O):
+    """A data layer (its input needs no gradient: conv1 of the stem) at small batch runs its whole backward in ONE kernel
+    (gy pass on the tensor pipe + adjoint + pre_conv^T, `fast_bwd_gy3_kernel<.., true>`).  All five parameter gradients against the
+    fp64 oracle (same bound as test_layer_f32: 5e-5 relative to max(1, |ref|)) and against the three-kernel path."""
+    _lib, qc = _mods()
+    lib = _lib.load()
+    params64 = qo.make_params(C, O, 3, 4, seed=9)
+    g = torch.Generator().manual_seed(10)
+    x64 = torch.randn(B, C, L, generator=g, dtype=torch.float64)
+    gy64 = torch.randn(B, O, L, generator=g, dtype=torch.float64)
+    xr = x64.float().double()
+    pr = [p.float().double() for p in params64]
+    ref = qo.qconv1d_grads(xr, pr, gy64.float().double(), 3, 1, 1, need_gx=False)
+    res = {}
+    launches = {}
+    try:
+        for fused in (1, 0):
+            _set_opt(lib, "BWD_FUSED", fused)
+            x = x64.float().to(cuda)  # no requires_grad: grad_x is not computed
+            ps = [p.float().to(cuda).requires_grad_(True) for p in params64]
+            y = qc.quantum_conv1d(x, *ps, kernel_size=3, stride=1, padding=1)
+            n0 = _lib.launch_count()
+            grads = torch.autograd.grad(y, ps, gy64.float().to(cuda))
+            torch.cuda.synchronize()
+            launches[fused] = _lib.launch_count() - n0
+            res[fused] = dict(zip(["w_pre", "b_pre", "qweights", "w_post", "b_post"], [t.cpu().double() for t in grads]))
+    finally:
+        _set_opt(lib, "BWD_FUSED", 1)
+    assert launches == {1: 2, 0: 4}, launches  # fused + finalize vs gy / adjoint / pre_conv^T / finalize
+    for k in ("w_pre", "b_pre", "qweights", "w_post", "b_post"):
+        assert _rel(res[1][k], ref[k]) <= 5e-5, k
+        assert _rel(res[0][k], ref[k]) <= 5e-5, k
+        assert _rel(res[1][k], res[0][k]) <= 2e-5, k
+
+
+@pytest.mark.parametrize("mma", [1, 0])
+def test_gy_pass_tensor_pipe_vs_ffma(cuda, mma):
+    """The gy pass of the backward exists in a tensor-pipe form (mma.sync m16n8k8, 3 x TF32 split, default) and an FFMA form:
+    both within the layer tolerance of the oracle at a stem-shaped geometry with ragged last tiles (L_out = 1500 = 46 x 32 + 28)."""
+    _lib, _ = _mods()
+    lib = _lib.load()
+    try:
+        _set_opt(lib, "GY_MMA", mma)
+        got, ref = _run_layer(cuda, (2, 384, 3000, 3, 2, 1, 384, 4), torch.float32, seed=13)
+    finally:
+        _set_opt(lib, "GY_MMA", 1)
+    assert (got["y"] - ref["y"]).abs().max().item() <= 5e-5
+    for k in ("x", "w_pre", "b_pre", "qweights", "w_post", "b_post"):
+        assert _rel(got[k], ref[k]) <= 5e-5, k
+
+
 @pytest.mark.parametrize("geom", GEOMS)
 def test_layer_f32(cuda, geom):
     got, ref = _run_layer(cuda, geom, torch.float32)

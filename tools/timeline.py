@@ -59,11 +59,8 @@ def main():
     for i in range(8):
         graphs[i % a.nsets].replay()
     torch.cuda.synchronize()
-    names = []
-    for layer, kinds in (("conv1", ["fwd"]), ("conv2", ["fwd"]), ("conv2", ["gy", "adj", "pre", "fin"]), ("conv1", ["gy", "adj", "pre", "fin"])):
-        names += [f"{layer}.{k}" for k in kinds]
-    if per_step == 8:
-        names = [n for n in names if not n.endswith(".fin")]
+    names = [n.replace("bwd_post(gy)", "gy").replace("bwd_adj", "adj").replace("bwd_pre", "pre").replace("bwd_finalize", "fin")
+             .replace("bwd_fused", "fused") for n in bench.step_kernel_names(runner)]
     rows = []
     for r in range(a.reps):
         reset()
