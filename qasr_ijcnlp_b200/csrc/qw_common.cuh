@@ -13,7 +13,7 @@ namespace qw {
 enum Option {
   kOptFastPath = 0,  // FAST_PATH  1: TMA fast path when the shape qualifies; 0: generic kernels
   kOptGyMma,         // GY_MMA     1: gy pass on the tensor pipe (mma.sync 3xTF32); 0: FFMA form
-  kOptBwdFused,      // BWD_FUSED  1: one backward kernel for small-batch data layers; 0: gy / adjoint / pre_conv^T kernels
+  kOptBwdFused,      // BWD_FUSED  0 (default): gy / adjoint / pre_conv^T kernels; 1: adjoint (+ pre_conv^T of a data layer) inside the gy kernel; 2: adjoint only
   kOptFwdMma,        // FWD_MMA    1: post_conv of the forward kernel on the tensor pipe; 0: FFMA form
   kOptFwdEtma,       // FWD_ETMA   1: forward requests its first x tiles before staging parameters
   kOptFinEarly,      // FIN_EARLY  1: finalize segments 1-2 run before the dependency wait (split backward only)
@@ -22,6 +22,8 @@ enum Option {
   kOptAdjSpec,       // ADJ_SPEC   1: single-layer specialisation of the adjoint kernel
   kOptPreCtas,       // PRE_CTAS   CTAs per SM of the pre_conv^T kernel (default 4)
   kOptGyWarps,       // GY_WARPS   12: wide FFMA gy kernel (only with GY_MMA=0)
+  kOptDbgFwd,        // DBG_FWD    bit mask: forward kernel skips pre_conv FMAs (1) / post_conv FMAs (2) / circuit (4); results are garbage
+  kOptDbgGy,         // DBG_GY     1: gy kernel skips its contractions (measures the streaming floor; results are garbage)
   kOptCount
 };
 int option(Option o);

@@ -45,6 +45,7 @@ struct FastFwdArgs {
   int tw;  // tile stride in windows
   int early_tma;
   unsigned long long* tl;
+  int dbg;  // experiment switch DBG_FWD (results are garbage): 1 = skip the pre_conv FMAs, 2 = skip the post_conv FMAs, 4 = skip the circuit
 };
 
 constexpr int kFwdStages = 4;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&pempty[pb]);
       float out[FQ] = {0.f, 0.f, 0.f, 0.f};
-      if (lane < a.tw && i < a.Lout) {
+      if ((a.dbg & 4) == 0 && lane < a.tw && i < a.Lout) {
         float re[1 << FQ], im[1 << FQ];
         circuit_forward_amp<float, FQ>(pre, gates, Lq, re, im, out);
         const size_t wi = (size_t)b * a.Lout + i;
@@ -230,7 +231,9 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
             xc[1] = v0.x; xc[2] = v0.y; xc[3] = v0.z; xc[4] = v0.w;
             xc[5] = v1.x; xc[6] = v1.y; xc[7] = v1.z; xc[8] = v1.w;
           }
-          if (c < a.C) {
+          if (a.dbg & 1) {
+            acc[0][0] += xc[0] + xc[4];
+          } else if (c < a.C) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               const float4 wv = ld4(wpre_t + (size_t)(c * 3 + k) * FQ);
@@ -296,10 +299,14 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
         const float4 wv = ld4(wpost + (size_t)o * FQ);
         const float bv = bpost[o];
         float4 r;
+        if (a.dbg & 2) {
+          r = make_float4(bv, bv, bv, bv);
+        } else {
         r.x = fmaf(wv.w, ov[0][3], fmaf(wv.z, ov[0][2], fmaf(wv.y, ov[0][1], fmaf(wv.x, ov[0][0], bv))));
         r.y = fmaf(wv.w, ov[1][3], fmaf(wv.z, ov[1][2], fmaf(wv.y, ov[1][1], fmaf(wv.x, ov[1][0], bv))));
         r.z = fmaf(wv.w, ov[2][3], fmaf(wv.z, ov[2][2], fmaf(wv.y, ov[2][1], fmaf(wv.x, ov[2][0], bv))));
         r.w = fmaf(wv.w, ov[3][3], fmaf(wv.z, ov[3][2], fmaf(wv.y, ov[3][1], fmaf(wv.x, ov[3][0], bv))));
+        }
         if (store_ok) st4(yb + (size_t)o * a.Lout, r);
       }
     }
@@ -529,33 +536,39 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 
-// ---- fused small-batch form (FUSED = true): gy pass + adjoint + pre_conv^T of a data layer (no grad_x) in ONE kernel.
-// At batch 16 a CTA of the persistent grid sees only 5-6 tiles, the three backward kernels of a layer run 5-20 us each, and a
+// ---- fused small-batch forms (FUSED = 1, 2): the adjoint (and for a data layer the pre_conv^T contraction) ride in the gy kernel.
+// At batch 16 a CTA of the persistent grid sees only 3-6 tiles, the backward kernels of a layer run 5-20 us each, and a
 // zero-compute TMA streaming kernel of the same footprint needs ~15 us for the 74 MB of gy (tools/probe/stream_probe.cu): launch
-// ramp, the ragged last round and the drain of every kernel boundary cost as much as the bytes.  Here every CTA owns a CONTIGUOUS
-// range of <= kFbMaxTiles tiles and carries them through all three phases on its own, so nothing waits for a grid-wide boundary:
-//   phase 1  the tensor-pipe gy pass above; gout stays in shared memory (never written to HBM), <Z> and pre_conv outputs of the
-//            tile's windows arrive by TMA next to its first stage;
-//   phase 2  adjoint differentiation, one window per thread over ALL warps at once (the round-1 fused attempt specialised two
-//            warps per CTA and serialised ~3 000 dependent instructions per tile on them); gate-gradient matrices are reduced
-//            with a transposing warp reduction (31 shuffles for 32 values) -- one window per thread needs no accumulators;
-//            the x tiles of phase 3 are requested before it starts and land while it runs;
-//   phase 3  grad pre_conv.weight[j][c][k] += gpre[w][j] x[c][w + k - 1]: threads = (c, k) pairs, register accumulators.
-// CTAs that own one tile fewer than their neighbours run phases 2-3 while the others still stream.  One partial row per CTA
-// and phase, reduced by the finalize kernel as before.
-constexpr int kFbMaxTiles = 6;   // 6 tiles x 32 windows = one window per thread in phase 2
+// ramp, the ragged last round and the drain of every kernel boundary cost as much as the bytes, while the gy pass itself leaves
+// most issue slots idle (it waits for HBM).  So the adjoint differentiation moves INTO those idle slots:
+//   warps 0-5  the tensor-pipe gy pass above over a CONTIGUOUS range of <= kFbMaxTiles tiles; gout stays in shared memory
+//              (never written to HBM); <Z> and pre_conv outputs of each tile arrive by TMA on a per-tile barrier;
+//   warp 6     adjoint warp, one window per lane: the forward recomputation of tile n runs as soon as its pre_conv outputs have
+//              landed (i.e. while the gy rows of that tile are still streaming), the backward sweep as soon as the tile's gout
+//              is summed.  Gate-gradient matrices accumulate in registers over the CTA's tiles and are reduced once (transposing
+//              warp reduction, 31 shuffles for 32 values).  Only the last tile's backward sweep (~1 650 instructions) is exposed.
+//              (Round 1 tried two specialised adjoint warps next to an FFMA gy pass and lost: that pass was issue-bound, so the
+//              adjoint warps and the streaming warps fought for the same slots.)
+//   FUSED = 1  data layer (stride 1, no grad_x: conv1 of the stem): gpre stays in shared memory and the streaming warps finish
+//              with grad pre_conv.weight[j][c][k] += gpre[w][j] x[c][w + k - 1] on x tiles requested when the gy ring drains
+//              (threads = (c, k) pairs, register accumulators) -- the whole backward of the layer is this kernel + finalize.
+//   FUSED = 2  any layer: gpre goes to the halo-padded workspace array the pre_conv^T kernel reads (the adjoint kernel is gone).
+// One partial row per CTA and role, reduced by the finalize kernel as before.
+constexpr int kFbMaxTiles = 6;   // tiles per CTA the shared-memory slots cover
 constexpr int kFbXW = 40;        // x tile columns (as the forward kernel: tap k of local window w = column 3 + w + k)
 constexpr int kFbXRows = 96;     // x tile rows (channels; C <= 96)
 __host__ __device__ constexpr size_t fast_gy3_fused_smem_bytes() {
   return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)4 * kFbMaxTiles * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 +
-         (size_t)FQ * kGateStride * 4 + (size_t)kGy3Warps * 40 * 4 + (2 * kGy3Stages + kGy3Stages) * 8;
+         (size_t)FQ * kGateStride * 4 + (3 * kGy3Stages + 2 * kFbMaxTiles + 1) * 8;
 }
 struct FastGy3Args {
   const float *w_post, *qw;
   float *gout, *part;       // plain: gout [B*Lout][4]; part: [grid][PA1]
   float *part2, *part3;     // fused: [grid][PA2], [grid][PB]
-  int B, C, O, Lout, tiles_per_utt, num_tiles, PA1, PA2, PB;
+  float* gpre_pad;          // FUSED = 2: [B][LP][4]
+  int B, C, O, Lout, LP, tiles_per_utt, num_tiles, PA1, PA2, PB;
   unsigned long long* tl;
+  int dbg;  // experiment switch DBG_GY: 1 = skip the contractions (streaming floor of the kernel); results are garbage
 };
 struct RegGateAcc {
   float m[FQ][8];
@@ -579,12 +592,12 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   }
   return v[0];
 }
+__device__ __forceinline__ void bar_sync_streaming() { asm volatile("bar.sync 1, %0;" ::"n"(kGy3Threads) : "memory"); }
 
-template <int NHALF, bool FUSED>
-__global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __grid_constant__ CUtensorMap tm_gy,
-                                                                       const __grid_constant__ CUtensorMap tm_qout,
-                                                                       const __grid_constant__ CUtensorMap tm_pre,
-                                                                       const __grid_constant__ CUtensorMap tm_x, const FastGy3Args a) {
+template <int NHALF, int FUSED>
+__global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
+    fast_bwd_gy3_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_qout,
+                        const __grid_constant__ CUtensorMap tm_pre, const __grid_constant__ CUtensorMap tm_x, const FastGy3Args a) {
   constexpr int SE = kGy3Rows * 32;  // floats per stage
   constexpr int NQT = FUSED ? kFbMaxTiles : 3;  // <Z> tiles kept (fused: all of the CTA's tiles)
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -596,10 +609,12 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
   float* gpre_s = gout_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);       // fused: [kFbMaxTiles][32][4]
   float* gred = gpre_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);         // [2][6 warps][32 windows][8]
   float* gates = gred + 2 * kGy3Warps * FTW * 8;                       // fused: [4][16]
-  float* red2 = gates + (FUSED ? FQ * kGateStride : 0);                // fused: [6 warps][40]
-  uint64_t* full = reinterpret_cast<uint64_t*>(red2 + (FUSED ? kGy3Warps * 40 : 0));
+  uint64_t* full = reinterpret_cast<uint64_t*>(gates + (FUSED ? FQ * kGateStride : 0));
   uint64_t* empty = full + kGy3Stages;
-  uint64_t* xfull = empty + kGy3Stages;                                // fused: [kGy3Stages] x tiles of phase 3
+  uint64_t* xfull = empty + kGy3Stages;                                // FUSED = 1: x tiles of the pre_conv^T phase
+  uint64_t* pqfull = xfull + kGy3Stages;                               // fused: [kFbMaxTiles] <Z> + pre_conv outputs of tile n landed
+  uint64_t* gfull = pqfull + kFbMaxTiles;                              // fused: [kFbMaxTiles] gout of tile n summed
+  uint64_t* gdone = gfull + kFbMaxTiles;                               // fused: the adjoint warp is through
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -607,18 +622,90 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
   if (tid == 0) {
     tma_prefetch_desc(&tm_gy);
     tma_prefetch_desc(&tm_qout);
-    if (FUSED) {
-      tma_prefetch_desc(&tm_pre);
-      tma_prefetch_desc(&tm_x);
-    }
+    if (FUSED) tma_prefetch_desc(&tm_pre);
+    if (FUSED == 1) tma_prefetch_desc(&tm_x);
     for (int s = 0; s < kGy3Stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kGy3Warps);
       if (FUSED) mbar_init(&xfull[s], 1);
     }
+    if (FUSED) {
+      for (int n = 0; n < kFbMaxTiles; ++n) {
+        mbar_init(&pqfull[n], 1);
+        mbar_init(&gfull[n], 1);
+      }
+      mbar_init(gdone, 1);
+    }
     fence_mbar_init();
   }
   if (FUSED && tid < FQ) make_gate<float>(a.qw + tid * 3, gates + tid * kGateStride);
+
+  // plain: round-robin tiles (neighbouring CTAs stream neighbouring row segments); fused: a contiguous range per CTA
+  int tile0, tstep, my_tiles;
+  if (FUSED) {
+    tile0 = (int)(((long long)blockIdx.x * a.num_tiles) / gridDim.x);
+    my_tiles = (int)(((long long)(blockIdx.x + 1) * a.num_tiles) / gridDim.x) - tile0;
+    tstep = 1;
+  } else {
+    tile0 = blockIdx.x;
+    tstep = gridDim.x;
+    my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  }
+
+  if (FUSED && warp == kGy3Warps) {
+    // ========================================================================= adjoint warp: one window per lane
+    __syncthreads();
+    pdl_wait();
+    RegGateAcc acc;
+#pragma unroll
+    for (int w = 0; w < FQ; ++w)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc.m[w][e] = 0.f;
+    float gb[FQ] = {0.f, 0.f, 0.f, 0.f};
+    for (int n = 0; n < my_tiles; ++n) {
+      const int tile = tile0 + n;
+      const int b = tile / a.tiles_per_utt;
+      const int i = (tile - b * a.tiles_per_utt) * FTW + lane;
+      const bool valid = i < a.Lout;
+      mbar_wait(&pqfull[n], 0);
+      const float4 pv = valid ? ld4(pre_s + ((size_t)n * FTW + lane) * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
+      const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
+      float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
+      const float inv = circuit_forward_amp<float, FQ>(pre, gates, 1, re, im, out);
+      mbar_wait(&gfull[n], 0);
+      const float4 gv = valid ? ld4(gout_s + ((size_t)n * FTW + lane) * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
+      circuit_backward_amp<float, FQ>(pre, inv, gates, 1, re, im, gout, gpre, acc);
+#pragma unroll
+      for (int j = 0; j < FQ; ++j) gb[j] += gpre[j];
+      if (FUSED == 1) st4(gpre_s + ((size_t)n * FTW + lane) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
+      if (FUSED == 2 && valid) st4(a.gpre_pad + ((size_t)b * a.LP + kHaloL + i) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
+    }
+    if (FUSED == 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gdone);  // gpre_s of every tile is in shared memory
+    }
+    // partial row of this CTA: [0,4) grad pre_conv.bias, [32,64) gate-gradient matrices, everything else padding
+    float mv[32];
+#pragma unroll
+    for (int w = 0; w < FQ; ++w)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mv[w * 8 + e] = acc.m[w][e];
+    const float msum = warp_transpose_sum32(mv, lane);
+    float* prow2 = a.part2 + (size_t)blockIdx.x * a.PA2;
+    float bsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < FQ; ++j) {
+      const float s_ = warp_sum(gb[j]);
+      if (lane == j) bsum = s_;
+    }
+    prow2[lane] = lane < FQ ? bsum : 0.f;
+    prow2[32 + lane] = msum;
+    for (int e = 64 + lane; e < a.PA2; e += 32) prow2[e] = 0.f;
+    if (a.tl && lane == 0) atomicMax(a.tl + 1, global_ns());  // the adjoint warp may be the last one out
+    return;
+  }
+
   // B fragments of the gout contraction (parameters: readable before the dependency wait)
   uint32_t bw[NHALF][4][2];
 #pragma unroll
@@ -645,17 +732,16 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
   pdl_wait();
   pdl_launch();
 
-  // plain: round-robin tiles (neighbouring CTAs stream neighbouring row segments); fused: a contiguous range per CTA
-  int tile0, tstep, my_tiles;
-  if (FUSED) {
-    tile0 = (int)(((long long)blockIdx.x * a.num_tiles) / gridDim.x);
-    my_tiles = (int)(((long long)(blockIdx.x + 1) * a.num_tiles) / gridDim.x) - tile0;
-    tstep = 1;
-  } else {
-    tile0 = blockIdx.x;
-    tstep = gridDim.x;
-    my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (FUSED == 2) {
+    // zero the halos of gpre_pad (left kHaloL and right kHaloR windows of every utterance): the pre_conv^T kernel reads them
+    const int per = (kHaloL + kHaloR) * FQ;
+    for (long long idx = (long long)blockIdx.x * kGy3Threads + tid; idx < (long long)a.B * per; idx += (long long)gridDim.x * kGy3Threads) {
+      const int b = (int)(idx / per), e = (int)(idx - (long long)b * per);
+      const int off = e < kHaloL * FQ ? e : (kHaloL + a.Lout) * FQ + (e - kHaloL * FQ);
+      a.gpre_pad[(size_t)b * a.LP * FQ + off] = 0.f;
+    }
   }
+
   const int total_stages = my_tiles * NHALF;
   float d1[NHALF * 4][4];  // [8-channel block][fragment]: rows = hi/lo of <Z_j> (and the ones row), columns = channels
 #pragma unroll
@@ -670,13 +756,18 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
     const int b = tile / a.tiles_per_utt;
     const int i0 = (tile - b * a.tiles_per_utt) * FTW;
     const int s = gs % kGy3Stages;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(SE + (h == 0 ? (FUSED ? 2 : 1) * FTW * FQ : 0)) * 4);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(SE + ((h == 0 && !FUSED) ? FTW * FQ : 0)) * 4);
 #pragma unroll
     for (int bx = 0; bx < kGy3Rows / 64; ++bx)
       tma_load_3d(stages + (size_t)s * SE + bx * 64 * 32, &tm_gy, i0, h * kGy3Rows + bx * 64, b, &full[s]);
     if (h == 0) {
-      tma_load_3d(outs + (n % NQT) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
-      if (FUSED) tma_load_3d(pre_s + n * FTW * FQ, &tm_pre, 0, i0, b, &full[s]);
+      if (FUSED) {
+        mbar_arrive_expect_tx(&pqfull[n], (uint32_t)(2 * FTW * FQ) * 4);
+        tma_load_3d(outs + n * FTW * FQ, &tm_qout, 0, i0, b, &pqfull[n]);
+        tma_load_3d(pre_s + n * FTW * FQ, &tm_pre, 0, i0, b, &pqfull[n]);
+      } else {
+        tma_load_3d(outs + (n % NQT) * FTW * FQ, &tm_qout, 0, i0, b, &full[s]);
+      }
     }
   };
   if (tid == 0)
@@ -704,7 +795,8 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
       mbar_wait(&full[s], (gs / kGy3Stages) & 1);
       const float* gsm = stages + (size_t)s * SE;
       if (h == 0) {
-        // A fragments of the weight-gradient contraction from this tile's <Z> (they arrived with the tile's first stage)
+        if (FUSED) mbar_wait(&pqfull[n], 0);
+        // A fragments of the weight-gradient contraction from this tile's <Z>
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           const int w0 = 4 * kb + 2 * (t & 1) + 16 * (t >> 1);
@@ -717,6 +809,9 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
           }
         }
       }
+      if (a.dbg) {
+        d2[0][0] += gsm[tid];
+      } else {
       // ---- grad post_conv.{weight,bias}: this warp's four 8-channel blocks of the stage, K = the tile's 32 windows
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -747,6 +842,7 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
           mma_tf32(d2[m], al, bw[h][i][0], bw[h][i][1]);
         }
       }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
@@ -759,7 +855,7 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
       st2(gr + (16 * m + 2 * g) * 8 + 2 * t, make_float2(d2[m][0], d2[m][1]));
       st2(gr + (16 * m + 2 * g + 1) * 8 + 2 * t, make_float2(d2[m][2], d2[m][3]));
     }
-    __syncthreads();
+    if (FUSED) bar_sync_streaming(); else __syncthreads();
     if (warp == n % kGy3Warps) {
       const float* gq = gred + (size_t)(n & 1) * kGy3Warps * FTW * 8 + (size_t)lane * 8;
       float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -770,6 +866,8 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
       }
       if (FUSED) {
         st4(gout_s + ((size_t)n * FTW + lane) * FQ, sacc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gfull[n]);  // hand the tile to the adjoint warp
       } else {
         const int tile = tile0 + n * tstep;
         const int b = tile / a.tiles_per_utt;
@@ -799,9 +897,9 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
     }
     for (int e = a.O * (FQ + 1) + tid; e < a.PA1; e += kGy3Threads) prow[e] = 0.f;
   }
-  if constexpr (FUSED) {
-    // =========================================================================== phase 2: adjoint, one window per thread
-    __syncthreads();  // gout_s complete; every warp is done with the gy ring
+  if constexpr (FUSED == 1) {
+    // =========================================================================== grad pre_conv.weight (streaming warps)
+    bar_sync_streaming();  // every streaming warp is done with the gy ring: it now takes the x tiles
     const int xtile_elems = kFbXRows * kFbXW;
     auto issue_x = [&](int n) {
       const int tile = tile0 + n;
@@ -813,66 +911,13 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
     };
     if (tid == 0)
       for (int n = 0; n < kGy3Stages && n < my_tiles; ++n) issue_x(n);
-    {
-      const int n = tid >> 5;  // tile of this thread's window (warp <-> tile), window = lane
-      bool valid = false;
-      if (n < my_tiles) {
-        const int tile = tile0 + n;
-        const int b = tile / a.tiles_per_utt;
-        valid = (tile - b * a.tiles_per_utt) * FTW + lane < a.Lout;
-      }
-      if (n < my_tiles) {  // warp-uniform: a warp whose tile does not exist only clears its row
-        const float4 pv = valid ? ld4(pre_s + ((size_t)n * FTW + lane) * FQ) : make_float4(1.f, 0.f, 0.f, 0.f);
-        const float4 gv = valid ? ld4(gout_s + ((size_t)n * FTW + lane) * FQ) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float pre[FQ] = {pv.x, pv.y, pv.z, pv.w};
-        const float gout[FQ] = {gv.x, gv.y, gv.z, gv.w};
-        float out[FQ], gpre[FQ], re[1 << FQ], im[1 << FQ];
-        const float inv = circuit_forward_amp<float, FQ>(pre, gates, 1, re, im, out);
-        RegGateAcc acc;
-#pragma unroll
-        for (int w = 0; w < FQ; ++w)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc.m[w][e] = 0.f;
-        circuit_backward_amp<float, FQ>(pre, inv, gates, 1, re, im, gout, gpre, acc);
-        st4(gpre_s + ((size_t)n * FTW + lane) * FQ, make_float4(gpre[0], gpre[1], gpre[2], gpre[3]));
-        // warp totals: 32 gate-matrix entries (transposing reduction) + 4 grad pre_conv.bias entries
-        float mv[32];
-#pragma unroll
-        for (int w = 0; w < FQ; ++w)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) mv[w * 8 + e] = acc.m[w][e];
-        const float msum = warp_transpose_sum32(mv, lane);
-        red2[warp * 40 + lane] = msum;
-#pragma unroll
-        for (int j = 0; j < FQ; ++j) {
-          const float bsum = warp_sum(gpre[j]);
-          if (lane == 0) red2[warp * 40 + 32 + j] = bsum;
-        }
-      } else {
-        red2[warp * 40 + lane] = 0.f;
-        if (lane < FQ) red2[warp * 40 + 32 + lane] = 0.f;
-      }
-    }
-    __syncthreads();  // gpre_s, red2 complete
-    {
-      float* prow2 = a.part2 + (size_t)blockIdx.x * a.PA2;
-      for (int e = tid; e < a.PA2; e += kGy3Threads) {
-        // row layout: [0,4) grad pre_conv.bias, [32, 64) gate-gradient matrices, everything else padding
-        const int src = e < FQ ? 32 + e : (e >= 32 && e < 64) ? e - 32 : -1;
-        float v = 0.f;
-        if (src >= 0)
-#pragma unroll
-          for (int w = 0; w < kGy3Warps; ++w) v += red2[w * 40 + src];
-        prow2[e] = v;
-      }
-    }
-    // =========================================================================== phase 3: grad pre_conv.weight
     // thread <-> (channel c, tap k): p = c * 3 + k; slot 1 covers p >= 192 (C <= 96: at most 288 pairs)
     const int nck = a.C * 3;
     const int p0 = tid, p1 = tid + kGy3Threads;
     const int c0 = p0 / 3, k0 = p0 - 3 * c0, c1 = p1 / 3, k1 = p1 - 3 * c1;
     const bool v0 = p0 < nck, v1 = p1 < nck;
     float acc0[FQ] = {0.f, 0.f, 0.f, 0.f}, acc1[FQ] = {0.f, 0.f, 0.f, 0.f};
+    mbar_wait(gdone, 0);  // gpre of every tile is in shared memory
     for (int n = 0; n < my_tiles; ++n) {
       const int s = n % kGy3Stages;
       mbar_wait(&xfull[s], (n / kGy3Stages) & 1);
@@ -890,7 +935,7 @@ __global__ void __launch_bounds__(kGy3Threads, 2) fast_bwd_gy3_kernel(const __gr
         acc1[2] = fmaf(gq.z, xb, acc1[2]); acc1[3] = fmaf(gq.w, xb, acc1[3]);
       }
       if (n + kGy3Stages < my_tiles) {
-        __syncthreads();  // every thread is done with slot s
+        bar_sync_streaming();  // every thread is done with slot s
         if (tid == 0) issue_x(n + kGy3Stages);
       }
     }
@@ -1391,7 +1436,7 @@ FastPlan make_fast_plan(const ConvDims& d) {
   p.off_gout = o; o = align_up(o + (size_t)W * FQ * 4, 256);
   p.off_gpre = o; o = align_up(o + (size_t)d.B * p.LP * FQ * 4, 256);
   p.off_p1 = o;   o = align_up(o + (size_t)p.gridGy * p.PA1 * 4, 256);
-  p.off_p2 = o;   o = align_up(o + (size_t)p.gridAdj * p.PA2 * 4, 256);
+  p.off_p2 = o;   o = align_up(o + (size_t)(p.gridAdj > p.gridGy ? p.gridAdj : p.gridGy) * p.PA2 * 4, 256);  // fused backward: one row per gy CTA
   p.off_p3 = o;   o = align_up(o + (size_t)(p.gridPx > p.gridGy ? p.gridPx : p.gridGy) * p.PB * 4, 256);  // fused backward: one row per gy CTA
   p.ws_bytes = o;
   return p;
@@ -1419,7 +1464,7 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
   if (int e = make_tmap_3d_f32(&tm, x, d.L, d.C, d.B, xw, p.rc, false)) return e;
   const size_t W = (size_t)d.B * d.Lout;
   FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
-                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot()};
+                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot(), option(kOptDbgFwd)};
   if (d.S == 1) {
     switch (p.rc) {
       case 32: return launch_fast_fwd<1, 32>(tm, a, p, st);
@@ -1454,7 +1499,7 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
 // gy 14.7 / 23.2 vs 12.9 / 21.8 us) -- the extra warps do not raise the issue rate of the two contractions, the 2-deep ring
 // loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.  Also measured and dropped:
 // 3 CTAs per SM of the 6-warp form with a 2-deep ring (444 CTAs): 139.2 us.
-template <int NHALF, bool FUSED>
+template <int NHALF, int FUSED>
 static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
                            const FastPlan& p, cudaStream_t st) {
   const size_t smem = FUSED ? fast_gy3_fused_smem_bytes() : fast_gy3_smem_bytes();
@@ -1462,12 +1507,12 @@ static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const C
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     KernelTimer kt(FUSED ? kKBwdFused : kKBwdPost, st);
-    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(kGy3Threads), smem, st, tg, tq, tp, tx, a));
+    QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(FUSED ? kGy3Threads + 32 : kGy3Threads), smem, st, tg, tq, tp, tx, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
-template <bool FUSED>
+template <int FUSED>
 static int launch_fast_gy3_any(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
                                const FastPlan& p, cudaStream_t st) {
   const int nhalf = (a.O + kGy3Rows - 1) / kGy3Rows;
@@ -1478,8 +1523,8 @@ static int launch_fast_gy3_any(const CUtensorMap& tg, const CUtensorMap& tq, con
 static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
   // default: the tensor-pipe form (fast_bwd_gy3_kernel); QW_GY_MMA=0 selects the FFMA form for A/B
   if (flag_gy_mma() && p.tw == FTW) {
-    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, a.B, 0, a.O, a.Lout, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl};
-    return launch_fast_gy3_any<false>(tg, tq, tq, tq, a3, p, st);
+    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, nullptr, a.B, 0, a.O, a.Lout, 0, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl, option(kOptDbgGy)};
+    return launch_fast_gy3_any<0>(tg, tq, tq, tq, a3, p, st);
   }
   const int forced = option(kOptGyWarps);
   const bool wide = forced == 12;
@@ -1521,16 +1566,24 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
   float* gout = reinterpret_cast<float*>(ws + p.off_gout);
   float* part2 = reinterpret_cast<float*>(ws + p.off_p2);
-  // small-batch data layer (no grad_x): gy pass + adjoint + pre_conv^T in one kernel (see fast_bwd_gy3_kernel<.., true>)
-  const bool fused = flag_bwd_fused() && flag_gy_mma() && gx == nullptr && d.S == 1 && d.P == 1 && d.Lq == 1 && d.C <= kFbXRows && p.tw == FTW &&
-                     (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy;
+  // small batch (<= kFbMaxTiles tiles per CTA), single-layer circuit: the adjoint rides in the gy kernel (fast_bwd_gy3_kernel<.., 1|2>).
+  // mode 1 = data layer (no grad_x, stride 1): pre_conv^T as well -- the whole backward is that kernel + finalize;
+  // mode 2 = gpre goes to the workspace for the pre_conv^T kernel below.
+  int fused = 0;
+  if (flag_bwd_fused() && flag_gy_mma() && d.Lq == 1 && p.tw == FTW && (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy)
+    fused = (gx == nullptr && d.S == 1 && d.P == 1 && d.C <= kFbXRows && flag_bwd_fused() == 1) ? 1 : 2;
   if (fused) {
     alignas(64) CUtensorMap tm_pre, tm_xf;
     if (int e = make_tmap_3d_f32(&tm_pre, pre_save, FQ, d.Lout, d.B, FQ, FTW, false)) return e;
-    if (int e = make_tmap_3d_f32(&tm_xf, x, d.L, d.C, d.B, kFbXW, kFbXRows, false)) return e;
-    FastGy3Args a{w_post, qwts, nullptr, part1, part2, part3, d.B, d.C, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.PA2, p.PB,
-                  timeline_next_slot()};
-    if (int e = launch_fast_gy3_any<true>(tm_gy, tm_qout, tm_pre, tm_xf, a, p, st)) return e;
+    if (fused == 1)
+      if (int e = make_tmap_3d_f32(&tm_xf, x, d.L, d.C, d.B, kFbXW, kFbXRows, false)) return e;
+    FastGy3Args a{w_post, qwts, nullptr, part1, part2, part3, gpre, d.B, d.C, d.O, d.Lout, p.LP, p.tiles_per_utt, p.num_tiles, p.PA1, p.PA2,
+                  p.PB, timeline_next_slot(), 0};
+    if (int e = fused == 1 ? launch_fast_gy3_any<1>(tm_gy, tm_qout, tm_pre, tm_xf, a, p, st)
+                           : launch_fast_gy3_any<2>(tm_gy, tm_qout, tm_pre, tm_pre, a, p, st))
+      return e;
+  }
+  if (fused == 1) {
     FastFinArgs f{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridGy, p.PA2,
                   p.gridGy, p.PB, d.C, d.O, d.Lq, timeline_next_slot(), FastDp{}, 0};
     const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
@@ -1547,12 +1600,12 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     return 0;
   }
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
-  {
+  if (!fused) {
     FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot()};
     if (int e = launch_fast_gy2_any(tm_gy, tm_qout, a, p, st)) return e;
   }
   // 2) adjoint differentiation of the circuit, one window per thread
-  {
+  if (!fused) {
     FastAdjArgs aa{pre_save, gout, qwts, gpre, part2, d.B, d.Lout, p.LP, d.Lq, p.PA2, (long long)W, flag_adj_trig(), timeline_next_slot()};
     const size_t smem = ((size_t)d.Lq * FQ * kGateStride + (size_t)4 * (FQ + d.Lq * 32) * kGyMS) * 4;
     const int adj_spec = option(kOptAdjSpec);
@@ -1577,7 +1630,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   }
   // 4) finalize
   {
-    FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, p.gridAdj, p.PA2,
+    FastFinArgs a{part1, part2, part3, qwts, gw_pre, gb_pre, gqw, gw_post, gb_post, p.gridGy, p.PA1, fused ? p.gridGy : p.gridAdj, p.PA2,
                   p.gridPx, p.PB, d.C, d.O, d.Lq, timeline_next_slot(), FastDp{}, flag_fin_early()};
     const int nblk = p.PA1 / 32 + p.PA2 / 32 + p.PB / 32;
     if (dp && dp->world > 1) {

@@ -6,6 +6,9 @@ Fixtures (all small):
   logmel_30s.npz       vendored output on a 30 s clip, every 61st frame + global stats
   mel_filters_ref.npz  the reference asset's nonzero pattern + values (sparse) for 80/128 mels
   audio_encoder.npz    vendored whisper AudioEncoder (tiny dims) state_dict + input + output
+  quantum_audio_encoder.npz  the vendored AudioEncoder SUBCLASSED exactly as quantum_whisper.py:130-137 does (conv1 / conv2 swapped
+                       for a QuantumConv1d), with the fp64 oracle standing in for the PennyLane layer: state_dict + input + output.
+                       The GPU test loads that state_dict (strict) into qasr_ijcnlp_b200.QuantumAudioEncoder and must reproduce y.
   qconv_kat.json       the known-answer vectors of SURVEY.md 8c (scratch fp64 restatement by the
                        surveyor; PennyLane itself is not installable -> "parity unpinned")
 Inputs are drawn with numpy RandomState so they can be regenerated anywhere.
@@ -18,12 +21,49 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, "/root/reference/whisper")
+from oracle import qconv_oracle as qo  # noqa: E402
 import whisper.audio as wa  # noqa: E402
 import whisper.model as wm  # noqa: E402
 
 
+class OracleQuantumConv1d(torch.nn.Module):
+    """CPU stand-in for the reference layer (quantum_whisper.py:45-128): same constructor, construction order and parameter
+    names; forward = the fp64 oracle (PennyLane is not installable)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, n_qubits=4):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.n_qubits = min(n_qubits, in_channels * kernel_size)
+        self.pre_conv = torch.nn.Linear(in_channels * kernel_size, self.n_qubits)
+        self.post_conv = torch.nn.Linear(self.n_qubits, out_channels)
+        self.quantum_weights = torch.nn.Parameter(torch.randn(self.n_qubits, 3))
+
+    def forward(self, x):
+        p = [t.detach().double() for t in (self.pre_conv.weight, self.pre_conv.bias, self.quantum_weights,
+                                           self.post_conv.weight, self.post_conv.bias)]
+        return qo.qconv1d_forward(x.double(), *p, K=self.kernel_size, S=self.stride, P=self.padding, cast_fp32=True).to(x.dtype)
+
+
+def quantum_audio_encoder_fixture():
+    class QuantumAudioEncoder(wm.AudioEncoder):  # quantum_whisper.py:130-137, verbatim structure
+        def __init__(self, n_mels, n_ctx, n_state, n_head, n_layer, n_qubits=4):
+            super().__init__(n_mels, n_ctx, n_state, n_head, n_layer)
+            self.conv1 = OracleQuantumConv1d(n_mels, n_state, kernel_size=3, padding=1, n_qubits=n_qubits)
+            self.conv2 = OracleQuantumConv1d(n_state, n_state, kernel_size=3, stride=2, padding=1, n_qubits=n_qubits)
+
+    torch.manual_seed(11)
+    enc = QuantumAudioEncoder(n_mels=8, n_ctx=12, n_state=16, n_head=2, n_layer=2).eval()
+    x = torch.randn(2, 8, 24)
+    with torch.no_grad():
+        y = enc(x)
+    sd = {k.replace(".", "__"): v.numpy() for k, v in enc.state_dict().items()}
+    np.savez_compressed(os.path.join(HERE, "quantum_audio_encoder.npz"), x=x.numpy(), y=y.numpy(), **sd)
+
+
 def main():
+    quantum_audio_encoder_fixture()
     rs = np.random.RandomState(1234)
     # ---- log-mel, short clips, full output
     a1 = (0.1 * rs.standard_normal(16000)).astype(np.float32)

@@ -140,3 +140,84 @@ def test_reference_checkpoint_formats_load(tmp_path):
     other = qw.QuantumWhisperClassifier(qw.QuantumWhisper(dims, n_qubits=3), 35)
     with pytest.raises(RuntimeError, match="shape mismatch"):
         ck.load_reference_state_dict(other, sd)
+
+
+def test_quantum_encoder_state_dict_matches_the_vendored_subclass(golden_dir):
+    """`quantum_audio_encoder.npz` is the state_dict of the VENDORED whisper AudioEncoder subclassed exactly as
+    quantum_whisper.py:130-137 does: every key and shape must load (strict) into the B200 QuantumAudioEncoder."""
+    g = np.load(os.path.join(golden_dir, "quantum_audio_encoder.npz"))
+    enc = qw.QuantumAudioEncoder(n_mels=8, n_ctx=12, n_state=16, n_head=2, n_layer=2, n_qubits=4)
+    sd = {k.replace("__", "."): torch.from_numpy(g[k]) for k in g.files if k not in ("x", "y")}
+    assert set(sd) == set(enc.state_dict())
+    enc.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc(torch.from_numpy(g["x"]))  # the product path has no CPU fallback
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/whisper"), reason="vendored whisper only exists in the build container")
+def test_drop_in_inside_the_real_vendored_audio_encoder():
+    """north_star: "a drop-in inside the official whisper/ AudioEncoder".  Subclass the vendored class the way
+    quantum_whisper.py:130-137 does, with the B200 QuantumConv1d: construction, positional call form, parameter names,
+    name-based freezing and `.to()` behave as in the reference; its forward reaches the layer (which refuses CPU tensors)."""
+    import sys
+    sys.path.insert(0, "/root/reference/whisper")
+    try:
+        import whisper.model as wm
+    finally:
+        sys.path.pop(0)
+
+    class QuantumAudioEncoder(wm.AudioEncoder):
+        def __init__(self, n_mels, n_ctx, n_state, n_head, n_layer, n_qubits=4):
+            super().__init__(n_mels, n_ctx, n_state, n_head, n_layer)
+            self.conv1 = qw.QuantumConv1d(n_mels, n_state, kernel_size=3, padding=1, n_qubits=n_qubits)
+            self.conv2 = qw.QuantumConv1d(n_state, n_state, kernel_size=3, stride=2, padding=1, n_qubits=n_qubits)
+
+    torch.manual_seed(0)
+    real = QuantumAudioEncoder(8, 12, 16, 2, 2)
+    mirror = qw.QuantumAudioEncoder(8, 12, 16, 2, 2)
+    assert [n for n, _ in real.named_parameters()] == [n for n, _ in mirror.named_parameters()]
+    assert {k: tuple(v.shape) for k, v in real.state_dict().items()} == {k: tuple(v.shape) for k, v in mirror.state_dict().items()}
+    mirror.load_state_dict(real.state_dict(), strict=True)
+    qw.freeze_non_quantum_layers(real)
+    assert {n for n, p in real.named_parameters() if p.requires_grad} == {
+        f"conv{i}.{s}" for i in (1, 2) for s in ("quantum_weights", "pre_conv.weight", "pre_conv.bias", "post_conv.weight", "post_conv.bias")}
+    assert real.to("cpu") is real
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        real(torch.randn(1, 8, 24))  # whisper/model.py:193 calls self.conv1(x): the B200 layer is what runs
+
+
+def test_char_asr_harness_vocab_shapes_and_one_step():
+    """SURVEY.md 8-f2 (config-3 harness): vocabulary ids as librispeech_asr.py:102-117, teacher-forcing shapes,
+    CE(ignore_index=0) as train_quantum_whisper_asr.py:133, and one optimisation step lowers the loss."""
+    assert qw.CHAR_VOCAB[:4] == ["<PAD>", "<UNK>", "<START>", "<END>"]
+    assert len(qw.CHAR_VOCAB) == 32 and len(set(qw.CHAR_VOCAB)) == 32
+    idx = {c: i for i, c in enumerate(qw.CHAR_VOCAB)}
+    text = "the cat's hat"
+    ids = [idx["<START>"]] + [idx.get(ch, idx["<UNK>"]) for ch in text] + [idx["<END>"]]
+    assert min(ids) >= 2 and idx.get("~", idx["<UNK>"]) == 1  # unknown characters map to <UNK>
+    T = 100  # librispeech_asr.py:44 max_text_length
+    tokens = torch.zeros(2, T, dtype=torch.long)
+    tokens[0, :len(ids)] = torch.tensor(ids)
+    tokens[1, :5] = torch.tensor([2, 10, 11, 12, 3])
+    torch.manual_seed(0)
+    head = qw.CharASRHead(n_state=16, hidden=32, num_layers=2)
+    feats = torch.randn(2, 12, 16)
+    logits = head(feats, tokens[:, :-1])
+    assert logits.shape == (2, T - 1, len(qw.CHAR_VOCAB))
+    crit = torch.nn.CrossEntropyLoss(ignore_index=0)
+    opt = torch.optim.AdamW(head.parameters(), lr=1e-2, weight_decay=0.01)
+
+    def loss_fn():
+        return crit(head(feats, tokens[:, :-1]).reshape(-1, len(qw.CHAR_VOCAB)), tokens[:, 1:].reshape(-1))
+
+    l0 = loss_fn()
+    assert torch.isfinite(l0) and abs(l0.item() - np.log(32)) < 1.0
+    for _ in range(5):
+        opt.zero_grad()
+        loss = loss_fn()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(head.parameters(), 1.0)  # train_quantum_whisper_asr.py:175
+        opt.step()
+    assert loss_fn().item() < l0.item() - 0.05
+    # gradient does not flow from padded positions: the embedding row of <PAD> stays zero (padding_idx=0)
+    assert head.embed.weight[0].abs().max().item() == 0.0

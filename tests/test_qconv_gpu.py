@@ -201,8 +201,9 @@ def _set_opt(lib, name, value):
 @pytest.mark.parametrize("B,C,L,O", [(16, 80, 3000, 384), (2, 80, 3000, 384), (3, 80, 260, 384), (1, 40, 1028, 8), (5, 96, 72, 200),
                                      (7, 33, 64, 64)])
 def test_fused_backward_data_layer(cuda, B, C, L, O):
-    """A data layer (its input needs no gradient: conv1 of the stem) at small batch runs its whole backward in ONE kernel
-    (gy pass on the tensor pipe + adjoint + pre_conv^T, `fast_bwd_gy3_kernel<.., true>`).  All five parameter gradients against the
+    """A data layer (its input needs no gradient: conv1 of the stem) at small batch can run its whole backward in ONE kernel
+    (gy pass on the tensor pipe + adjoint warp + pre_conv^T, `fast_bwd_gy3_kernel<.., 1>`, option BWD_FUSED=1; measured slower
+    than the three kernels on B200 and therefore off by default).  All five parameter gradients against the
     fp64 oracle (same bound as test_layer_f32: 5e-5 relative to max(1, |ref|)) and against the three-kernel path."""
     _lib, qc = _mods()
     lib = _lib.load()
@@ -227,12 +228,75 @@ def test_fused_backward_data_layer(cuda, B, C, L, O):
             launches[fused] = _lib.launch_count() - n0
             res[fused] = dict(zip(["w_pre", "b_pre", "qweights", "w_post", "b_post"], [t.cpu().double() for t in grads]))
     finally:
-        _set_opt(lib, "BWD_FUSED", 1)
+        _set_opt(lib, "BWD_FUSED", 0)
     assert launches == {1: 2, 0: 4}, launches  # fused + finalize vs gy / adjoint / pre_conv^T / finalize
     for k in ("w_pre", "b_pre", "qweights", "w_post", "b_post"):
         assert _rel(res[1][k], ref[k]) <= 5e-5, k
         assert _rel(res[0][k], ref[k]) <= 5e-5, k
         assert _rel(res[1][k], res[0][k]) <= 2e-5, k
+
+
+def _abi_forward_backward(lib, _lib, cuda, x, params, gy, K, S, P, need_gx=True):
+    """One forward + backward straight through the C ABI; returns y, pre_save (2, W, q) and the gradients."""
+    B, C, L = x.shape
+    O, q = params[3].shape
+    Lo = qo.out_length(L, K, S, P)
+    dev = [t.to(cuda).contiguous() for t in (x, *params)]
+    y = torch.empty(B, O, Lo, device=cuda)
+    pre_save = torch.empty(2, B * Lo, q, device=cuda)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P_ = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(lib.qw_conv1d_forward(*[P_(t) for t in dev], P_(y), P_(pre_save), B, C, L, K, S, P, O, q, 1, 0, st), "qw_conv1d_forward")
+    gyd = gy.to(cuda).contiguous()
+    gx = torch.empty_like(dev[0]) if need_gx else None
+    grads = [torch.empty_like(t) for t in dev[1:]]
+    n = lib.qw_conv1d_workspace_bytes(B, C, L, K, S, P, O, q, 1, 4)
+    ws = torch.empty(n, device=cuda, dtype=torch.uint8)
+    _lib.check(lib.qw_conv1d_backward(P_(gyd), P_(dev[0]), P_(pre_save), P_(dev[1]), P_(dev[3]), P_(dev[4]), P_(gx), *[P_(t) for t in grads],
+                                      P_(ws), n, B, C, L, K, S, P, O, q, 1, 0, st), "qw_conv1d_backward")
+    torch.cuda.synchronize()
+    out = dict(zip(["w_pre", "b_pre", "qweights", "w_post", "b_post"], [t.cpu().double() for t in grads]))
+    if need_gx:
+        out["x"] = gx.cpu().double()
+    return y.cpu().double(), pre_save.cpu().double(), out
+
+
+@pytest.mark.parametrize("layer", ["conv1", "conv2"])
+def test_stem_layers_batch16_full_parity(cuda, layer):
+    """BASELINE.json configs[1]/[2] stem shapes at the bench batch (16): every output of the fast path against the fp64 oracle at
+    FULL size -- y, the saved pre_conv outputs (plane 0) and per-window <Z_i> (plane 1, <= 1e-5 abs: the north_star bound on
+    expectation values), and all gradients (5e-5 relative to max(1, |ref|), summed quantities) -- for the default backward
+    (tensor-pipe gy pass, adjoint kernel, pre_conv^T kernel) and for the two forms with the adjoint inside the gy kernel
+    (BWD_FUSED = 1 / 2: measured slower at batch 16, kept as A/B switches)."""
+    _lib, _ = _mods()
+    lib = _lib.load()
+    C, S, need_gx = (80, 1, False) if layer == "conv1" else (384, 2, True)
+    B, L, O = 16, 3000, 384
+    params64 = qo.make_params(C, O, 3, 4, seed=31)
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(B, C, L, generator=g)
+    Lo = qo.out_length(L, 3, S, 1)
+    gy = torch.randn(B, O, Lo, generator=g)
+    params = [p.float() for p in params64]
+    p64 = [p.double() for p in params]
+    yo, preo, qouto = qo.qconv1d_forward(x.double(), *p64, K=3, S=S, P=1, return_intermediates=True)
+    ref = qo.qconv1d_grads(x.double(), p64, gy.double(), 3, S, 1, need_gx=need_gx)
+    try:
+        for fused in (0, 1, 2):
+            _set_opt(lib, "BWD_FUSED", fused)
+            y, pre_save, got = _abi_forward_backward(lib, _lib, cuda, x, params, gy, 3, S, 1, need_gx=need_gx)
+            assert (y - yo).abs().max().item() <= 5e-5
+            # plane 0: pre_conv outputs (fp32 sums of C*K products of O(1) terms): 2e-6 * sqrt(C*K) abs
+            assert (pre_save[0] - preo.reshape(-1, 4)).abs().max().item() <= 2e-6 * (3 * C) ** 0.5
+            # plane 1: <Z_i> per window, evaluated by the kernel on ITS fp32 pre_conv output -> compare with the oracle circuit on
+            # exactly those values: the north_star's 1e-5 bound on expectation values
+            z_ref = qo.circuit_expvals(pre_save[0].contiguous(), p64[2])
+            assert (pre_save[1] - z_ref).abs().max().item() <= 1e-5
+            assert (pre_save[1] - qouto.reshape(-1, 4)).abs().max().item() <= 5e-5  # and end to end from x
+            for k, v in got.items():
+                assert _rel(v, ref[k]) <= 5e-5, (k, fused)
+    finally:
+        _set_opt(lib, "BWD_FUSED", 0)
 
 
 @pytest.mark.parametrize("mma", [1, 0])
@@ -322,6 +386,13 @@ def test_config1_full_size_parity(cuda):
         for n, gr in zip(names, grads):
             assert _rel(gr.cpu().double(), ref[key[n]]) <= 5e-5, n
         m = m.to("cpu")
+        # per-window <Z_i> (pre_save plane 1) on the kernel's own fp32 pre_conv output (plane 0): <= 1e-5 abs
+        _lib, _ = _mods()
+        _, pre_save, _ = _abi_forward_backward(_lib.load(), _lib, cuda, xin, [p.detach() for p in params], gy, 3, 1, 1, need_gx=True)
+        yo, preo, qouto = qo.qconv1d_forward(xin.double(), *p64, K=3, S=1, P=1, return_intermediates=True)
+        assert (pre_save[0] - preo.reshape(-1, 4)).abs().max().item() <= 2e-6 * 240 ** 0.5
+        assert (pre_save[1] - qo.circuit_expvals(pre_save[0].contiguous(), p64[2])).abs().max().item() <= 1e-5
+        assert (pre_save[1] - qouto.reshape(-1, 4)).abs().max().item() <= 5e-5
 
 
 def test_full_size_properties_conv2(cuda):

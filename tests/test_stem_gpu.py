@@ -94,3 +94,27 @@ def test_fused_stem_rejects_other_regimes(cuda):
     assert not fused_stem_eligible(c1, c3, torch.zeros(1, 80, 3000, device=cuda))           # n_qubits != 4
     with pytest.raises(ValueError):
         fused_stem_forward(c1, c3, torch.zeros(1, 80, 3000, device=cuda))
+
+
+def test_quantum_audio_encoder_reproduces_the_vendored_subclass(cuda, golden_dir):
+    """north_star "drop-in inside the official whisper/ AudioEncoder": tests/golden/quantum_audio_encoder.npz was produced in the
+    build container by the VENDORED whisper.model.AudioEncoder subclassed exactly as quantum_whisper.py:130-137 does (conv1 / conv2
+    swapped for a QuantumConv1d whose forward is the fp64 oracle, PennyLane being uninstallable).  Loading that state_dict
+    (strict) into the B200 encoder must reproduce its output, both through the training path (two operators, autograd on) and
+    the fused inference stem.  Bound: 1e-4 abs after two transformer blocks + LayerNorm (the stem itself is <= 5e-5)."""
+    import os
+
+    import qasr_ijcnlp_b200 as qw
+
+    g = np.load(os.path.join(golden_dir, "quantum_audio_encoder.npz"))
+    enc = qw.QuantumAudioEncoder(n_mels=8, n_ctx=12, n_state=16, n_head=2, n_layer=2, n_qubits=4)
+    enc.load_state_dict({k.replace("__", "."): torch.from_numpy(g[k]) for k in g.files if k not in ("x", "y")}, strict=True)
+    enc = enc.to(cuda).eval()
+    x = torch.from_numpy(g["x"]).to(cuda)
+    want = torch.from_numpy(g["y"])
+    y_train = enc(x)  # grad enabled: operator-by-operator path
+    assert y_train.requires_grad
+    assert (y_train.detach().cpu() - want).abs().max().item() <= 1e-4
+    with torch.no_grad():
+        y_inf = enc(x)
+    assert (y_inf.cpu() - want).abs().max().item() <= 1e-4
