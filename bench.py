@@ -306,6 +306,54 @@ def algorithmic_bytes(kernel, layer, B):
     return 0.0
 
 
+def make_config(B, world, nsets):
+    """The workload both arms are measured on (the reference arm times a bounded sample of it: `cpu_baseline.sample`)."""
+    return {
+        "workload": f"Whisper-Tiny quantum stem: QuantumConv1d conv1(80->384,k3,s1,p1)+conv2(384->384,k3,s2,p1) "
+                    f"fwd+bwd, n_qubits=4, batch {B}/GPU x 80 mel x 3000 frames (BASELINE configs[1]/[2] shape)",
+        "windows_per_step_per_gpu": B * WINDOWS_PER_UTT, "batch_per_gpu": B, "n_qubits": Q, "n_layers": 1,
+        "l2": f"GPU arm: {nsets} rotating buffer sets ({nsets} x {runner_bytes(B) / 1e6:.0f} MB > 126 MB L2), CUDA graphs of {nsets} consecutive "
+              f"steps (one per buffer set); "
+              f"CPU reference arm: not applicable",
+        "parallelism": f"dp{world} (batch shard over {world} GPU(s); forward: no collective; training: one mean of the gradients)",
+    }
+
+
+def check_dp_parity(runner, world, dev):
+    """One step with the configured gradient collective (NVLink peer-memory kernels) and one with the plain backward followed by
+    torch.distributed.all_reduce(AVG) (NCCL) on the same inputs and parameters: max error relative to the largest reference
+    entry, bitwise equality of the result across ranks, and the collectives' status words.  (The reference trains single
+    process, train_quantum_whisper.py:195-214: this is the correctness proof of what replaces DistributedDataParallel.)"""
+    import torch.distributed as dist
+
+    runner.step(0)
+    torch.cuda.synchronize()
+    got = runner.params.flat_grads.clone()
+    saved = (runner.fused_dp, runner.hybrid, runner.allreduce, runner.allreduce_split)
+    runner.fused_dp = runner.hybrid = runner.allreduce = runner.allreduce_split = None
+    try:
+        runner.step(0)
+        torch.cuda.synchronize()
+        ref = runner.params.flat_grads.clone()
+    finally:
+        runner.fused_dp, runner.hybrid, runner.allreduce, runner.allreduce_split = saved
+    local_max = ref.abs().max().item()
+    dist.all_reduce(ref, op=dist.ReduceOp.AVG)
+    err = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+    gathered = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(gathered, got)
+    bitwise = all(torch.equal(gathered[0], t) for t in gathered)
+    status = 0
+    for obj in list((runner.fused_dp or {}).values()) + ([runner.hybrid[0]] if runner.hybrid else []) + \
+            (list(runner.allreduce_split[:2]) if runner.allreduce_split else []):
+        status |= int(obj.status())
+    t = torch.tensor([err, 0.0 if bitwise else 1.0, float(status)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"max_rel_err": float(t[0].item()), "bitwise_equal_across_ranks": bool(t[1].item() == 0.0), "status_word": int(t[2].item()),
+            "reference": "qw_conv1d_backward + torch.distributed.all_reduce(AVG) (NCCL) on the same inputs",
+            "tolerance": 1e-6, "grad_floats": int(got.numel()), "local_grad_absmax": local_max}
+
+
 def time_events(fn, steps):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -336,6 +384,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pin_to_gpu_numa_node(local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     from qasr_ijcnlp_b200 import _lib
@@ -382,6 +431,16 @@ def run_b200(args):
             runner.allreduce = lambda t: torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG)
             collective = f"NCCL all_reduce(AVG) of the {4 * n} B bucket, in the step's CUDA graph ({type(e).__name__}: {str(e)[:80]})"
 
+    # ---- data-parallel parity (driver-visible): the configured collective against plain backward + NCCL all_reduce(AVG)
+    dp_parity = None
+    if world > 1:
+        dp_parity = check_dp_parity(runner, world, dev)
+        if dp_parity["max_rel_err"] > 1e-6 or not dp_parity["bitwise_equal_across_ranks"] or dp_parity["status_word"] != 0:
+            if rank == 0:
+                emit({"metric": METRIC, "error": "data-parallel gradient parity failed", "dp_parity": dp_parity, "n_gpus": world})
+            torch.distributed.destroy_process_group()
+            sys.exit(3)
+
     # ---- warm up eagerly (also sets function attributes), then capture one CUDA graph per buffer set
     for i in range(2):
         n_before = _lib.launch_count()
@@ -397,6 +456,13 @@ def run_b200(args):
             with torch.cuda.graph(g, stream=side):
                 runner.step(s_)
             gs.append(g)
+        # `nsets` consecutive steps (one per buffer set) as ONE graph: the boundary between two steps becomes an ordinary
+        # kernel-to-kernel edge of the programmatic-dependent-launch chain instead of a graph-launch gap (~3.5 us on B200)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for s_ in range(nsets):
+                runner.step(s_)
+        gs.append(g)
         return gs
 
     post = None
@@ -421,14 +487,30 @@ def run_b200(args):
         if post is not None:
             post(runner.params.flat_grads)
 
+    def replay_steps(n):
+        """exactly n steps: blocks of `nsets` steps through the multi-step graph, the remainder step by step"""
+        if post is not None:
+            for i in range(n):
+                replay(i)
+            return
+        q, r = divmod(n, nsets)
+        for _ in range(q):
+            graphs[nsets].replay()
+        for i in range(r):
+            graphs[i].replay()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    for i in range(Wm):
-        replay(i)
+    replay_steps(max(Wm, nsets))
     barrier(world)
-    ms = time_events(replay, K)
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record()
+    replay_steps(K)
+    ev_b.record()
+    torch.cuda.synchronize()
+    ms = ev_a.elapsed_time(ev_b)
     barrier(world)
     ms = max_over_ranks(ms, world, dev)
     value = world * windows_per_step * K / (ms * 1e-3)
@@ -455,18 +537,40 @@ def run_b200(args):
     step_kernel_ms = sum(kern.values())
     dom = max(kern, key=lambda k: kern[k])
     dom_bytes = algorithmic_bytes(dom[1], dom[0], B)
-    achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9
+    # The dominant kernel's AVERAGE LAUNCH DURATION, CUDA events on the launching stream: `reps` launches of that C-ABI call back
+    # to back over the rotating buffer sets between two events (the way the kernel runs inside the step: queued behind its
+    # predecessor, programmatic dependent launch on), divided by `reps`.  The single-launch bracket (an event pair around ONE
+    # launch, qw_profile_*) is kept beside it: it adds ~3-5 us of launch / event latency that no step ever pays.
+    dom_ms, dom_how = kern[dom], "CUDA events around one launch (qw_profile_*)"
+    if dom[1] == "qconv_fwd_kernel":
+        reps = max(40, K)
+        for i in range(8):
+            runner.fwd(dom[0], i % nsets)
+        dom_ms = time_events(lambda i: runner.fwd(dom[0], i % nsets), reps) / reps
+        dom_how = (f"CUDA events around {reps} back-to-back launches of qw_conv1d_forward[{dom[0]}] over {nsets} rotating buffer sets "
+                   f"/ {reps} (average launch duration in stream order)")
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    symbols = {}
+    for layer in ("conv1", "conv2"):  # the symbols an ncu launch list shows, per layer (template arguments differ)
+        runner.fwd(layer, 0)
+        runner.bwd(layer, 0)
+        for kname, sym in _lib.kernel_symbols().items():
+            symbols[(layer, kname)] = sym
+    torch.cuda.synchronize()
     traffic = load_traffic().get(f"{dom[0]}.{dom[1]}")
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": traffic, "kernel": f"{dom[1]}[{dom[0]}]", "kernel_ms": round(kern[dom], 5),
+        "traffic": traffic, "kernel": f"qw::{symbols.get(dom, dom[1])}", "layer": dom[0], "kernel_ms": round(dom_ms, 5), "how": dom_how,
+        "kernel_ms_single_launch_bracket": round(kern[dom], 5),
+        "frac_single_launch_bracket": round(dom_bytes / (kern[dom] * 1e-3) / 1e9 / peak, 4),
         "kernel_share_of_step": round(kern[dom] / step_kernel_ms, 4), "algorithmic_bytes_per_launch": dom_bytes,
         "peak_source": peak_src,
     }
     kernels = {}
     for (layer, kname), t in sorted(kern.items()):
         ab = algorithmic_bytes(kname, layer, B)
-        kernels[f"{layer}.{kname}"] = {"ms": round(t, 5), "share": round(t / step_kernel_ms, 4),
+        kernels[f"{layer}.{kname}"] = {"symbol": "qw::" + symbols.get((layer, kname), kname), "ms": round(t, 5),
+                                       "share": round(t / step_kernel_ms, 4),
                                        "GBps": round(ab / (t * 1e-3) / 1e9, 1) if ab else None,
                                        "frac": round(ab / (t * 1e-3) / 1e9 / peak, 4) if ab else None}
     # whole-step roofline: algorithmic bytes of the step (3712 + 12288/2 ... per window) / step time
@@ -475,11 +579,26 @@ def run_b200(args):
 
     # ---- where the step goes INSIDE the replayed graph (CUDA events cannot see there): %globaltimer stamps per kernel
     in_graph = None
-    if world == 1:
-        try:
-            in_graph = in_graph_timeline(runner, nsets, dev, B, peak)
-        except Exception as e:
-            in_graph = {"error": repr(e)[:200]}
+    try:
+        in_graph = in_graph_timeline(runner, nsets, dev, B, peak, world=world)
+        if world == 1:
+            # the same step with the arithmetic of the three streaming kernels removed (A/B switches DBG_FWD / DBG_GY: TMA
+            # pipelines, barriers, stores and launch structure unchanged, results garbage): what the memory system and the
+            # kernel boundaries alone cost at this batch -- the floor `step_us` can be compared with
+            lib = _lib.load()
+            try:
+                lib.qw_set_option(b"DBG_FWD", 7)
+                lib.qw_set_option(b"DBG_GY", 1)
+                floor = in_graph_timeline(runner, nsets, dev, B, peak, world=world)
+            finally:
+                lib.qw_set_option(b"DBG_FWD", 0)
+                lib.qw_set_option(b"DBG_GY", 0)
+            in_graph["zero_compute_floor"] = {
+                "step_us": floor["step_us"], "kernels_us": {k: v["us"] for k, v in floor["kernels"].items()},
+                "step_roofline_frac": round(step_bytes / (floor["step_us"] * 1e-6) / 1e9 / peak, 4),
+                "how": "same graph, forward / gy kernels with their FMAs / MMAs / circuit removed (qw_set_option DBG_FWD=7, DBG_GY=1)"}
+    except Exception as e:
+        in_graph = {"error": repr(e)[:200]}
 
     # ---- e2e through the nn.Module API with host buffers
     e2e = run_e2e(runner, B, K, Wm, world, dev, graphed=not args.e2e_eager)
@@ -508,10 +627,9 @@ def run_b200(args):
 
     # ---- clocks: make sure the sampler saw the workload for >= 1.5 s
     n_extra = min(200000, int(1.5 / max(1e-6, ms / K * 1e-3)))  # same count on every rank (ms is the max over ranks)
-    for i in range(n_extra):
-        replay(i)
-        if i % 64 == 63:
-            torch.cuda.synchronize()
+    for i in range(0, n_extra, 64):
+        replay_steps(64)
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else {}
     barrier(world)
@@ -525,15 +643,10 @@ def run_b200(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"Whisper-Tiny quantum stem: QuantumConv1d conv1(80->384,k3,s1,p1)+conv2(384->384,k3,s2,p1) "
-                            f"fwd+bwd, n_qubits=4, batch {B}/GPU x 80 mel x 3000 frames (BASELINE configs[1]/[2] shape)",
-                "windows_per_step_per_gpu": windows_per_step, "batch_per_gpu": B, "n_qubits": Q, "n_layers": 1,
-                "l2": f"{nsets} rotating buffer sets ({nsets} x {runner_bytes(B) / 1e6:.0f} MB > 126 MB L2)",
-                "launch": f"one CUDA graph per step ({own_per_step} kernels)",
-                "parallelism": f"dp{world} (batch shard; forward: no collective; gradients: {collective})",
-            },
+            "config": make_config(B, world, nsets),
+            "collective": collective, "kernels_per_step": own_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "dp_parity": dp_parity,
             "step_roofline_frac": round(step_frac, 4), "kernels": kernels, "in_graph": in_graph,
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
             "stem_infer": stem_inf, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
@@ -566,7 +679,7 @@ def step_kernel_names(runner):
     return names
 
 
-def in_graph_timeline(runner, nsets, dev, B, peak, reps=20):
+def in_graph_timeline(runner, nsets, dev, B, peak, reps=20, world=1):
     """Per-kernel critical-path times inside the replayed step graph (qw_timeline_set: every kernel records min(CTA start) /
     max(CTA end) of %globaltimer).  delta = end of the kernel - end of its predecessor, i.e. what the kernel adds to the step
     with the programmatic-dependent-launch overlap it really has; median over `reps` single replays.  Explains `value`; the
@@ -595,14 +708,20 @@ def in_graph_timeline(runner, nsets, dev, B, peak, reps=20):
         for r in range(reps):
             buf[0::2] = torch.iinfo(torch.int64).max
             buf[1::2] = 0
-            torch.cuda.synchronize()
+            barrier(world)  # all ranks replay together (the step holds the gradient exchange)
             graphs[r % nsets].replay()
             torch.cuda.synchronize()
             t = buf.cpu().tolist()
             rows.append([(t[2 * k], t[2 * k + 1]) for k in range(per_step)])
     finally:
         lib.qw_timeline_set(None, 0)
+    barrier(world)
     names = step_kernel_names(runner)
+    # kernels without a timeline slot (the one-shot all-reduce kernel of the hybrid collective) leave their slot untouched
+    used = [k for k in range(per_step) if rows[0][k][1] > 0]
+    if len(used) == len(names):
+        rows = [[r[k] for k in used] for r in rows]
+        per_step = len(used)
     if per_step != len(names):
         names = [f"k{k}" for k in range(per_step)]
     algo = {}
@@ -623,6 +742,47 @@ def in_graph_timeline(runner, nsets, dev, B, peak, reps=20):
     return {"step_us": round(total, 2), "kernels": out,
             "how": "median of %d single graph replays; us a kernel adds to the step = its last CTA end - its predecessor's last CTA "
                    "end (%%globaltimer); frac = algorithmic bytes / that time / HBM peak" % reps}
+
+
+def host_topology(dev):
+    """NUMA node of the GPU's PCIe function and of this process' allowed CPUs (the pinned staging buffers are first-touched by
+    this process, so they live where it runs)."""
+    out = {}
+    try:
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev).pci_domain_id
+        devn = torch.cuda.get_device_properties(dev).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devn:02x}.0/numa_node"
+        out["gpu_numa_node"] = int(open(path).read().strip())
+    except Exception:
+        out["gpu_numa_node"] = None
+    try:
+        out["cpus_allowed"] = len(os.sched_getaffinity(0))
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        out["numa_nodes"] = len(nodes)
+    except Exception:
+        pass
+    return out
+
+
+def pin_to_gpu_numa_node(local):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, when the box has several."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def runner_bytes(B):
@@ -743,12 +903,41 @@ def run_e2e(runner, B, K, Wm, world, dev, graphed=True):
     torch.cuda.synchronize()
     ms = max_over_ranks(a.elapsed_time(b), world, dev)
     barrier(world)
+
+    loss_value = float(host_out[(K - 1) % nhost][0])
+    # copy-only control leg: the SAME loop with the compute taken out (H2D of every step's input from pinned memory, D2H of the
+    # result vector): the ceiling the host link of this box puts on the e2e number at this GPU count
+    flat_dummy = torch.zeros(1 + n_grad, device=dev)
+
+    def copy_loop(n):
+        for s_ in range(2):
+            ev_free[s_].record(main)
+        issue_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_copy(i + 1)
+            slot = i % 2
+            main.wait_event(ev_copied[slot])
+            ev_free[slot].record(main)
+            host_out[i % nhost].copy_(flat_dummy, non_blocking=True)
+
+    copy_loop(Wm)
+    barrier(world)
+    a.record()
+    copy_loop(K)
+    b.record()
+    torch.cuda.synchronize()
+    ms_copy = max_over_ranks(a.elapsed_time(b), world, dev)
+    barrier(world)
+    h2d = B * N_MELS * N_FRAMES * 4
     val = world * B * WINDOWS_PER_UTT * K / (ms * 1e-3)
-    return {"value": round(val, 1), "unit": UNIT, "h2d_bytes_per_step": B * N_MELS * N_FRAMES * 4,
+    return {"value": round(val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": 4 * (1 + n_grad), "ms_per_step": round(ms / K, 5),
+            "copy_only_ms": round(ms_copy / K, 5), "h2d_GBps": round(h2d / (ms_copy / K * 1e-3) / 1e9, 2),
+            "copy_bound_frac": round(ms_copy / ms, 4), "host": host_topology(dev),
             "api": api + " + MSE-style loss, torch.autograd, pinned host in/out, H2D double-buffered on a copy stream" +
                    dp_note,
-            "loss": float(host_out[(K - 1) % nhost][0])}
+            "loss": loss_value}
 
 
 def run_encoder_fwd(B, K, dev, world):
@@ -854,11 +1043,37 @@ def run_encoder_train(B, K, dev, world, rank):
 
 
 # --------------------------------------------------------------------------------------------- CPU legs
+_PENNYLANE_REF = "unprobed"
+
+
+def _reference_kind():
+    """"reference" when the unmodified /root/reference QuantumConv1d can run here (PennyLane importable: SURVEY.md section 7 step 1),
+    else "port" (the literal-loop restatement)."""
+    global _PENNYLANE_REF
+    if _PENNYLANE_REF == "unprobed":
+        import oracle
+
+        _PENNYLANE_REF = oracle.pennylane_reference()
+    return "reference" if _PENNYLANE_REF is not None else "port"
+
+
 def _literal_step(layers_cols, seed=0):
-    """One bounded sample of the stem through the literal-loop restatement of the reference (fwd + bwd)."""
+    """One bounded sample of the stem through the reference's own layer when PennyLane is importable, else through the
+    literal-loop restatement of it (fwd + bwd)."""
     from oracle import qconv_oracle as qo
 
     n = 0
+    if _reference_kind() == "reference":
+        for name, cols in layers_cols.items():
+            cfg = LAYERS[name]
+            torch.manual_seed(seed)
+            m = _PENNYLANE_REF(cfg["C"], cfg["O"], cfg["K"], stride=cfg["S"], padding=cfg["P"], n_qubits=Q)
+            Lneed = (cols - 1) * cfg["S"] + cfg["K"] - 2 * cfg["P"]
+            x = torch.randn(2, cfg["C"], max(1, Lneed), requires_grad=cfg["need_gx"])
+            y = m(x)
+            y.square().sum().backward()
+            n += 2 * y.shape[-1]
+        return n
     for name, cols in layers_cols.items():
         cfg = LAYERS[name]
         params = [p.requires_grad_(True) for p in qo.make_params(cfg["C"], cfg["O"], cfg["K"], Q, seed=seed)]
@@ -882,7 +1097,7 @@ def cpu_baseline(target_s=12.0):
     t0 = time.perf_counter()
     n = _literal_step(cols)
     dt = time.perf_counter() - t0
-    out = {"value": round(n / dt, 2), "unit": UNIT, "cores": cores, "kind": "port",
+    out = {"value": round(n / dt, 2), "unit": UNIT, "cores": cores, "kind": _reference_kind(),
            "sample": f"literal-loop fp64 restatement of quantum_whisper.py:107-126 (PennyLane unavailable), fwd+bwd, "
                      f"batch 2, first {cols['conv1']} conv1 + {cols['conv2']} conv2 output columns = {n} windows in {dt:.1f} s; "
                      f"torch threads={cores}, os.cpu_count()={os.cpu_count()} (the loop is scalar Python: ~1 core busy)"}
@@ -928,14 +1143,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = n / dt
     sample = (f"literal-loop fp64 restatement of quantum_whisper.py:107-126 (PennyLane unavailable), fwd+bwd, batch 2, "
-              f"{cols['conv1']} conv1 + {cols['conv2']} conv2 output columns per step = {n // max(1, K)} windows/step")
+              f"{cols['conv1']} conv1 + {cols['conv2']} conv2 output columns per step = {n // max(1, K)} windows/step: a bounded "
+              f"sample of the batch-{args.batch} workload (the cost per window is constant in the reference's Python loop)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": Wm, "ms_per_step": round(dt / max(1, K) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Whisper-Tiny quantum stem conv1+conv2 fwd+bwd, n_qubits=4 (bounded sample of the "
-                               "batch-16 workload; cost per window is constant in the reference's Python loop)"},
-        "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": make_config(args.batch, world, args.nsets),
+        "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": _reference_kind(), "sample": sample},
         "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)

@@ -42,6 +42,8 @@ long long qw_launch_count(void);
 void qw_profile_enable(int on);
 int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset);
 const char* qw_kernel_name(int kernel_id);
+/* The kernel symbol (as ncu prints it, e.g. "fast_fwd_kernel<2, 64>") last launched under that id; "" if none yet. */
+const char* qw_kernel_symbol(int kernel_id);
 /* Debug timeline: register a caller-owned DEVICE buffer of 2*nslots uint64 (pre-filled by the caller with ~0 for even and 0 for
  * odd entries).  Every fast-path QuantumConv1d kernel launched afterwards takes the next slot (round robin from 0) and records
  * min(CTA start) / max(CTA end) of %globaltimer in nanoseconds there -- also inside a replayed CUDA graph, which events cannot
@@ -88,8 +90,10 @@ int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_
  * peer_bufs[r] is rank r's receive buffer as seen from the calling process, peer_flags[rank] the caller's own bookkeeping
  * buffer (the other entries are ignored).  Each rank stores (epoch, value) words straight into its peers' buffers over NVLink.
  * After the call (in stream order) gw_pre ... gb_post hold scale * sum over ranks, bitwise identical on every rank; gx stays
- * local.  All ranks must call it the same number of times with the same shapes.  A peer that never arrives makes the kernel
- * give up after ~1 s, keep the local gradient and set the last bookkeeping word to 1 (never hangs).  Fast-path regime only
+ * local.  All ranks must call it the same number of times with the same shapes.  Like an NCCL collective the kernel WAITS for a
+ * late peer (checkpointing, evaluation, a data-loader stall); a peer that stays away longer than the DP_TIMEOUT_MS option (default
+ * 600 000 ms, 0 = forever; qw_set_option) makes it set the last bookkeeping word to 1 and TRAP -- the CUDA context fails loudly,
+ * it never continues with an un-averaged gradient.  Fast-path regime only
  * (-2 otherwise: use qw_conv1d_backward + qw_grads_allreduce_p2p / NCCL).  world == 1: plain backward. */
 size_t qw_conv1d_dp_buffer_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world);
 size_t qw_conv1d_dp_flag_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world);
@@ -146,8 +150,9 @@ int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* 
  * torch.distributed._symmetric_memory); peer_flags[rank] is the caller's own zero-initialised bookkeeping array
  * (qw_grads_allreduce_p2p_flag_bytes(world) bytes; the other entries are ignored).  Each rank stores (epoch, value) words
  * straight into its peers' buffers (no fence, no remote read).  Every rank must enqueue the call the same number of times; the
- * kernel keeps its epoch in the bookkeeping array, so it is graph-capturable.  A peer that never arrives makes the kernel give
- * up after ~1 s and set the last bookkeeping word to 1 (no hang). */
+ * kernel keeps its epoch in the bookkeeping array, so it is graph-capturable.  Like NCCL it waits for a late peer; a peer that
+ * stays away longer than the DP_TIMEOUT_MS option (default 600 000 ms, 0 = forever) makes it set the last bookkeeping word to 1 and
+ * trap (loud launch failure; the gradient is never left un-averaged). */
 size_t qw_grads_allreduce_p2p_buffer_bytes(long long n, int world);
 size_t qw_grads_allreduce_p2p_flag_bytes(int world);
 int qw_grads_allreduce_p2p(float* grads, long long n, void* const* peer_bufs, void* const* peer_flags, int rank, int world,

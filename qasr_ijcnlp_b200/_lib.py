@@ -31,6 +31,7 @@ _SIGNATURES = {
     "qw_profile_enable": (None, [_I]),
     "qw_profile_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_LL), _I]),
     "qw_kernel_name": (ctypes.c_char_p, [_I]),
+    "qw_kernel_symbol": (ctypes.c_char_p, [_I]),
     "qw_timeline_set": (_I, [_P, _I]),
     "qw_set_fast_path": (None, [_I]),
     "qw_set_option": (_I, [ctypes.c_char_p, _I]),
@@ -154,5 +155,21 @@ def profile_read(reset: bool = True) -> dict:
         lib.qw_profile_read(kid, ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0)
         if n.value:
             out[name.decode()] = (ms.value, int(n.value))
+        kid += 1
+    return out
+
+
+def kernel_symbols() -> dict:
+    """{kernel name: symbol last launched under it} -- the names an ncu launch list shows."""
+    lib = load()
+    out = {}
+    kid = 0
+    while True:
+        name = lib.qw_kernel_name(kid)
+        if not name:
+            break
+        sym = lib.qw_kernel_symbol(kid)
+        if sym:
+            out[name.decode()] = sym.decode()
         kid += 1
     return out

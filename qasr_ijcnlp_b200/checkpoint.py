@@ -38,9 +38,13 @@ def load_reference_state_dict(module: torch.nn.Module, checkpoint, strict: bool 
     return missing, reference_only
 
 
-def load_reference_checkpoint(module: torch.nn.Module, path: str, device="cpu", strict: bool = True):
-    """``utils.load_model`` counterpart (``utils.py:440-473``): returns (module, training_history, model_info)."""
-    ckpt = torch.load(path, map_location=device, weights_only=False)
+def load_reference_checkpoint(module: torch.nn.Module, path: str, device="cpu", strict: bool = True, allow_pickle: bool = False):
+    """``utils.load_model`` counterpart (``utils.py:440-473``): returns (module, training_history, model_info).
+
+    The reference format (``utils.save_model``) is a state_dict plus dicts of primitives and strings, so the safe
+    ``weights_only=True`` loader is enough and is the default; ``allow_pickle=True`` opts into full unpickling for a legacy file
+    from a TRUSTED source (unpickling executes arbitrary code)."""
+    ckpt = torch.load(path, map_location=device, weights_only=not allow_pickle)
     load_reference_state_dict(module, ckpt, strict=strict)
     hist = ckpt.get("training_history", {}) if isinstance(ckpt, Mapping) else {}
     info = ckpt.get("model_info", {}) if isinstance(ckpt, Mapping) else {}

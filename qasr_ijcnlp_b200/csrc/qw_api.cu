@@ -35,7 +35,7 @@ struct OptDef {
   int dflt;
 };
 static const OptDef kOptDefs[kOptCount] = {{"FAST_PATH", 1}, {"GY_MMA", 1}, {"BWD_FUSED", 0}, {"FWD_MMA", 1}, {"FWD_ETMA", 1}, {"FIN_EARLY", 1},
-                                           {"ADJ_TRIG", 1}, {"PRE_EX", 1}, {"ADJ_SPEC", 1}, {"PRE_CTAS", 4}, {"GY_WARPS", 0}, {"DBG_FWD", 0}, {"DBG_GY", 0}};
+                                           {"ADJ_TRIG", 1}, {"PRE_EX", 1}, {"ADJ_SPEC", 1}, {"PRE_CTAS", 4}, {"GY_WARPS", 0}, {"DP_TIMEOUT_MS", 600000}, {"DBG_FWD", 0}, {"DBG_GY", 0}};
 static std::atomic<int> g_opt[kOptCount];
 static std::once_flag g_opt_once;
 static void opt_init() {
@@ -83,6 +83,15 @@ static bool g_prof = false;
 static std::vector<ProfRec> g_recs[kKCount];
 static cudaEvent_t g_open[kKCount];
 
+static char g_sym[kKCount][96];
+void note_symbol(int id, const char* fmt, ...) {
+  if (id < 0 || id >= kKCount) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_sym[id], sizeof(g_sym[id]), fmt, ap);
+  va_end(ap);
+}
+const char* kernel_symbol(int id) { return (id >= 0 && id < kKCount) ? g_sym[id] : ""; }
 bool profiling_enabled() { return g_prof; }
 void profile_begin(int id, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_pmu);
@@ -150,6 +159,7 @@ int qw_profile_read(int kernel_id, double* total_ms, long long* count, int reset
   }
   return 0;
 }
+const char* qw_kernel_symbol(int kernel_id) { return qw::kernel_symbol(kernel_id); }
 const char* qw_kernel_name(int kernel_id) {
   static const char* names[] = {"qconv_fwd_kernel", "qconv_bwd_post_kernel", "qconv_bwd_pre_kernel", "qconv_bwd_finalize_kernel",
                                 "circuit_fwd_kernel", "circuit_bwd_kernel", "circuit_finalize_kernel", "logmel_stft_kernel",

@@ -22,6 +22,7 @@ enum Option {
   kOptAdjSpec,       // ADJ_SPEC   1: single-layer specialisation of the adjoint kernel
   kOptPreCtas,       // PRE_CTAS   CTAs per SM of the pre_conv^T kernel (default 4)
   kOptGyWarps,       // GY_WARPS   12: wide FFMA gy kernel (only with GY_MMA=0)
+  kOptDpTimeoutMs,   // DP_TIMEOUT_MS  how long the NVLink gradient all-reduce kernels wait for a peer before trapping (default 600 000; 0 = forever)
   kOptDbgFwd,        // DBG_FWD    bit mask: forward kernel skips pre_conv FMAs (1) / post_conv FMAs (2) / circuit (4); results are garbage
   kOptDbgGy,         // DBG_GY     1: gy kernel skips its contractions (measures the streaming floor; results are garbage)
   kOptCount
@@ -36,6 +37,8 @@ int num_sms();
 
 // Optional per-kernel CUDA-event timing (qw_profile_enable): KernelTimer brackets one launch on `st`.
 enum KernelId { kKFwd = 0, kKBwdPost, kKBwdPre, kKBwdFinalize, kKCircFwd, kKCircBwd, kKCircFinalize, kKLogMelStft, kKLogMelFinish, kKBwdAdj, kKLogMelPrep, kKGradAllReduce, kKStem2, kKBwdFused, kKCount };
+// the demangled name ncu shows for the kernel last launched under this id (fast path only; "" otherwise)
+void note_symbol(int id, const char* fmt, ...);
 bool profiling_enabled();
 void profile_begin(int id, cudaStream_t st);
 void profile_end(int id, cudaStream_t st);

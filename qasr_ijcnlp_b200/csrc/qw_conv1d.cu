@@ -273,6 +273,7 @@ int qw_conv1d_backward_dp(const float* gy, const float* x, const float* pre_save
   dp.rank = rank;
   dp.world = world;
   dp.scale = scale;
+  dp.timeout_ns = (unsigned long long)(qw::option(qw::kOptDpTimeoutMs) > 0 ? qw::option(qw::kOptDpTimeoutMs) : 0) * 1000000ull;
   return qw::conv1d_backward_impl<float>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
                                          workspace, ws_bytes, d, stream, &dp);
 }

@@ -1218,9 +1218,10 @@ struct FastFinArgs {
 // remote loads) spent 3-6 us in EACH system-scope fence and 19 us per exchange in total.
 // The raw column sums are exchanged (gate-gradient matrices included: the (phi, theta, omega) chain rule is linear in them and
 // is applied after the sum).  The epoch lives in device memory (CUDA-graph capturable); parity double-buffering is enough
-// because a rank can only be one epoch ahead of its slowest reader.  A CTA only ever waits for the SAME CTA index of its peers
-// and the whole grid is resident, so there is no inter-CTA deadlock; a peer that never arrives trips a ~1 s bound, the local
-// gradient is kept and the status word set.
+// because a rank can only be one epoch ahead of its slowest reader (it cannot finish epoch e + 1 before the slowest rank has
+// posted e + 1, i.e. has finished reading e).  A CTA only ever waits for the SAME CTA index of its peers and the whole grid is
+// resident, so there is no inter-CTA deadlock.  Like NCCL the kernel WAITS for a late peer; a peer that stays away for
+// dp.timeout_ns (default 10 min, option DP_TIMEOUT_MS) trips a trap -- a loud launch failure, never a silently local gradient.
 __device__ __forceinline__ void dp_st_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
@@ -1244,24 +1245,23 @@ __device__ __forceinline__ double dp_allreduce_columns(const FastDp& dp, double 
     if (r < dp.world) dp_st_u64(reinterpret_cast<unsigned long long*>(dp.bufs[r]) + (slot_base + dp.rank) * dp.ncol + col, word);
   const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(dp.bufs[dp.rank]);
   double sum = 0.0;
-  bool bad = false;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
   for (int r = 0; r < dp.world; ++r) {
     const unsigned long long* src = mine + (slot_base + r) * dp.ncol + col;
     unsigned long long v = dp_ld_u64(src);
+    unsigned spins = 0;
     while ((unsigned)(v >> 32) != epoch) {
-      if (clock64() - t0 > 2000000000LL) {  // ~1 s
-        bad = true;
-        break;
+      // NCCL semantics: WAIT for the peer (a late rank -- checkpointing, evaluation, a data-loader stall -- is normal).  Only a
+      // peer that stays away for dp.timeout_ns (default 10 min, like the NCCL watchdog; 0 = forever) is an error, and then the
+      // kernel traps: the context dies with a launch failure, it never continues with an un-averaged gradient.
+      if ((++spins & 1023u) == 0 && dp.timeout_ns != 0 && global_ns() - t0 > dp.timeout_ns) {
+        myflags[nblk] = 1u;
+        __threadfence_system();
+        __trap();
       }
       v = dp_ld_u64(src);
     }
     sum += (double)__uint_as_float((unsigned)v);
-  }
-  bad = __any_sync(0xffffffffu, bad);
-  if (bad) {
-    sum = t * dp.world;  // keep the local gradient; the status word tells the host
-    if (lane == 0) myflags[nblk] = 1u;
   }
   if (lane == 0) myflags[blk] = epoch;
   return sum * (double)dp.scale;
@@ -1448,6 +1448,7 @@ static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const Fa
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast forward needs %zu bytes of shared memory", smem);
   auto k = fast_fwd_kernel<S, RC>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_symbol(kKFwd, "fast_fwd_kernel<%d, %d>", S, RC);
   {
     KernelTimer kt(kKFwd, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridF), dim3(kFwdThreads), smem, st, tm, a));
@@ -1487,6 +1488,7 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast backward(gy) needs %zu bytes of shared memory", smem);
   auto k = fast_bwd_gy2_kernel<NHALF, NW, NST>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_symbol(kKBwdPost, "fast_bwd_gy2_kernel<%d, %d, %d>", NHALF, NW, NST);
   {
     KernelTimer kt(kKBwdPost, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(32 * NW), smem, st, tg, tq, a));
@@ -1505,6 +1507,7 @@ static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const C
   const size_t smem = FUSED ? fast_gy3_fused_smem_bytes() : fast_gy3_smem_bytes();
   auto k = fast_bwd_gy3_kernel<NHALF, FUSED>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_symbol(FUSED ? kKBwdFused : kKBwdPost, "fast_bwd_gy3_kernel<%d, %d>", NHALF, FUSED);
   {
     KernelTimer kt(FUSED ? kKBwdFused : kKBwdPost, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(FUSED ? kGy3Threads + 32 : kGy3Threads), smem, st, tg, tq, tp, tx, a));
@@ -1543,6 +1546,7 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
   const size_t smem = fast_pre_smem_bytes<S>();
   auto k = fast_bwd_pre_kernel<S, PAR, GX>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_symbol(kKBwdPre, "fast_bwd_pre_kernel<%d, %d, %d>", S, PAR, (int)GX);
   {
     KernelTimer kt(kKBwdPre, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridPx * p.nchunks), dim3(kThreads), smem, st, tx, tgx, a));
@@ -1591,6 +1595,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
       f.dp = *dp;
       f.dp.ncol = nblk * 32;
     }
+    note_symbol(kKBwdFinalize, "fast_finalize_kernel<%d>", f.dp.world > 1 ? 512 : 1024);
     {
       KernelTimer kt(kKBwdFinalize, st);
       if (f.dp.world > 1) QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel<512>, dim3(nblk), dim3(512), 0, st, f));
@@ -1611,6 +1616,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     const int adj_spec = option(kOptAdjSpec);
     auto k = (d.Lq == 1 && adj_spec) ? fast_bwd_adj_kernel<false> : fast_bwd_adj_kernel<true>;
     if (smem > 48 * 1024) QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    note_symbol(kKBwdAdj, "fast_bwd_adj_kernel<%d>", (d.Lq == 1 && adj_spec) ? 0 : 1);
     {
       KernelTimer kt(kKBwdAdj, st);
       QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridAdj), dim3(kAdjThreads), smem, st, aa));
@@ -1637,6 +1643,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
       a.dp = *dp;
       a.dp.ncol = nblk * 32;
     }
+    note_symbol(kKBwdFinalize, "fast_finalize_kernel<%d>", a.dp.world > 1 ? 512 : 1024);
     {
       KernelTimer kt(kKBwdFinalize, st);
       if (a.dp.world > 1) QW_CUDA_OK(launch_pdl(p.small, fast_finalize_kernel<512>, dim3(nblk), dim3(512), 0, st, a));

@@ -52,6 +52,7 @@ struct FastDp {
   unsigned* flags[kDpMaxWorld];  // only [rank] is used: epoch[cta], status (local bookkeeping)
   int rank, world, ncol;
   float scale;
+  unsigned long long timeout_ns;  // 0 = wait forever
 };
 inline int fast_dp_columns(const FastPlan& p) { return p.PA1 + p.PA2 + p.PB; }
 inline size_t fast_dp_buffer_bytes(const FastPlan& p, int world) { return (size_t)2 * world * fast_dp_columns(p) * 8; }

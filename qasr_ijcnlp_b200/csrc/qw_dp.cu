@@ -9,8 +9,10 @@
 //   1. every thread packs (epoch << 32 | float bits) of its elements and stores the word straight into slot
 //      [epoch parity][my rank][i] of EVERY peer's buffer (posted P2P stores; data and flag in ONE atomic 8-byte store, the idea
 //      of NCCL's LL protocol: no fence, no separate flag, no remote read);
-//   2. it polls its own buffer until the word of every rank carries the epoch (bounded: ~1 s, then status = 1 and the local
-//      value is kept) and sums the payloads in fixed rank order -> bitwise identical on all ranks; out[i] = scale * sum.
+//   2. it polls its own buffer until the word of every rank carries the epoch (NCCL semantics: it WAITS for a late peer; a peer
+//      that stays away for the DP_TIMEOUT_MS option -- default 10 min -- makes the kernel trap: a loud launch failure, never a
+//      silently un-averaged gradient) and sums the payloads in fixed rank order -> bitwise identical on all ranks;
+//      out[i] = scale * sum.
 // First version (publish into my own buffer, __threadfence_system, st.release.sys flags into the peers, acquire-spin, remote
 // loads): each system-scope fence cost 3-6 us on B200 and the whole exchange ~19 us; this one is one NVLink write latency.
 // The epoch lives in device memory and is advanced by the kernel itself, so the launch is CUDA-graph capturable.
@@ -35,6 +37,7 @@ struct ARArgs {
   long long n;
   int rank, world, per_cta;            // elements per CTA
   float scale;
+  unsigned long long timeout_ns;       // 0 = wait forever
 };
 
 __device__ __forceinline__ void st_u64(unsigned long long* p, unsigned long long v) {
@@ -48,12 +51,8 @@ __device__ __forceinline__ unsigned long long ld_u64(const unsigned long long* p
 
 __global__ void __launch_bounds__(kThreadsAR) grads_allreduce_p2p_kernel(const ARArgs a) {
   __shared__ unsigned s_epoch;
-  __shared__ int s_bad;
   const int tid = threadIdx.x, cta = blockIdx.x;
-  if (tid == 0) {
-    s_epoch = a.book[cta] + 1u;
-    s_bad = 0;
-  }
+  if (tid == 0) s_epoch = a.book[cta] + 1u;
   __syncthreads();
   const unsigned epoch = s_epoch;
   const size_t slot_base = (size_t)(epoch & 1u) * a.world;
@@ -66,29 +65,30 @@ __global__ void __launch_bounds__(kThreadsAR) grads_allreduce_p2p_kernel(const A
     for (int r = 0; r < kMaxWorld; ++r)
       if (r < a.world) st_u64(a.bufs[r] + (slot_base + a.rank) * a.n + i, word);
   }
-  // 2. gather: poll my own buffer, fixed rank order
+  // 2. gather: poll my own buffer, fixed rank order.  NCCL semantics: wait for a late peer; only after a.timeout_ns (default
+  // 10 min, 0 = forever) trap -- the context dies loudly instead of training on with an un-averaged gradient.
   const unsigned long long* mine = a.bufs[a.rank];
-  const long long t0 = clock64();
-  bool bad = false;
+  const unsigned long long t0 = global_ns();
   for (long long i = i0 + tid; i < i1; i += kThreadsAR) {
     float s = 0.f;
     for (int r = 0; r < a.world; ++r) {
       const unsigned long long* src = mine + (slot_base + r) * a.n + i;
       unsigned long long v = ld_u64(src);
-      while ((unsigned)(v >> 32) != epoch && !bad) {
-        if (clock64() - t0 > 2000000000LL) bad = true;  // ~1 s: give up instead of hanging the GPU
-        else v = ld_u64(src);
+      unsigned spins = 0;
+      while ((unsigned)(v >> 32) != epoch) {
+        if ((++spins & 1023u) == 0 && a.timeout_ns != 0 && global_ns() - t0 > a.timeout_ns) {
+          a.book[kMaxCtas] = 1u;
+          __threadfence_system();
+          __trap();
+        }
+        v = ld_u64(src);
       }
       s += __uint_as_float((unsigned)v);
     }
-    if (!bad) a.grads[i] = s * a.scale;
+    a.grads[i] = s * a.scale;
   }
-  if (bad) s_bad = 1;
   __syncthreads();
-  if (tid == 0) {
-    if (s_bad) a.book[kMaxCtas] = 1u;
-    a.book[cta] = epoch;
-  }
+  if (tid == 0) a.book[cta] = epoch;
 }
 
 }  // namespace dp
@@ -124,6 +124,7 @@ int qw_grads_allreduce_p2p(float* grads, long long n, void* const* peer_bufs, vo
   a.rank = rank;
   a.world = world;
   a.scale = scale;
+  a.timeout_ns = (unsigned long long)(option(kOptDpTimeoutMs) > 0 ? option(kOptDpTimeoutMs) : 0) * 1000000ull;
   cudaStream_t st = (cudaStream_t)stream;
   {
     KernelTimer kt(kKGradAllReduce, st);

@@ -159,7 +159,8 @@ class FusedLayerGradAllReduce:
         return self._bufs, self._flags, self.rank, self.world, self._ctypes.c_float(1.0 / self.world)
 
     def status(self) -> int:
-        """0 ok; 1 if some backward timed out waiting for a peer (synchronises)."""
+        """0 ok; 1 if a backward trapped after waiting DP_TIMEOUT_MS for a peer (the CUDA context is dead by then: this is only
+        readable from a fresh mapping; kept for diagnostics).  Synchronises."""
         return int(self.flags[self.nflag - 1].item())
 
 
@@ -223,5 +224,5 @@ class P2PGradAllReduce:
         return int(self.flags[self.nflag - 1 - 64].item())
 
     def status(self) -> int:
-        """0 ok; 1 if some call timed out waiting for a peer (synchronises)."""
+        """0 ok; 1 if a call trapped after waiting DP_TIMEOUT_MS for a peer (diagnostics; synchronises)."""
         return int(self.flags[self.nflag - 1].item())

@@ -84,6 +84,16 @@ def _worker(rank, world, port, q):
             torch.cuda.synchronize()
             ok = ok and bool((y - want).abs().max().item() <= 1e-6)
         ok = ok and ar.status() == 0
+        # late rank (> 1 s): the one-shot kernel waits for it
+        z = torch.full((n,), float(rank + 1), device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            import time
+            time.sleep(1.6)
+        ar(z)
+        torch.cuda.synchronize()
+        ok = ok and bool((z - want).abs().max().item() <= 1e-6)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -169,6 +179,23 @@ def _worker_fused(rank, world, port, q):
             torch.cuda.synchronize()
             ok = ok and all(torch.equal(a, b) for a, b in zip(eager, captured))
         ok = ok and fused._grad_allreduce.status() == 0
+        # a rank that is LATE by more than a second (checkpointing, evaluation, a data-loader stall) must still get -- and give --
+        # the true mean: the kernels wait like an NCCL collective (round 1 gave up after ~1 s and kept the local gradient)
+        torch.manual_seed(11)
+        plain = QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(dev)
+        ref = list(torch.autograd.grad(plain(x), list(plain.parameters()), gy))
+        for t in ref:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t /= world
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 1:
+            import time
+            time.sleep(1.6)
+        late = torch.autograd.grad(fused(x), list(fused.parameters()), gy)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, late):
+            ok = ok and (a - b).abs().max().item() <= 1e-6 * max(1.0, a.abs().max().item())
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -261,3 +261,27 @@ def test_stem_oracle_is_the_composition_of_the_literal_layers():
     got = qo.stem_forward(x, p1, p2, pos)
     assert got.shape == (2, 6, 8)
     assert (got - ref).abs().max().item() < 1e-12
+
+
+def test_pennylane_probe_pins_the_restatement_when_available():
+    """SURVEY.md section 7 step 1.  Where PennyLane and the reference tree are both present, the UNMODIFIED reference
+    QuantumConv1d (quantum_whisper.py:45-128) is run and the fp64 restatement must match it: forward to 1e-6 (the reference casts
+    its readout to fp32 at :122), all gradients to 1e-5 relative.  Here (no PennyLane, no wheel, no network) the probe reports
+    "unavailable" and the test is skipped -- which is what "parity unpinned" means."""
+    import oracle
+
+    Ref = oracle.pennylane_reference()
+    if Ref is None:
+        pytest.skip("PennyLane is not importable (or /root/reference is absent): parity stays unpinned at the PennyLane boundary")
+    torch.manual_seed(0)
+    m = Ref(5, 7, 3, stride=2, padding=1, n_qubits=4)
+    x = torch.randn(2, 5, 12, requires_grad=True)
+    y = m(x)
+    gy = torch.randn_like(y)
+    grads = torch.autograd.grad(y, [x] + [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias], gy)
+    p64 = [t.detach().double() for t in (m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias)]
+    ref = qo.qconv1d_grads(x.detach().double(), p64, gy.double(), 3, 2, 1)
+    assert (y.detach().double() - ref["y"]).abs().max().item() <= 1e-6
+    for got, key in zip(grads, ["x", "w_pre", "b_pre", "qweights", "w_post", "b_post"]):
+        scale = max(1.0, ref[key].abs().max().item())
+        assert (got.double() - ref[key]).abs().max().item() <= 1e-5 * scale, key
