@@ -518,9 +518,11 @@ __global__ void __launch_bounds__(32 * NW, 2) fast_bwd_gy2_kernel(const __grid_c
 //                    gradient rides along for free), rows 9-15 = 0.
 //   gout:            A[m][k] = gy[8 kb + r(k)][16 mb + w(m)], r(t) = 2 t, r(t + 4) = 2 t + 1, w(g) = 2 g, w(g + 8) = 2 g + 1
 //                    (again two conflict-free LDS.64); B[k][n] = [hi | lo] of W_post[8 kb + r(k)][n & 3], held in registers for the
-//                    CTA lifetime (each warp owns 4 of the 24 channel blocks of a stage; partial sums of the 6 warps meet in
+//                    CTA lifetime (each warp owns 3 of the 24 channel blocks of a stage; partial sums of the 8 warps meet in
 //                    shared memory, double-buffered, one __syncthreads per tile).
-constexpr int kGy3Warps = 6, kGy3Threads = 32 * kGy3Warps, kGy3Rows = 32 * kGy3Warps, kGy3Stages = 3;
+constexpr int kGy3Warps = 8, kGy3Threads = 32 * kGy3Warps, kGy3Rows = 192, kGy3Stages = 3;
+constexpr int kGy3Bpw = kGy3Rows / 8 / kGy3Warps;  // 8-channel blocks of a stage per warp (24 blocks over 8 warps: an even load on the 4 sub-partitions)
+static_assert(kGy3Bpw * kGy3Warps * 8 == kGy3Rows, "stage rows must split evenly over the warps");
 __host__ __device__ constexpr size_t fast_gy3_smem_bytes() {
   return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 + 2 * kGy3Stages * 8;
 }
@@ -541,9 +543,9 @@ __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<floa
 // zero-compute TMA streaming kernel of the same footprint needs ~15 us for the 74 MB of gy (tools/probe/stream_probe.cu): launch
 // ramp, the ragged last round and the drain of every kernel boundary cost as much as the bytes, while the gy pass itself leaves
 // most issue slots idle (it waits for HBM).  So the adjoint differentiation moves INTO those idle slots:
-//   warps 0-5  the tensor-pipe gy pass above over a CONTIGUOUS range of <= kFbMaxTiles tiles; gout stays in shared memory
+//   warps 0-7  the tensor-pipe gy pass above over a CONTIGUOUS range of <= kFbMaxTiles tiles; gout stays in shared memory
 //              (never written to HBM); <Z> and pre_conv outputs of each tile arrive by TMA on a per-tile barrier;
-//   warp 6     adjoint warp, one window per lane: the forward recomputation of tile n runs as soon as its pre_conv outputs have
+//   warp 8     adjoint warp, one window per lane: the forward recomputation of tile n runs as soon as its pre_conv outputs have
 //              landed (i.e. while the gy rows of that tile are still streaming), the backward sweep as soon as the tile's gout
 //              is summed.  Gate-gradient matrices accumulate in registers over the CTA's tiles and are reduced once (transposing
 //              warp reduction, 31 shuffles for 32 values).  Only the last tile's backward sweep (~1 650 instructions) is exposed.
@@ -707,14 +709,14 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
   }
 
   // B fragments of the gout contraction (parameters: readable before the dependency wait)
-  uint32_t bw[NHALF][4][2];
+  uint32_t bw[NHALF][kGy3Bpw][2];
 #pragma unroll
   for (int h = 0; h < NHALF; ++h)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kGy3Bpw; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int o = h * kGy3Rows + (warp * 4 + i) * 8 + 2 * t + e;
+        const int o = h * kGy3Rows + (warp * kGy3Bpw + i) * 8 + 2 * t + e;
         const float v = (o < a.O) ? __ldg(a.w_post + (size_t)o * FQ + (g & 3)) : 0.f;
         uint32_t hi, lo;
         split_tf32(v, hi, lo);
@@ -743,9 +745,9 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
   }
 
   const int total_stages = my_tiles * NHALF;
-  float d1[NHALF * 4][4];  // [8-channel block][fragment]: rows = hi/lo of <Z_j> (and the ones row), columns = channels
+  float d1[NHALF * kGy3Bpw][4];  // [8-channel block][fragment]: rows = hi/lo of <Z_j> (and the ones row), columns = channels
 #pragma unroll
-  for (int m = 0; m < NHALF * 4; ++m)
+  for (int m = 0; m < NHALF * kGy3Bpw; ++m)
 #pragma unroll
     for (int j = 0; j < 4; ++j) d1[m][j] = 0.f;
   const uint32_t one_g0 = (g == 0) ? 0x3f800000u : 0u;  // A rows 8..15: row 8 (lanes g == 0) = 1.0f
@@ -814,22 +816,22 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
       } else {
       // ---- grad post_conv.{weight,bias}: this warp's four 8-channel blocks of the stage, K = the tile's 32 windows
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* rp = gsm + (warp * 4 + i) * 256;
+      for (int i = 0; i < kGy3Bpw; ++i) {
+        const float* rp = gsm + (warp * kGy3Bpw + i) * 256;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           const float2 u = ld2(rp + off1[kb]);
           uint32_t bh[2], bl[2];
           split_tf32(u.x, bh[0], bl[0]);
           split_tf32(u.y, bh[1], bl[1]);
-          mma_tf32(d1[h * 4 + i], aq[kb], bh[0], bh[1]);
-          mma_tf32(d1[h * 4 + i], aq[kb], bl[0], bl[1]);
+          mma_tf32(d1[h * kGy3Bpw + i], aq[kb], bh[0], bh[1]);
+          mma_tf32(d1[h * kGy3Bpw + i], aq[kb], bl[0], bl[1]);
         }
       }
       // ---- gout partials: this warp's four 8-channel blocks of the stage, both 16-window halves of the tile
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* rp = gsm + (warp * 4 + i) * 256;
+      for (int i = 0; i < kGy3Bpw; ++i) {
+        const float* rp = gsm + (warp * kGy3Bpw + i) * 256;
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
           const float2 u = ld2(rp + off2[m][0]), v = ld2(rp + off2[m][1]);
@@ -846,7 +848,7 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
-    // ---- the 6 warps' partial gout rows meet in shared memory; warp n % 6 sums and stores the tile's gout.  Double-buffered:
+    // ---- the 8 warps' partial gout rows meet in shared memory; warp n % 8 sums and stores the tile's gout.  Double-buffered:
     // a warp can only be writing buffer (n + 2) & 1 after the barrier of tile n + 1, which the summing warp of tile n reaches
     // after its reads.
     float* gr = gred + (size_t)(n & 1) * kGy3Warps * FTW * 8 + (size_t)warp * FTW * 8;
@@ -880,9 +882,9 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
   {
     float* prow = a.part + (size_t)blockIdx.x * a.PA1;
 #pragma unroll
-    for (int m = 0; m < NHALF * 4; ++m) {
-      const int h = m >> 2, i = m & 3;
-      const int o = h * kGy3Rows + (warp * 4 + i) * 8 + 2 * t;  // this lane's two channels: o, o + 1
+    for (int m = 0; m < NHALF * kGy3Bpw; ++m) {
+      const int h = m / kGy3Bpw, i = m - h * kGy3Bpw;
+      const int o = h * kGy3Rows + (warp * kGy3Bpw + i) * 8 + 2 * t;  // this lane's two channels: o, o + 1
       // rows j (hi half of <Z_j>) and j + 4 (lo half) live in lanes g and g + 4
       const float c0 = d1[m][0] + __shfl_xor_sync(0xffffffffu, d1[m][0], 16);
       const float c1 = d1[m][1] + __shfl_xor_sync(0xffffffffu, d1[m][1], 16);
