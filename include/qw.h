@@ -129,9 +129,24 @@ int qw_circuit_backward_f64(const double* pre, const double* qw, const double* g
                             void* workspace, size_t ws_bytes, long long W, int q, int n_layers, int embedding,
                             void* stream);
 
+/* ---- OPT-IN collapsed evaluation of the amplitude-embedded circuit (SURVEY.md 8a iii): <Z_i> = xh^T M_i xh, xh = pre/||pre||, with the
+ * q x q x q matrices M ([i][a][b], symmetric in a, b) supplied by the caller -- qasr_ijcnlp_b200.quantum_circuit(simulator=
+ * "collapsed") reads them off the STATEVECTOR kernel evaluated on q(q+1)/2 probe windows, so the semantics (any weights, any
+ * n_layers) stay those of qw_circuit_forward.  pre (W,q) -> out (W,q); backward: gout -> gpre (W,q) and gM (q,q,q) = sum over
+ * windows of gout_i xh_a xh_b.  Not the headline path and not used by QuantumConv1d: a separately reported mode and the
+ * device-side second oracle of the parity tests.  n_qubits 1..12, amplitude embedding only. */
+size_t qw_circuit_collapsed_workspace_bytes(long long W, int q, int elem_size);
+int qw_circuit_forward_collapsed(const float* pre, const float* M, float* out, long long W, int q, void* stream);
+int qw_circuit_backward_collapsed(const float* pre, const float* M, const float* gout, float* gpre, float* gM, void* workspace,
+                                  size_t ws_bytes, long long W, int q, void* stream);
+int qw_circuit_forward_collapsed_f64(const double* pre, const double* M, double* out, long long W, int q, void* stream);
+int qw_circuit_backward_collapsed_f64(const double* pre, const double* M, const double* gout, double* gpre, double* gM,
+                                      void* workspace, size_t ws_bytes, long long W, int q, void* stream);
+
 /* ---- whisper.log_mel_spectrogram (whisper/whisper/audio.py:110-157), batched, max taken per utterance.
- * audio (B, n_samples) fp32, n_samples % 160 == 0; filters (n_mels, 201) fp32 (audio.py:91-107);
- * mel (B, n_mels, n_samples/160).  workspace: qw_log_mel_workspace_bytes(B, n_samples, n_mels). */
+ * audio (B, n_samples) fp32, any n_samples > 200 (like the reference: T = n_samples / 160 frames, the samples past the last full
+ * hop still feed the last frames); filters (n_mels, 201) fp32 (audio.py:91-107); mel (B, n_mels, n_samples/160).
+ * workspace: qw_log_mel_workspace_bytes(B, n_samples, n_mels). */
 size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels);
 int qw_log_mel(const float* audio, const float* filters, float* mel, void* workspace, size_t ws_bytes, int B,
                int n_samples, int n_mels, void* stream);
@@ -142,6 +157,13 @@ size_t qw_log_mel_prep_bytes(int n_mels);
 int qw_log_mel_prepare(const float* filters, int n_mels, void* prep, size_t prep_bytes, void* stream);
 int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B,
                         int n_samples, int n_mels, void* stream);
+/* whisper.pad_or_trim (audio.py:65-88) fused into the front end -- the batched data path of SURVEY.md 8-f4 (the reference pads every
+ * clip to 480 000 samples on the CPU inside Dataset.__getitem__, train_quantum_whisper.py:52-77): audio is (B, n_in) with row
+ * stride n_in; utterance b holds lengths[b] valid samples (lengths == NULL: all n_in); the result is exactly
+ * log_mel_spectrogram(pad_or_trim(audio[b, :lengths[b]], n_samples)): zero padding up to n_samples, or the first n_samples samples of
+ * a longer clip.  Tiles that lie entirely in the padding skip the FFT.  mel (B, n_mels, n_samples/160); workspace: B floats. */
+int qw_log_mel_padded(const float* audio, const int* lengths, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B,
+                      int n_in, int n_samples, int n_mels, void* stream);
 
 /* ---- data-parallel training collective (the reference is single-process, train_quantum_whisper.py:195-214):
  * one-shot all-reduce of a small fp32 gradient bucket (n <= 2^20) over NVLink peer memory, fused with the `scale` (1/world)

@@ -50,11 +50,17 @@ _SIGNATURES = {
     "qw_circuit_forward_f64": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),
     "qw_circuit_backward": (_I, [_P] * 5 + [_P, _SZ, _LL, _I, _I, _I, _P]),
     "qw_circuit_backward_f64": (_I, [_P] * 5 + [_P, _SZ, _LL, _I, _I, _I, _P]),
+    "qw_circuit_collapsed_workspace_bytes": (_SZ, [_LL, _I, _I]),
+    "qw_circuit_forward_collapsed": (_I, [_P, _P, _P, _LL, _I, _P]),
+    "qw_circuit_forward_collapsed_f64": (_I, [_P, _P, _P, _LL, _I, _P]),
+    "qw_circuit_backward_collapsed": (_I, [_P] * 5 + [_P, _SZ, _LL, _I, _P]),
+    "qw_circuit_backward_collapsed_f64": (_I, [_P] * 5 + [_P, _SZ, _LL, _I, _P]),
     "qw_log_mel_workspace_bytes": (_SZ, [_I, _I, _I]),
     "qw_log_mel": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _P]),
     "qw_log_mel_prep_bytes": (_SZ, [_I]),
     "qw_log_mel_prepare": (_I, [_P, _I, _P, _SZ, _P]),
     "qw_log_mel_prepared": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _P]),
+    "qw_log_mel_padded": (_I, [_P, _P, _P, _P, _P, _SZ, _I, _I, _I, _I, _P]),
     "qw_grads_allreduce_p2p_buffer_bytes": (_SZ, [_LL, _I]),
     "qw_grads_allreduce_p2p_flag_bytes": (_SZ, [_I]),
     "qw_grads_allreduce_p2p": (_I, [_P, _LL, ctypes.POINTER(_P), ctypes.POINTER(_P), _I, _I, ctypes.c_float, _P]),

@@ -113,10 +113,18 @@ def mel_filters(device, n_mels: int) -> torch.Tensor:
 
 
 def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80, padding: int = 0,
-                        device: Optional[Union[str, torch.device]] = None) -> torch.Tensor:
+                        device: Optional[Union[str, torch.device]] = None, *, pad_to: Optional[int] = None,
+                        lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     """audio (n_samples,) or (B, n_samples) -> (n_mels, n_frames) or (B, n_mels, n_frames), n_frames = n_samples // 160.
 
-    Signature of audio.py:110-115 (minus the file-path form).  The tensor must end up on a CUDA device."""
+    Signature of audio.py:110-115 (minus the file-path form); any n_samples > 200 works like the reference (the last, partial
+    STFT frame is dropped, audio.py:149).  The tensor must end up on a CUDA device.
+
+    Batched data path (keyword-only, not in the reference): ``pad_to=N`` fuses ``pad_or_trim(audio, N)`` into the
+    kernel -- the result equals ``log_mel_spectrogram(pad_or_trim(audio, N))`` but only the stored samples cross PCIe / HBM and
+    tiles that lie in the zero padding skip the FFT (a 1 s Speech-Commands clip is 16 000 samples, not 480 000:
+    train_quantum_whisper.py:62-77 pads every clip on the CPU).  ``lengths`` (B,) int32 gives the valid samples of every row of a
+    ragged batch (see ``collate_clips``)."""
     if isinstance(audio, str):
         raise TypeError("file-path input (ffmpeg) is outside this package's scope: pass samples")
     if not torch.is_tensor(audio):
@@ -132,19 +140,42 @@ def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80
     single = audio.dim() == 1
     a = audio.reshape(1, -1) if single else audio
     a = a.to(torch.float32).contiguous()
-    B, n = a.shape
-    if n % HOP_LENGTH:
-        # torch.stft yields 1 + n // 160 frames and the reference drops the last: the tail samples beyond the last
-        # full hop only ever feed frames through reflect padding.  Keep exact framing by handling whole hops only.
-        raise ValueError(f"n_samples={n} must be a multiple of {HOP_LENGTH} (use pad_or_trim)")
+    B, n_in = a.shape
+    n = int(pad_to) if pad_to is not None else n_in
+    if n <= N_FFT // 2 or n < HOP_LENGTH:
+        raise ValueError(f"n_samples={n} must be > {N_FFT // 2} (reflect padding of torch.stft) and >= {HOP_LENGTH}")
+    if lengths is not None:
+        lengths = lengths.to(device=a.device, dtype=torch.int32).contiguous()
+        if lengths.shape != (B,):
+            raise ValueError(f"lengths must have shape ({B},), got {tuple(lengths.shape)}")
     lib = _lib.load()
     T = n // HOP_LENGTH
     prep = _prepared_filters(a.device, n_mels)
     mel = torch.empty(B, n_mels, T, device=a.device, dtype=torch.float32)
     ws = torch.empty(B, device=a.device, dtype=torch.float32)
+    P = ctypes.c_void_p
     with torch.cuda.device(a.device):
-        st = lib.qw_log_mel_prepared(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(prep.data_ptr()), ctypes.c_void_p(mel.data_ptr()),
-                                     ctypes.c_void_p(ws.data_ptr()), 4 * B, B, n, n_mels,
-                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    _lib.check(st, "qw_log_mel_prepared")
+        st = lib.qw_log_mel_padded(P(a.data_ptr()), P(lengths.data_ptr()) if lengths is not None else None, P(prep.data_ptr()),
+                                   P(mel.data_ptr()), P(ws.data_ptr()), 4 * B, B, n_in, n, n_mels,
+                                   P(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "qw_log_mel_padded")
     return mel[0] if single else mel
+
+
+def collate_clips(clips, device, pin: bool = True):
+    """Batched replacement of the reference's per-item CPU preprocessing (Dataset.__getitem__, train_quantum_whisper.py:52-77,
+    librispeech_asr.py:53-84: pad_or_trim to 480 000 samples + log-mel per clip): stack variable-length clips into one
+    (B, max_len) pinned host buffer, ship only that, and let ``log_mel_spectrogram(..., pad_to=N_SAMPLES, lengths=...)`` pad on the
+    device.  Returns (audio (B, max_len) on `device`, lengths (B,) int32 on `device`)."""
+    arrs = [torch.as_tensor(np.asarray(c) if not torch.is_tensor(c) else c, dtype=torch.float32).reshape(-1) for c in clips]
+    if not arrs:
+        raise ValueError("empty batch")
+    lens = torch.tensor([min(int(t.numel()), N_SAMPLES) for t in arrs], dtype=torch.int32)
+    width = max(int(lens.max().item()), 1)
+    width = (width + 3) // 4 * 4  # 16-byte rows
+    host = torch.zeros(len(arrs), width, dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        host = host.pin_memory()
+    for i, t in enumerate(arrs):
+        host[i, :lens[i]] = t[:lens[i]]
+    return host.to(device, non_blocking=True), lens.to(device, non_blocking=True)

@@ -46,7 +46,8 @@ struct Args {
   const Meta* meta;
   const float* vals;
   int B, n, T, n_mels, tiles_per_utt, num_tiles;
-
+  int n_in;            // row stride of `audio` = samples stored per utterance (pad_or_trim fused: n_in != n is allowed)
+  const int* lengths;  // (B) valid samples per utterance (<= n_in) or NULL: every row holds min(n_in, n) valid samples
 };
 
 __global__ void __launch_bounds__(1024) logmel_prep_kernel(const float* __restrict__ filters, int n_mels, Meta* meta, float* vals) {
@@ -125,19 +126,38 @@ __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
   constexpr int NT = 32 * G;
 
   // asynchronous fill of the audio staging buffer for one tile (reflect padding resolved per sample)
+  // valid samples of utterance b: whisper.pad_or_trim (audio.py:65-88) fused -- samples past the clip are zeros, samples past n
+  // are trimmed -- so a 1 s Speech-Commands clip crosses PCIe and HBM as 16 000 samples, not as 480 000
+  auto valid_len = [&](int b) {
+    int v = a.lengths ? a.lengths[b] : a.n_in;
+    v = v < a.n_in ? v : a.n_in;
+    return v < a.n ? v : a.n;
+  };
+  // a tile all of whose samples (after reflection at the END of the padded signal) lie in the zero padding: every power is 0
+  auto tile_is_silent = [&](int tile) {
+    const int b = tile / a.tiles_per_utt;
+    const int t0 = (tile - b * a.tiles_per_utt) * kFrames;
+    const int p0 = t0 * kHop - kNfft / 2, p1 = p0 + kSpan - 1;  // first / last original index (before reflection)
+    const int nv = valid_len(b);
+    if (p0 < nv || p0 < 0) return false;
+    return p1 < a.n || 2 * (a.n - 1) - p1 >= nv;
+  };
   auto fill = [&](int tile) {
     const int b = tile / a.tiles_per_utt;
     const int t0 = (tile - b * a.tiles_per_utt) * kFrames;
-    const float* src = a.audio + (size_t)b * a.n;
+    const float* src = a.audio + (size_t)b * a.n_in;
+    const int nv = valid_len(b);
     const int p0 = t0 * kHop - kNfft / 2;  // original index of the tile's first sample (before reflection)
+    if (!tile_is_silent(tile)) {
 #pragma unroll 4
-    for (int s = tid; s < kSpan; s += NT) {
-      int p = p0 + s;
-      p = p < 0 ? -p : p;                     // reflect (no edge repeat), torch.stft center=True
-      p = p >= a.n ? 2 * (a.n - 1) - p : p;
-      float* dst = aud + s + (s >> 5);
-      if (p >= 0 && p < a.n) cp_async4(dst, src + p);
-      else *dst = 0.f;                        // frames >= T of a ragged last tile read zeros
+      for (int s = tid; s < kSpan; s += NT) {
+        int p = p0 + s;
+        p = p < 0 ? -p : p;                     // reflect (no edge repeat), torch.stft center=True
+        p = p >= a.n ? 2 * (a.n - 1) - p : p;
+        float* dst = aud + s + (s >> 5);
+        if (p >= 0 && p < nv) cp_async4(dst, src + p);
+        else *dst = 0.f;                        // zero padding; frames >= T of a ragged last tile read zeros
+      }
     }
     cp_async_commit();
   };
@@ -160,6 +180,22 @@ __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
     const int t0 = (tile - b * a.tiles_per_utt) * kFrames;
     cp_async_wait_all();
     __syncthreads();  // audio of this tile visible; previous tile's mel readers are done with `work`
+    const int t = t0 + lane;
+    float vmax = -INFINITY;
+    if (tile_is_silent(tile)) {
+      // zero padding (29/30 of a Speech-Commands batch): power 0 in every bin -> the clamp value, the same expression and bits
+      // the arithmetic path produces
+      if (tile + (int)gridDim.x < a.num_tiles) fill(tile + gridDim.x);
+      const float v = 0.30102999566398120f * __log2f(fmaxf(0.f, 1e-10f));
+      if (t < a.T) {
+        for (int m = g; m < a.n_mels; m += G) a.mel[((size_t)b * a.n_mels + m) * a.T + t] = v;
+        vmax = v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (lane == 0 && g == 0 && vmax > -INFINITY) atomic_max_float(a.umax + b, vmax + 0.0f);
+      continue;
+    }
     pass_a(g, G, au, col);
     __syncthreads();
     if (tile + (int)gridDim.x < a.num_tiles) fill(tile + gridDim.x);  // overlaps pass B / untangle / mel
@@ -167,8 +203,6 @@ __global__ void __launch_bounds__(32 * G) logmel_stft_kernel(const Args a) {
     __syncthreads();
     untangle_power(g, G, col);
     __syncthreads();
-    const int t = t0 + lane;
-    float vmax = -INFINITY;
     for (int m = g; m < a.n_mels; m += G) {
       const int lo = mlo[m], hi = mhi[m];
       const bool top = hi == kNfreq;          // P[200] lives at float slot 1, everything else at float 2k
@@ -263,9 +297,12 @@ static int run_prepare(const float* filters, int n_mels, void* prep, cudaStream_
   return 0;
 }
 
-static int run_prepared(const float* audio, const void* prep, float* mel, float* umax, int B, int n_samples, int n_mels, cudaStream_t st) {
+static int run_prepared(const float* audio, const int* lengths, const void* prep, float* mel, float* umax, int B, int n_in, int n_samples,
+                        int n_mels, cudaStream_t st) {
   Args a{};
   a.audio = audio;
+  a.n_in = n_in;
+  a.lengths = lengths;
   a.filters = nullptr;
   a.mel = mel;
   a.umax = umax;
@@ -299,8 +336,10 @@ static int run_prepared(const float* audio, const void* prep, float* mel, float*
 
 static int check_shape(int B, int n_samples, int n_mels) {
   QW_CHECK_ARG(B > 0 && n_mels > 0 && n_mels <= kMaxMels, -1, "qw_log_mel: bad shape B=%d n_mels=%d (n_mels <= %d)", B, n_mels, kMaxMels);
-  QW_CHECK_ARG(n_samples > kNfft / 2 && n_samples % kHop == 0, -1,
-               "qw_log_mel: n_samples=%d must be a multiple of %d and > %d (reflect padding)", n_samples, kHop, kNfft / 2);
+  // any length works like the reference: torch.stft(center=True) yields 1 + n / 160 frames and audio.py:149 drops the last one, so
+  // T = n / 160 and the samples past the last full hop still feed the last frames (and the reflection at the end)
+  QW_CHECK_ARG(n_samples > kNfft / 2 && n_samples >= kHop, -1, "qw_log_mel: n_samples=%d must be > %d (reflect padding) and >= %d (one frame)",
+               n_samples, kNfft / 2, kHop);
   QW_CHECK_ARG((long long)B * n_samples < (1LL << 40), -1, "qw_log_mel: tensor too large");
   return 0;
 }
@@ -327,7 +366,18 @@ int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* 
   if (int e = lm::check_shape(B, n_samples, n_mels)) return e;
   QW_CHECK_ARG(ws_bytes >= (size_t)B * sizeof(float), -3, "qw_log_mel_prepared: workspace too small (B floats)");
   QW_CHECK_ARG(((uintptr_t)prep & 255) == 0 && ((uintptr_t)workspace & 3) == 0, -1, "qw_log_mel_prepared: misaligned buffer");
-  return lm::run_prepared(audio, prep, mel, (float*)workspace, B, n_samples, n_mels, (cudaStream_t)stream);
+  return lm::run_prepared(audio, nullptr, prep, mel, (float*)workspace, B, n_samples, n_samples, n_mels, (cudaStream_t)stream);
+}
+
+int qw_log_mel_padded(const float* audio, const int* lengths, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B,
+                      int n_in, int n_samples, int n_mels, void* stream) {
+  using namespace qw;
+  QW_CHECK_ARG(audio && prep && mel && workspace, -1, "qw_log_mel_padded: null pointer argument");
+  if (int e = lm::check_shape(B, n_samples, n_mels)) return e;
+  QW_CHECK_ARG(n_in > 0, -1, "qw_log_mel_padded: n_in=%d must be positive", n_in);
+  QW_CHECK_ARG(ws_bytes >= (size_t)B * sizeof(float), -3, "qw_log_mel_padded: workspace too small (B floats)");
+  QW_CHECK_ARG(((uintptr_t)prep & 255) == 0 && ((uintptr_t)workspace & 3) == 0, -1, "qw_log_mel_padded: misaligned buffer");
+  return lm::run_prepared(audio, lengths, prep, mel, (float*)workspace, B, n_in, n_samples, n_mels, (cudaStream_t)stream);
 }
 
 size_t qw_log_mel_workspace_bytes(int B, int n_samples, int n_mels) {
@@ -345,7 +395,7 @@ int qw_log_mel(const float* audio, const float* filters, float* mel, void* works
   unsigned char* ws = (unsigned char*)workspace;
   void* prep = ws + align_up((size_t)B * sizeof(float), 256);
   if (int e = lm::run_prepare(filters, n_mels, prep, (cudaStream_t)stream)) return e;
-  return lm::run_prepared(audio, prep, mel, (float*)ws, B, n_samples, n_mels, (cudaStream_t)stream);
+  return lm::run_prepared(audio, nullptr, prep, mel, (float*)ws, B, n_samples, n_samples, n_mels, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -255,11 +255,80 @@ class _CircuitFn(torch.autograd.Function):
         return gpre, gqw, None, None
 
 
+class _CollapsedFn(torch.autograd.Function):
+    """out_i = xh^T M_i xh per window (qw_circuit_forward_collapsed); backward returns gpre and gM."""
+
+    @staticmethod
+    def forward(ctx, pre, M):
+        lib = _lib.load()
+        W, q = pre.shape
+        f64 = pre.dtype == torch.float64
+        pre = pre.contiguous()
+        M = M.contiguous()
+        out = torch.empty_like(pre)
+        fn = lib.qw_circuit_forward_collapsed_f64 if f64 else lib.qw_circuit_forward_collapsed
+        with torch.cuda.device(pre.device):
+            st = fn(_ptr(pre), _ptr(M), _ptr(out), W, q, _stream())
+        _lib.check(st, "qw_circuit_forward_collapsed")
+        ctx.save_for_backward(pre, M)
+        ctx.cfg = (W, q, f64)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        pre, M = ctx.saved_tensors
+        W, q, f64 = ctx.cfg
+        gout = gout.contiguous()
+        gpre = torch.empty_like(pre)
+        gM = torch.empty_like(M)
+        nbytes = lib.qw_circuit_collapsed_workspace_bytes(W, q, 8 if f64 else 4)
+        ws = torch.empty(max(nbytes, 16), device=pre.device, dtype=torch.uint8)
+        fn = lib.qw_circuit_backward_collapsed_f64 if f64 else lib.qw_circuit_backward_collapsed
+        with torch.cuda.device(pre.device):
+            st = fn(_ptr(pre), _ptr(M), _ptr(gout), _ptr(gpre), _ptr(gM), _ptr(ws), nbytes, W, q, _stream())
+        _lib.check(st, "qw_circuit_backward_collapsed")
+        return gpre, gM
+
+
+def collapsed_matrices(quantum_weights: torch.Tensor, n_qubits: int, n_layers: int = 1) -> torch.Tensor:
+    """M (q, q, q), M[i] = Re(U[:, :q]^H Z'_i U[:, :q]) of SURVEY.md 8a (iii), read off the STATEVECTOR kernel: it is evaluated on the
+    q (q + 1) / 2 probe windows e_a and (e_a + e_b) / sqrt 2 and M_aa = f(e_a), M_ab = f((e_a + e_b)/sqrt 2) - (M_aa + M_bb) / 2.
+    Differentiable: gradients wrt the weights flow back through the statevector adjoint kernel on those probes."""
+    q = n_qubits
+    dev, dt = quantum_weights.device, quantum_weights.dtype
+    ia, ib = torch.triu_indices(q, q, device=dev)
+    probes = torch.zeros(ia.numel(), q, device=dev, dtype=dt)
+    rows = torch.arange(ia.numel(), device=dev)
+    probes[rows, ia] = 1.0
+    probes[rows, ib] = 1.0  # diagonal probes: e_a (normalised by the embedding); off-diagonal: e_a + e_b -> (e_a + e_b)/sqrt 2
+    f = _CircuitFn.apply(probes, quantum_weights, int(n_layers), EMBEDDINGS["amplitude"])  # (n_probes, q): f[p, i]
+    diag = f[ia == ib]                                    # (q, q): diag[a, i] = M_i[a][a]
+    off = f - 0.5 * (diag[ia] + diag[ib])                 # for a == b this is 0 and is replaced below
+    vals = torch.where((ia == ib)[:, None], f, off)       # (n_probes, q)
+    M = torch.zeros(q, q, q, device=dev, dtype=dt)
+    M = M.index_put((torch.arange(q, device=dev)[None, :].expand(ia.numel(), q), ia[:, None].expand(-1, q), ib[:, None].expand(-1, q)), vals)
+    M = M + M.transpose(1, 2) - torch.diag_embed(torch.diagonal(M, dim1=1, dim2=2))
+    return M
+
+
 def quantum_circuit(pre: torch.Tensor, quantum_weights: torch.Tensor, n_layers: int = 1,
-                    embedding: str = "amplitude") -> torch.Tensor:
-    """The QNode alone, batched: pre (W, q) -> <Z_i> (W, q)  (quantum_whisper.py:64-85)."""
+                    embedding: str = "amplitude", simulator: str = "statevector") -> torch.Tensor:
+    """The QNode alone, batched: pre (W, q) -> <Z_i> (W, q)  (quantum_whisper.py:64-85).
+
+    ``simulator="statevector"`` (default) is the batched statevector simulator + adjoint differentiation.
+    ``simulator="collapsed"`` (opt-in, amplitude embedding only) evaluates the same circuit through the quadratic forms
+    ``xh^T M_i xh`` (SURVEY.md 8a iii) with M read off the statevector kernel on q(q+1)/2 probe windows: a separately reported
+    mode and the device-side second oracle of the tests -- never the default."""
     if not pre.is_cuda:
         raise RuntimeError("quantum_circuit (B200 build) has no CPU path")
     if pre.dim() != 2:
         raise ValueError("pre must be (windows, n_qubits)")
-    return _CircuitFn.apply(pre, quantum_weights, int(n_layers), EMBEDDINGS[embedding])
+    if simulator == "statevector":
+        return _CircuitFn.apply(pre, quantum_weights, int(n_layers), EMBEDDINGS[embedding])
+    if simulator != "collapsed":
+        raise ValueError(f"simulator must be 'statevector' or 'collapsed', got {simulator!r}")
+    if embedding != "amplitude":
+        raise ValueError("the collapsed quadratic-form evaluation exists for amplitude embedding only")
+    M = collapsed_matrices(quantum_weights, pre.shape[1], n_layers)
+    return _CollapsedFn.apply(pre, M)
