@@ -618,6 +618,13 @@ def run_b200(args):
         except Exception as e:
             stem_inf = {"error": repr(e)[:200]}
 
+    stem_train = None
+    if not args.no_encoder and rank == 0:
+        try:
+            stem_train = run_stem_train(B, max(3, min(K, 50)), dev)
+        except Exception as e:
+            stem_train = {"error": repr(e)[:200]}
+
     enc_train = None
     if not args.no_encoder:
         try:
@@ -649,7 +656,7 @@ def run_b200(args):
             "dp_parity": dp_parity,
             "step_roofline_frac": round(step_frac, 4), "kernels": kernels, "in_graph": in_graph,
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
-            "stem_infer": stem_inf, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
+            "stem_infer": stem_inf, "stem_train": stem_train, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
         }
         emit(line)
     if world > 1:
@@ -1016,6 +1023,62 @@ def run_stem_infer(B, K, dev):
     return {"fused_ms": round(t_f, 5), "unfused_ms": round(t_u, 5), "fused_utt_per_s": round(B / t_f * 1e3, 1),
             "unfused_utt_per_s": round(B / t_u * 1e3, 1), "max_abs_diff_fused_vs_unfused": diff,
             "workload": f"inference stem, batch {B}: mel (B,80,3000) -> (B,1500,384) incl. both GELUs, permute, positional embedding"}
+
+
+def run_stem_train(B, K, dev, nsets=4):
+    """SURVEY.md 8-f1 at training time: the encoder stem AS THE MODEL RUNS IT (whisper/whisper/model.py:193-194:
+    gelu(conv1(x)), gelu(conv2(x))) forward + backward through the nn.Module API, inputs resident in HBM, whole step captured as
+    one CUDA graph per input set.  `fused_gelu`: QuantumConv1d.forward_gelu (GELU in the forward epilogue, gelu' in the backward's gy
+    pass: no activation pass of its own in either direction); `op_by_op`: the plain operators + ATen GELU (three extra passes over
+    the (B,384,3000) / (B,384,1500) tensors per layer and direction-pair)."""
+    import torch.nn.functional as F
+
+    from qasr_ijcnlp_b200 import QuantumConv1d
+
+    torch.manual_seed(0)
+    c1 = QuantumConv1d(N_MELS, N_STATE, kernel_size=3, padding=1, n_qubits=Q).to(dev)
+    c2 = QuantumConv1d(N_STATE, N_STATE, kernel_size=3, stride=2, padding=1, n_qubits=Q).to(dev)
+    params = list(c1.parameters()) + list(c2.parameters())
+    xs = [torch.rand(B, N_MELS, 3000, device=dev) * 3 - 1.5 for _ in range(nsets)]
+
+    def step(fused, x):
+        y = c2.forward_gelu(c1.forward_gelu(x)) if fused else F.gelu(c2(F.gelu(c1(x))))
+        loss = y.square().mean()
+        return loss, torch.autograd.grad(loss, params)
+
+    out = {}
+    ref = None
+    for fused in (True, False):
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            for _ in range(3):
+                step(fused, xs[0])
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        graphs = []
+        for x in xs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap):
+                res = step(fused, x)
+            graphs.append((g, res))
+        torch.cuda.synchronize()
+        for i in range(4):
+            graphs[i % nsets][0].replay()
+        ms = time_events(lambda i: graphs[i % nsets][0].replay(), K) / K
+        graphs[0][0].replay()
+        torch.cuda.synchronize()
+        loss, grads = graphs[0][1]
+        flat = torch.cat([loss.reshape(1)] + [t.reshape(-1) for t in grads]).clone()
+        if ref is None:
+            ref = flat
+        out["fused_gelu" if fused else "op_by_op"] = {"ms_per_step": round(ms, 5), "utt_per_s": round(B / ms * 1e3, 1)}
+        if not fused:
+            out["max_rel_diff_loss_and_grads"] = float(((flat - ref).abs() / ref.abs().clamp(min=1.0)).max())
+    out["speedup"] = round(out["op_by_op"]["ms_per_step"] / out["fused_gelu"]["ms_per_step"], 3)
+    out["workload"] = (f"stem training step incl. both GELUs, batch {B}: mel (B,80,3000) -> gelu(conv1) -> gelu(conv2) -> loss, backward to all "
+                       f"ten parameter gradients; nn.Module API, one CUDA graph per input set, {nsets} rotating sets")
+    return out
 
 
 def run_encoder_train(B, K, dev, world, rank):

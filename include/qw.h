@@ -28,6 +28,8 @@ extern "C" {
 #define QW_EMB_AMPLITUDE 0
 #define QW_EMB_ANGLE 1
 #define QW_ABI_VERSION 1
+#define QW_ACT_NONE 0
+#define QW_ACT_GELU 1
 
 /* ABI version / build info. */
 int qw_abi_version(void);
@@ -57,6 +59,7 @@ void qw_set_fast_path(int enable);
  * is initialised from the environment variable QW_<name> on first use.  Process-global and NOT re-entrant: do not change an
  * option while another thread is inside a qw_* call.  Returns 0, or -1 for an unknown name. */
 int qw_set_option(const char* name, int value);
+int qw_get_option(const char* name); /* current value, or -1 for an unknown name */
 
 /* ---- QuantumConv1d.forward  (quantum_whisper.py:95-128; circuit :64-85; params :58-59,88)
  * x (B,C,L) -> y (B,O,L_out), L_out = (L+2P-K)/S+1 (:103).  w_pre (q, C*K) with column c*K+k (:58,:111),
@@ -102,6 +105,23 @@ int qw_conv1d_backward_dp(const float* gy, const float* x, const float* pre_save
                           float* gb_post, void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O,
                           int q, int n_layers, int embedding, void* const* peer_bufs, void* const* peer_flags, int rank,
                           int world, float scale, void* stream);
+
+/* ---- the layer with the activation that follows it in the encoder stem FUSED (whisper/whisper/model.py:193-194:
+ * x = F.gelu(self.conv1(x)); x = F.gelu(self.conv2(x)), exact-erf GELU): training-time counterpart of qw_stem_forward.
+ * forward:  y = gelu(post_conv(<Z>)) is what gets stored (the pre-activation never exists in HBM); pre_save as qw_conv1d_forward.
+ * backward: gy is the gradient wrt that ACTIVATED output; the gy kernel multiplies every staged tile by gelu'(post_conv(<Z>)),
+ *           rebuilt from the 16 bytes per window in pre_save (needs b_post), before its contractions -- so neither the GELU forward
+ *           (read + write of the (B,O,L_out) tensor) nor the GELU backward (two reads + a write) ever runs as a separate pass.
+ * activation: QW_ACT_NONE (then identical to qw_conv1d_forward / qw_conv1d_backward) or QW_ACT_GELU.  Fast-path regime only
+ * (fp32, n_qubits = 4, amplitude embedding, K = 3, stride 1|2, padding 1, aligned shapes): -2 otherwise -- apply the plain operator
+ * and a separate GELU instead (qasr_ijcnlp_b200.QuantumConv1d.forward_gelu does). */
+int qw_conv1d_forward_act(const float* x, const float* w_pre, const float* b_pre, const float* qw, const float* w_post,
+                          const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O, int q,
+                          int n_layers, int embedding, int activation, void* stream);
+int qw_conv1d_backward_act(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qw,
+                           const float* w_post, const float* b_post, float* gx, float* gw_pre, float* gb_pre, float* gqw,
+                           float* gw_post, float* gb_post, void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P,
+                           int O, int q, int n_layers, int embedding, int activation, void* stream);
 
 /* ---- fused INFERENCE forward of the encoder stem (whisper/whisper/model.py:193-198 with the two QuantumConv1d layers of
  * quantum_whisper.py:136-137):

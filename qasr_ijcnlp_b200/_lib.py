@@ -35,11 +35,14 @@ _SIGNATURES = {
     "qw_timeline_set": (_I, [_P, _I]),
     "qw_set_fast_path": (None, [_I]),
     "qw_set_option": (_I, [ctypes.c_char_p, _I]),
+    "qw_get_option": (_I, [ctypes.c_char_p]),
     "qw_conv1d_forward": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_forward_f64": (_I, [_P] * 8 + _CONV_DIMS + [_P]),
     "qw_conv1d_workspace_bytes": (_SZ, [_I] * 10),
     "qw_conv1d_backward": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [_P]),
     "qw_conv1d_backward_f64": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [_P]),
+    "qw_conv1d_forward_act": (_I, [_P] * 8 + _CONV_DIMS + [_I, _P]),
+    "qw_conv1d_backward_act": (_I, [_P] * 13 + [_P, _SZ] + _CONV_DIMS + [_I, _P]),
     "qw_conv1d_dp_buffer_bytes": (_SZ, [_I] * 10),
     "qw_conv1d_dp_flag_bytes": (_SZ, [_I] * 10),
     "qw_conv1d_backward_dp": (_I, [_P] * 12 + [_P, _SZ] + _CONV_DIMS + [ctypes.POINTER(_P), ctypes.POINTER(_P), _I, _I, ctypes.c_float, _P]),

@@ -120,6 +120,13 @@ int qw_set_option(const char* name, int value) {
   if (r != 0) qw::set_error("qw_set_option: unknown option '%s'", name ? name : "(null)");
   return r;
 }
+int qw_get_option(const char* name) {
+  if (!name) return -1;
+  if (strncmp(name, "QW_", 3) == 0) name += 3;
+  for (int i = 0; i < qw::kOptCount; ++i)
+    if (strcmp(name, qw::kOptDefs[i].name) == 0) return qw::option((qw::Option)i);
+  return -1;
+}
 void qw_set_fast_path(int enable) { qw::set_option("FAST_PATH", enable != 0); }
 const char* qw_last_error(void) { return qw::g_err; }
 long long qw_launch_count(void) { return qw::g_launches.load(std::memory_order_relaxed); }

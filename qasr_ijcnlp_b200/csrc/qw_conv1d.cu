@@ -81,10 +81,20 @@ static int check_dims(ConvDims& d) {
 
 template <typename T>
 static int conv1d_forward_impl(const T* x, const T* w_pre, const T* b_pre, const T* qwts, const T* w_post, const T* b_post,
-                               T* y, T* pre_save, ConvDims d, void* stream) {
+                               T* y, T* pre_save, ConvDims d, void* stream, int act = 0) {
   QW_CHECK_ARG(x && w_pre && b_pre && qwts && w_post && b_post && y, -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  QW_CHECK_ARG(act == 0 || act == QW_ACT_GELU, -2, "activation=%d is neither none (0) nor gelu (1)", act);
+  if (act) {
+    // the fused activation exists in the fast-path kernels only: callers fall back to the plain operator + a separate GELU
+    if constexpr (sizeof(T) == 4) {
+      if (!is_general(d) && fast_eligible(d, x, y, pre_save, true))
+        return fast_forward(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, st, act);
+    }
+    set_error("the fused activation needs the fast-path regime (fp32, n_qubits=4, amplitude embedding, K=3, stride 1|2, padding 1, aligned shapes)");
+    return -2;
+  }
   if (is_general(d)) return gen::general_forward<T>(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, st);
   if constexpr (sizeof(T) == 4) {
     if (fast_eligible(d, x, y, pre_save, true)) return fast_forward(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, st);
@@ -102,7 +112,8 @@ static int conv1d_forward_impl(const T* x, const T* w_pre, const T* b_pre, const
 template <typename T>
 static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* qwts, const T* w_post,
                                 T* gx, T* gw_pre, T* gb_pre, T* gqw, T* gw_post, T* gb_post, void* workspace,
-                                size_t ws_bytes, ConvDims d, void* stream, const FastDp* dp = nullptr) {
+                                size_t ws_bytes, ConvDims d, void* stream, const FastDp* dp = nullptr, const T* b_post = nullptr,
+                                int act = 0) {
   QW_CHECK_ARG(gy && x && pre_save && w_pre && qwts && w_post && gw_pre && gb_pre && gqw && gw_post && gb_post && workspace,
                -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
@@ -111,16 +122,21 @@ static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, cons
   unsigned char* ws = (unsigned char*)workspace;
   const bool want_dp = dp && dp->world > 1;
   QW_CHECK_ARG(!(want_dp && is_general(d)), -2, "the fused gradient all-reduce needs the fast-path regime (n_qubits=4, amplitude embedding)");
-  if (is_general(d))
+  QW_CHECK_ARG(act == 0 || act == QW_ACT_GELU, -2, "activation=%d is neither none (0) nor gelu (1)", act);
+  QW_CHECK_ARG(!act || b_post, -1, "the fused activation needs post_conv.bias");
+  if (is_general(d)) {
+    QW_CHECK_ARG(!act, -2, "the fused activation needs the fast-path regime (n_qubits=4, amplitude embedding)");
     return gen::general_backward<T>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, ws_bytes, d, st);
+  }
   QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
   if constexpr (sizeof(T) == 4) {
     if (fast_eligible(d, x, gy, gx, false) && (((uintptr_t)pre_save) & 15) == 0) {
       const FastPlan fp = make_fast_plan(d);
       QW_CHECK_ARG(ws_bytes >= fp.ws_bytes, -3, "workspace too small: %zu < %zu", ws_bytes, fp.ws_bytes);
-      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st, dp);
+      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st, dp, b_post, act);
     }
   }
+  QW_CHECK_ARG(!act, -2, "the fused activation needs the fast-path regime (fp32, K=3, stride 1|2, L %% 4 == 0, O %% 4 == 0, aligned tensors)");
   QW_CHECK_ARG(!want_dp, -2, "the fused gradient all-reduce needs the fast-path regime (fp32, K=3, stride 1|2, L %% 4 == 0, O %% 4 == 0, aligned tensors)");
   const Plan p = make_plan(d);
   const WsLayout<T> wl = ws_layout<T>(d, p);
@@ -241,6 +257,21 @@ int qw_conv1d_backward_f64(const double* gy, const double* x, const double* pre_
   ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
   return qw::conv1d_backward_impl<double>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
                                           workspace, ws_bytes, d, stream);
+}
+
+int qw_conv1d_forward_act(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
+                          const float* b_post, float* y, float* pre_save, int B, int C, int L, int K, int S, int P, int O, int q,
+                          int n_layers, int embedding, int activation, void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  return qw::conv1d_forward_impl<float>(x, w_pre, b_pre, qwts, w_post, b_post, y, pre_save, d, stream, activation);
+}
+int qw_conv1d_backward_act(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
+                           const float* w_post, const float* b_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post,
+                           float* gb_post, void* workspace, size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O, int q,
+                           int n_layers, int embedding, int activation, void* stream) {
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  return qw::conv1d_backward_impl<float>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
+                                         workspace, ws_bytes, d, stream, nullptr, b_post, activation);
 }
 
 size_t qw_conv1d_dp_buffer_bytes(int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int world) {

@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "../../include/qw.h"
+#include "qw_act.cuh"
 #include "qw_conv1d_plan.cuh"
 #include "qw_tma.cuh"
 
@@ -46,6 +47,7 @@ struct FastFwdArgs {
   int early_tma;
   unsigned long long* tl;
   int dbg;  // experiment switch DBG_FWD (results are garbage): 1 = skip the pre_conv FMAs, 2 = skip the post_conv FMAs, 4 = skip the circuit
+  int act;  // 1: store gelu(post_conv(<Z>)) -- the activation that follows the layer in the encoder stem, fused into the epilogue
 };
 
 constexpr int kFwdStages = 4;
@@ -70,7 +72,7 @@ __host__ __device__ constexpr size_t fast_fwd_smem_bytes(int CK, int O, int Lq) 
 // Hand-offs: pfull/pempty (part), ofull/oempty (outs).  No CTA-wide barrier inside the loop.
 // (Specialising this kernel for n_layers == 1 like the adjoint kernel -- 56 -> 48 KB of SASS, 96 -> 72 registers -- changed
 // nothing: 131.9 us per step either way.  Its circuit code is one warp's side job, not the whole kernel.)
-template <int S, int RC>
+template <int S, int RC, bool ACT>
 __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const FastFwdArgs a) {
   const int Lq = a.Lq;
   constexpr int XW = fwd_xw<S>();
@@ -307,6 +309,9 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
         r.z = fmaf(wv.w, ov[2][3], fmaf(wv.z, ov[2][2], fmaf(wv.y, ov[2][1], fmaf(wv.x, ov[2][0], bv))));
         r.w = fmaf(wv.w, ov[3][3], fmaf(wv.z, ov[3][2], fmaf(wv.y, ov[3][1], fmaf(wv.x, ov[3][0], bv))));
         }
+        if (ACT) {
+          r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
+        }
         if (store_ok) st4(yb + (size_t)o * a.Lout, r);
       }
     }
@@ -330,6 +335,8 @@ struct FastGy2Args {
   int B, O, Lout, tiles_per_utt, num_tiles, PA1;
   int tw;  // tile stride in windows (the qout box has tw rows)
   unsigned long long* tl;
+  const float* b_post = nullptr;  // fused activation (tensor-pipe kernel only)
+  int act = 0;
 };
 // NW warps, one thread per stage row (stage = 32*NW output channels x 32 windows), NST-deep ring
 __host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O, int NW, int NST) {
@@ -524,7 +531,8 @@ constexpr int kGy3Warps = 8, kGy3Threads = 32 * kGy3Warps, kGy3Rows = 192, kGy3S
 constexpr int kGy3Bpw = kGy3Rows / 8 / kGy3Warps;  // 8-channel blocks of a stage per warp (24 blocks over 8 warps: an even load on the 4 sub-partitions)
 static_assert(kGy3Bpw * kGy3Warps * 8 == kGy3Rows, "stage rows must split evenly over the warps");
 __host__ __device__ constexpr size_t fast_gy3_smem_bytes() {
-  return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 + 2 * kGy3Stages * 8;
+  return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 +
+         (3 * kGy3Stages + 2 * 6 + 1) * 8;  // barrier block laid out as in the fused forms
 }
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(v) & 0xffffe000u;
@@ -571,6 +579,8 @@ struct FastGy3Args {
   int B, C, O, Lout, LP, tiles_per_utt, num_tiles, PA1, PA2, PB;
   unsigned long long* tl;
   int dbg;  // experiment switch DBG_GY: 1 = skip the contractions (streaming floor of the kernel); results are garbage
+  const float* b_post;  // act != 0 only
+  int act;  // 1: the incoming gradient is that of gelu(post_conv(<Z>)): every stage is multiplied by gelu'(post_conv(<Z>)) in place first
 };
 struct RegGateAcc {
   float m[FQ][8];
@@ -596,7 +606,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 }
 __device__ __forceinline__ void bar_sync_streaming() { asm volatile("bar.sync 1, %0;" ::"n"(kGy3Threads) : "memory"); }
 
-template <int NHALF, int FUSED>
+template <int NHALF, int FUSED, bool ACT>
 __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
     fast_bwd_gy3_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_qout,
                         const __grid_constant__ CUtensorMap tm_pre, const __grid_constant__ CUtensorMap tm_x, const FastGy3Args a) {
@@ -790,6 +800,9 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
         const int gn = gs + kGy3Stages - 1;
         if (gn < total_stages) {
           if (gn >= kGy3Stages) mbar_wait(&empty[gn % kGy3Stages], ((gn / kGy3Stages) - 1) & 1);
+          // the slot was rewritten in place by generic-proxy stores (fused activation) that the empty barrier has ordered before
+          // this point: one proxy fence in the issuing thread orders them before the TMA engine's refill
+          if (ACT) fence_proxy_async();
           issue(gn);
         }
       }
@@ -810,6 +823,34 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
             aq[kb][2 * e + 1] = one_g0;
           }
         }
+      }
+      if (ACT) {
+        // fused activation backward: g <- g * gelu'(z), z = post_conv(<Z>) rebuilt from the 16 bytes per window the forward saved
+        // (the pre-activation itself is never stored).  In place on the stage, one pass, 128-byte rows; then everybody syncs.
+        // Measured on B200 (batch 16, conv1): this pass takes the kernel from 28 to 70 us -- 27 instructions per element at the
+        // ~0.4 IPC these kernels run at (the arithmetic of gelu' is only 9 us of it; the rest is the loads, z and the in-place store)
+        // -- against ~45 us for ATen's separate gelu_backward pass (two reads + a write of the tensor) plus the 28 us kernel.
+        float* gmut = stages + (size_t)s * SE;
+        for (int u = tid; u < kGy3Rows * 8; u += kGy3Threads) {
+          const int rl = u >> 3, c = u & 7, r = h * kGy3Rows + rl;
+          if (r < a.O) {
+            float* p = gmut + swz128(rl, c);
+            float4 gv = ld4(p);
+            // post_conv weights / bias straight from global memory (7.7 KB, L1-resident): keeping them in shared memory pushed the
+            // CTA past 98 KB and the SM to ONE resident CTA (the 196 KB carve-out), which doubled the kernel time
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w_post) + r);
+            const float bv = __ldg(a.b_post + r);
+            float* ge = reinterpret_cast<float*>(&gv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 q4 = ld4(os + (4 * c + e) * FQ);
+              const float z = fmaf(wv.w, q4.w, fmaf(wv.z, q4.z, fmaf(wv.y, q4.y, fmaf(wv.x, q4.x, bv))));
+              ge[e] *= gelu_erf_grad(z);
+            }
+            st4(p, gv);
+          }
+        }
+        __syncthreads();
       }
       if (a.dbg) {
         d2[0][0] += gsm[tid];
@@ -1444,13 +1485,13 @@ FastPlan make_fast_plan(const ConvDims& d) {
   return p;
 }
 
-template <int S, int RC>
-static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const FastPlan& p, cudaStream_t st) {
+template <int S, int RC, bool ACT>
+static int launch_fast_fwd_t(const CUtensorMap& tm, const FastFwdArgs& a, const FastPlan& p, cudaStream_t st) {
   const size_t smem = fast_fwd_smem_bytes<S, RC>(a.C * 3, a.O, a.Lq);
   QW_CHECK_ARG(smem <= 227 * 1024, -2, "fast forward needs %zu bytes of shared memory", smem);
-  auto k = fast_fwd_kernel<S, RC>;
+  auto k = fast_fwd_kernel<S, RC, ACT>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  note_symbol(kKFwd, "fast_fwd_kernel<%d, %d>", S, RC);
+  note_symbol(kKFwd, "fast_fwd_kernel<%d, %d, %d>", S, RC, (int)ACT);
   {
     KernelTimer kt(kKFwd, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridF), dim3(kFwdThreads), smem, st, tm, a));
@@ -1458,16 +1499,20 @@ static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const Fa
   QW_CUDA_OK(cudaGetLastError());
   return 0;
 }
+template <int S, int RC>
+static int launch_fast_fwd(const CUtensorMap& tm, const FastFwdArgs& a, const FastPlan& p, cudaStream_t st) {
+  return a.act ? launch_fast_fwd_t<S, RC, true>(tm, a, p, st) : launch_fast_fwd_t<S, RC, false>(tm, a, p, st);
+}
 
 int fast_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
-                 const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st) {
+                 const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st, int act) {
   const FastPlan p = make_fast_plan(d);
   alignas(64) CUtensorMap tm;
   const int xw = d.S == 1 ? fwd_xw<1>() : fwd_xw<2>();
   if (int e = make_tmap_3d_f32(&tm, x, d.L, d.C, d.B, xw, p.rc, false)) return e;
   const size_t W = (size_t)d.B * d.Lout;
   FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
-                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot(), option(kOptDbgFwd)};
+                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot(), option(kOptDbgFwd), act};
   if (d.S == 1) {
     switch (p.rc) {
       case 32: return launch_fast_fwd<1, 32>(tm, a, p, st);
@@ -1503,19 +1548,27 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
 // gy 14.7 / 23.2 vs 12.9 / 21.8 us) -- the extra warps do not raise the issue rate of the two contractions, the 2-deep ring
 // loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.  Also measured and dropped:
 // 3 CTAs per SM of the 6-warp form with a 2-deep ring (444 CTAs): 139.2 us.
-template <int NHALF, int FUSED>
-static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
-                           const FastPlan& p, cudaStream_t st) {
+template <int NHALF, int FUSED, bool ACT>
+static int launch_fast_gy3_t(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
+                             const FastPlan& p, cudaStream_t st) {
   const size_t smem = FUSED ? fast_gy3_fused_smem_bytes() : fast_gy3_smem_bytes();
-  auto k = fast_bwd_gy3_kernel<NHALF, FUSED>;
+  auto k = fast_bwd_gy3_kernel<NHALF, FUSED, ACT>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  note_symbol(FUSED ? kKBwdFused : kKBwdPost, "fast_bwd_gy3_kernel<%d, %d>", NHALF, FUSED);
+  note_symbol(FUSED ? kKBwdFused : kKBwdPost, "fast_bwd_gy3_kernel<%d, %d, %d>", NHALF, FUSED, (int)ACT);
   {
     KernelTimer kt(FUSED ? kKBwdFused : kKBwdPost, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(FUSED ? kGy3Threads + 32 : kGy3Threads), smem, st, tg, tq, tp, tx, a));
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
+}
+template <int NHALF, int FUSED>
+static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
+                           const FastPlan& p, cudaStream_t st) {
+  if constexpr (FUSED == 0) {
+    if (a.act) return launch_fast_gy3_t<NHALF, 0, true>(tg, tq, tp, tx, a, p, st);
+  }
+  return launch_fast_gy3_t<NHALF, FUSED, false>(tg, tq, tp, tx, a, p, st);
 }
 template <int FUSED>
 static int launch_fast_gy3_any(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
@@ -1528,7 +1581,7 @@ static int launch_fast_gy3_any(const CUtensorMap& tg, const CUtensorMap& tq, con
 static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
   // default: the tensor-pipe form (fast_bwd_gy3_kernel); QW_GY_MMA=0 selects the FFMA form for A/B
   if (flag_gy_mma() && p.tw == FTW) {
-    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, nullptr, a.B, 0, a.O, a.Lout, 0, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl, option(kOptDbgGy)};
+    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, nullptr, a.B, 0, a.O, a.Lout, 0, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl, option(kOptDbgGy), a.b_post, a.act};
     return launch_fast_gy3_any<0>(tg, tq, tq, tq, a3, p, st);
   }
   const int forced = option(kOptGyWarps);
@@ -1559,7 +1612,7 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
 
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
-                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp) {
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp, const float* b_post, int act) {
   const FastPlan p = make_fast_plan(d);
   const size_t W = (size_t)d.B * d.Lout;
   float* gpre = reinterpret_cast<float*>(ws + p.off_gpre);
@@ -1576,7 +1629,8 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   // mode 1 = data layer (no grad_x, stride 1): pre_conv^T as well -- the whole backward is that kernel + finalize;
   // mode 2 = gpre goes to the workspace for the pre_conv^T kernel below.
   int fused = 0;
-  if (flag_bwd_fused() && flag_gy_mma() && d.Lq == 1 && p.tw == FTW && (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy)
+  QW_CHECK_ARG(!act || (flag_gy_mma() && b_post), -2, "the fused activation needs the tensor-pipe gy kernel (option GY_MMA=1) and post_conv.bias");
+  if (!act && flag_bwd_fused() && flag_gy_mma() && d.Lq == 1 && p.tw == FTW && (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy)
     fused = (gx == nullptr && d.S == 1 && d.P == 1 && d.C <= kFbXRows && flag_bwd_fused() == 1) ? 1 : 2;
   if (fused) {
     alignas(64) CUtensorMap tm_pre, tm_xf;
@@ -1584,7 +1638,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
     if (fused == 1)
       if (int e = make_tmap_3d_f32(&tm_xf, x, d.L, d.C, d.B, kFbXW, kFbXRows, false)) return e;
     FastGy3Args a{w_post, qwts, nullptr, part1, part2, part3, gpre, d.B, d.C, d.O, d.Lout, p.LP, p.tiles_per_utt, p.num_tiles, p.PA1, p.PA2,
-                  p.PB, timeline_next_slot(), 0};
+                  p.PB, timeline_next_slot(), 0, nullptr, 0};
     if (int e = fused == 1 ? launch_fast_gy3_any<1>(tm_gy, tm_qout, tm_pre, tm_xf, a, p, st)
                            : launch_fast_gy3_any<2>(tm_gy, tm_qout, tm_pre, tm_pre, a, p, st))
       return e;
@@ -1608,7 +1662,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   }
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
   if (!fused) {
-    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot()};
+    FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot(), b_post, act};
     if (int e = launch_fast_gy2_any(tm_gy, tm_qout, a, p, st)) return e;
   }
   // 2) adjoint differentiation of the circuit, one window per thread

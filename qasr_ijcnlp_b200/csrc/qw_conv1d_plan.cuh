@@ -68,10 +68,11 @@ struct FastAdjArgs {
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd);
 FastPlan make_fast_plan(const ConvDims& d);
 int fast_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
-                 const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st);
+                 const float* b_post, float* y, float* pre_save, const ConvDims& d, cudaStream_t st, int act = 0);
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
-                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp = nullptr);
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp = nullptr, const float* b_post = nullptr,
+                  int act = 0);
 
 // fused inference stem (qw_stem.cu)
 size_t stem_workspace_bytes(int B, int L);

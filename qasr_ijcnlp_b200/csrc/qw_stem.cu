@@ -15,6 +15,7 @@
 //
 // Inference only: nothing is saved for a backward pass (training goes through the two QuantumConv1d operators).
 #include "../../include/qw.h"
+#include "qw_act.cuh"
 #include "qw_async.cuh"
 #include "qw_conv1d_plan.cuh"
 
@@ -31,26 +32,6 @@ constexpr int kQ1Slots = kQ1Cols + kQ1Cols / 8;   // skewed by one float4 per 8 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ int q1_slot(int p) { return p + (p >> 3); }
-// torch.nn.functional.gelu (approximate='none'): 0.5 v (1 + erf(v / sqrt 2)) = max(v, 0) - 0.5 |v| erfc(|v| / sqrt 2).
-// The second form has no 1 - e cancellation, and erfc(u / sqrt 2) = 2^(-u Q(u)) with Q a degree-7 polynomial (weighted
-// least-squares fit on [0, 6] of -log2(erfc(u / sqrt 2)) / u, weight u erfc: the error of the RESULT is what is minimised;
-// Q stays > 4.8 beyond 6, so the tail underflows to the right limit).  11 instructions instead of erff's 24 (two coefficient
-// sets + selects), max |error| 2.7e-7 against the fp64 GELU on [-40, 40] -- ATen's own fp32 gelu is 1.2e-6 off on that range.
-// The factor 0.5 rides in the exponent (-u Q - 1) and the final subtraction is one fma.
-__device__ __forceinline__ float gelu_erf(float v) {
-  const float u = fabsf(v);
-  float q = 2.8103786462452263e-06f;
-  q = fmaf(q, u, -3.908000508090481e-05f);
-  q = fmaf(q, u, 0.00018477895355317742f);
-  q = fmaf(q, u, 0.00014021758397575468f);
-  q = fmaf(q, u, -0.007067482452839613f);
-  q = fmaf(q, u, 0.05249877646565437f);
-  q = fmaf(q, u, 0.4592074155807495f);
-  q = fmaf(q, u, 1.151105284690857f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(-u, q, -1.f)));
-  return fmaf(-u, e, fmaxf(v, 0.f));
-}
 __device__ __forceinline__ void bar_stream() { asm volatile("bar.sync 1, %0;" ::"n"(kSW * 32) : "memory"); }
 
 struct Stem2Args {

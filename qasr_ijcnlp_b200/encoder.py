@@ -141,7 +141,19 @@ class QuantumAudioEncoder(AudioEncoder):
             for blk in self.blocks:
                 x = blk(x)
             return self.ln_post(x)
-        return super().forward(x)
+        if not self.fused_stem:
+            return super().forward(x)
+        # training (or a shape outside the fused inference kernel): the two operators with their GELUs fused into them
+        # (QuantumConv1d.forward_gelu: no separate activation pass in either direction); the rest as AudioEncoder.forward
+        x = self.conv1.forward_gelu(x)
+        x = self.conv2.forward_gelu(x)
+        x = x.permute(0, 2, 1)
+        if x.shape[1:] != self.positional_embedding.shape:
+            raise AssertionError("incorrect audio shape")  # whisper/model.py:197
+        x = (x + self.positional_embedding).to(x.dtype)
+        for blk in self.blocks:
+            x = blk(x)
+        return self.ln_post(x)
 
 
 class QuantumWhisper(nn.Module):

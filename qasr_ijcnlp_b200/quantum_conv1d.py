@@ -93,6 +93,59 @@ class _QuantumConv1dFn(torch.autograd.Function):
         return gx, gw_pre, gb_pre, gqw, gw_post, gb_post, None, None, None, None, None, None
 
 
+class _QuantumConv1dGeluFn(torch.autograd.Function):
+    """y = gelu(QuantumConv1d(x)) with the activation fused into the layer's kernels (qw_conv1d_forward_act / _backward_act):
+    the pre-activation tensor never exists in HBM and neither GELU pass (forward, backward) runs on its own."""
+
+    @staticmethod
+    def forward(ctx, x, w_pre, b_pre, qw, w_post, b_post, K, S, P, n_layers):
+        lib = _lib.load()
+        B, C, L = x.shape
+        O, q = w_post.shape
+        Lout = out_length(L, K, S, P)
+        x = x.contiguous()
+        params = [t.contiguous() for t in (w_pre, b_pre, qw, w_post, b_post)]
+        y = torch.empty(B, O, Lout, device=x.device, dtype=x.dtype)
+        need_bwd = any(ctx.needs_input_grad[:6])
+        pre_save = torch.empty(2, B * Lout, q, device=x.device, dtype=x.dtype) if need_bwd else None
+        with torch.cuda.device(x.device):
+            st = lib.qw_conv1d_forward_act(_ptr(x), *[_ptr(p) for p in params], _ptr(y), _ptr(pre_save),
+                                           B, C, L, K, S, P, O, q, n_layers, 0, 1, _stream())
+        _lib.check(st, "qw_conv1d_forward_act")
+        if need_bwd:
+            ctx.save_for_backward(x, pre_save, *params)
+            ctx.cfg = (B, C, L, K, S, P, O, q, n_layers)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, pre_save, w_pre, b_pre, qw, w_post, b_post = ctx.saved_tensors
+        B, C, L, K, S, P, O, q, n_layers = ctx.cfg
+        gy = gy.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        grads = [torch.empty_like(t) for t in (w_pre, b_pre, qw, w_post, b_post)]
+        nbytes = lib.qw_conv1d_workspace_bytes(B, C, L, K, S, P, O, q, n_layers, 4)
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        with torch.cuda.device(x.device):
+            st = lib.qw_conv1d_backward_act(_ptr(gy), _ptr(x), _ptr(pre_save), _ptr(w_pre), _ptr(qw), _ptr(w_post), _ptr(b_post), _ptr(gx),
+                                            *[_ptr(g) for g in grads], _ptr(ws), nbytes, B, C, L, K, S, P, O, q, n_layers, 0, 1, _stream())
+        _lib.check(st, "qw_conv1d_backward_act")
+        return (gx, *grads, None, None, None, None)
+
+
+def gelu_fusion_eligible(x, w_post, kernel_size, stride, padding, n_layers, embedding) -> bool:
+    """Shapes the activation-fused kernels cover (the fast-path regime of csrc/qw_conv1d_fast.cu, forward needs padding 1)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and embedding == "amplitude"):
+        return False
+    O, q = w_post.shape
+    L = x.shape[2]
+    Lout = out_length(L, kernel_size, stride, padding)
+    return (q == 4 and kernel_size == 3 and stride in (1, 2) and padding == 1 and n_layers <= 4 and L % 4 == 0 and Lout % 4 == 0
+            and O % 4 == 0 and O <= 576 and x.shape[1] * 3 * 16 <= 96 * 1024 and _lib.load().qw_get_option(b"GY_MMA") != 0
+            and _lib.load().qw_get_option(b"FAST_PATH") != 0)
+
+
 def quantum_conv1d(x, w_pre, b_pre, quantum_weights, w_post, b_post, kernel_size, stride=1, padding=0,
                    n_layers=1, embedding="amplitude", grad_allreduce=None):
     """Functional form.  x: (B, C, L) CUDA float32 (or float64 for the validation build)."""
@@ -164,6 +217,17 @@ class QuantumConv1d(nn.Module):
         return quantum_conv1d(x, self.pre_conv.weight, self.pre_conv.bias, self.quantum_weights,
                               self.post_conv.weight, self.post_conv.bias, self.kernel_size, self.stride,
                               self.padding, self.n_layers, self.embedding, self._grad_allreduce)
+
+    def forward_gelu(self, x: torch.Tensor) -> torch.Tensor:
+        """``F.gelu(self(x))`` -- what the encoder does with both stem layers (whisper/whisper/model.py:193-194) -- with the GELU
+        fused into the layer's forward epilogue and its derivative into the backward's gy pass when the shape is in the fast-path
+        regime (same result up to the 3e-7 error of the fused erf GELU; saves two full passes over the (B, O, L_out) tensor in
+        the forward and three in the backward); otherwise exactly ``F.gelu(self(x))``."""
+        if (self._grad_allreduce is None and x.dim() == 3 and x.shape[1] == self.in_channels
+                and gelu_fusion_eligible(x, self.post_conv.weight, self.kernel_size, self.stride, self.padding, self.n_layers, self.embedding)):
+            return _QuantumConv1dGeluFn.apply(x, self.pre_conv.weight, self.pre_conv.bias, self.quantum_weights, self.post_conv.weight,
+                                              self.post_conv.bias, self.kernel_size, self.stride, self.padding, self.n_layers)
+        return torch.nn.functional.gelu(self.forward(x))
 
     def extra_repr(self) -> str:
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "

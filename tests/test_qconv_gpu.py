@@ -299,6 +299,60 @@ def test_stem_layers_batch16_full_parity(cuda, layer):
         _set_opt(lib, "BWD_FUSED", 0)
 
 
+@pytest.mark.parametrize("C,S,B,L", [(80, 1, 2, 3000), (384, 2, 2, 3000), (384, 2, 16, 3000), (40, 2, 3, 136), (96, 1, 1, 260)])
+def test_gelu_fused_layer(cuda, C, S, B, L):
+    """SURVEY.md 8-f1 at training time: `QuantumConv1d.forward_gelu` == F.gelu(layer(x)) (whisper/whisper/model.py:193-194) with
+    the GELU inside the forward epilogue and gelu' inside the backward's gy pass.  Output and all six gradients against the fp64
+    oracle composed with torch's exact GELU (5e-5 abs on y, 5e-5 relative to max(1, |ref|) on the gradients), and against the
+    unfused device path (plain operator + ATen GELU); the fused path must take exactly the layer's own launches (no GELU kernel)."""
+    _lib, qc = _mods()
+    torch.manual_seed(41)
+    m = qc.QuantumConv1d(C, 384, 3, stride=S, padding=1, n_qubits=4).to(cuda)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, C, L, generator=g) * 1.5
+    Lo = qo.out_length(L, 3, S, 1)
+    gy = torch.randn(B, 384, Lo, generator=g)
+    params = [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias]
+    # oracle: fp64, exact erf GELU
+    leaves = [p.detach().cpu().double().requires_grad_(True) for p in params]
+    xo = x.double().requires_grad_(True)
+    yo = torch.nn.functional.gelu(qo.qconv1d_forward(xo, *leaves, K=3, S=S, P=1))
+    ref = torch.autograd.grad(yo, [xo] + leaves, gy.double())
+    xc = x.to(cuda).requires_grad_(True)
+    n0 = _lib.launch_count()
+    y = m.forward_gelu(xc)
+    n_fwd = _lib.launch_count() - n0
+    got = torch.autograd.grad(y, [xc] + params, gy.to(cuda))
+    torch.cuda.synchronize()
+    assert n_fwd == 1 and _lib.launch_count() - n0 == 5  # forward kernel + gy / adjoint / pre_conv^T / finalize: the whole step
+    assert (y.detach().cpu().double() - yo.detach()).abs().max().item() <= 5e-5
+    for name, a, b in zip(["x", "w_pre", "b_pre", "qweights", "w_post", "b_post"], got, ref):
+        assert _rel(a.cpu().double(), b) <= 5e-5, name
+    # unfused device path
+    y2 = torch.nn.functional.gelu(m(xc))
+    got2 = torch.autograd.grad(y2, [xc] + params, gy.to(cuda))
+    assert (y - y2).abs().max().item() <= 2e-6
+    for name, a, b in zip(["x", "w_pre", "b_pre", "qweights", "w_post", "b_post"], got, got2):
+        assert _rel(a.double(), b.double()) <= 2e-5, name
+
+
+def test_gelu_fused_layer_falls_back_outside_the_fast_path(cuda):
+    _lib, qc = _mods()
+    torch.manual_seed(1)
+    m = qc.QuantumConv1d(7, 33, 3, stride=2, padding=0, n_qubits=3).to(cuda)  # generic kernels: no fused activation
+    x = torch.randn(2, 7, 65, device=cuda)
+    assert torch.equal(m.forward_gelu(x), torch.nn.functional.gelu(m(x)))
+    lib = _lib.load()
+    st = lib.qw_conv1d_forward_act(None, None, None, None, None, None, None, None, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, None)
+    assert st == -1  # null pointers
+    y = torch.empty(2, 33, 32, device=cuda)
+    p = [m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias]
+    P_ = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = lib.qw_conv1d_forward_act(P_(x), *[P_(t) for t in p], P_(y), None, 2, 7, 65, 3, 2, 0, 33, 3, 1, 0, 1,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == -2 and b"fast-path" in lib.qw_last_error()
+
+
 @pytest.mark.parametrize("mma", [1, 0])
 def test_gy_pass_tensor_pipe_vs_ffma(cuda, mma):
     """The gy pass of the backward exists in a tensor-pipe form (mma.sync m16n8k8, 3 x TF32 split, default) and an FFMA form:

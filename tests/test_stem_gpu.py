@@ -78,10 +78,17 @@ def test_encoder_uses_fused_stem_in_inference_only(cuda):
     assert "stem2_kernel" not in k_train and k_train.get("qconv_fwd_kernel") == 2
     assert y_train.requires_grad and not y_fused.requires_grad
     assert (y_fused - y_train.detach()).abs().max().item() <= 2e-4   # through 1 transformer block + LayerNorm
+    # training path: the two layers run with their GELUs fused (QuantumConv1d.forward_gelu); with fused_stem off the encoder is the
+    # literal op-by-op sequence of AudioEncoder.forward (separate ATen GELUs): same output and same gradients
+    loss = y_train.square().mean()
+    qparams = [p for n, p in enc.named_parameters() if "conv1" in n or "conv2" in n]
+    g_fused = torch.autograd.grad(loss, qparams)
     enc.fused_stem = False
-    with torch.no_grad():
-        y_off = enc(mel)
-    assert torch.equal(y_off, y_train.detach())
+    y_off = enc(mel)
+    assert (y_off - y_train).abs().max().item() <= 2e-5
+    g_off = torch.autograd.grad(y_off.square().mean(), qparams)
+    for a, b in zip(g_fused, g_off):
+        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item())
 
 
 def test_fused_stem_rejects_other_regimes(cuda):

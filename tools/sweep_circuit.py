@@ -50,10 +50,29 @@ for q in (4, 6, 8, 10, 12):
         bytes_fb = 4.0 * q * (2 + 3)                       # fwd: pre in, out out; bwd: pre, gout in, gpre out
         ceil = min(FMA / flop_fb, HBM / bytes_fb)
         wps = W / ((t_f + t_b) * 1e-3)
+        collapsed = None
+        if a.embedding == "amplitude":
+            # opt-in collapsed quadratic-form evaluation (SURVEY.md 8a iii), reported BESIDE the statevector numbers: same inputs,
+            # M read off the statevector kernel on q(q+1)/2 probes; timed end to end through the public function with CUDA events
+            from qasr_ijcnlp_b200 import quantum_circuit
+            pre_r, w_r = pre.clone().requires_grad_(True), (w[0] if Lq == 1 else w).clone().requires_grad_(True)
+            def both():
+                o = quantum_circuit(pre_r, w_r, n_layers=Lq, simulator="collapsed")
+                return o, torch.autograd.grad(o, [pre_r, w_r], gout)
+            o_c, (gp_c, gw_c) = both()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters): both()
+            e1.record(); torch.cuda.synchronize()
+            t_c = e0.elapsed_time(e1) / a.iters
+            collapsed = {"fwd_bwd_ms": round(t_c, 4), "windows_per_s_fwd_bwd": round(W / (t_c * 1e-3), 1),
+                         "max_abs_diff_out_vs_statevector": float((o_c - out).abs().max()),
+                         "max_rel_diff_gqw_vs_statevector": float((gw_c.reshape(-1) - gw.reshape(-1)).abs().max() / max(1.0, float(gw.abs().max())))}
         row = {"config": 4, "embedding": a.embedding, "n_qubits": q, "n_layers": Lq, "windows": W, "fwd_ms": round(t_f, 4),
                "bwd_ms": round(t_b, 4), "windows_per_s_fwd_bwd": round(wps, 1), "roofline_windows_per_s": round(ceil, 1),
                "bound": "fma" if FMA / flop_fb < HBM / bytes_fb else "hbm", "frac": round(wps / ceil, 4),
-               "fwd_windows_per_s": round(W / (t_f * 1e-3), 1)}
+               "fwd_windows_per_s": round(W / (t_f * 1e-3), 1), "collapsed": collapsed}
         rows.append(row)
         print(json.dumps(row), flush=True)
 if a.out:
