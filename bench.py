@@ -618,6 +618,13 @@ def run_b200(args):
         except Exception as e:
             stem_inf = {"error": repr(e)[:200]}
 
+    config1 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            config1 = run_config1(dev, K)
+        except Exception as e:
+            config1 = {"error": repr(e)[:200]}
+
     stem_train = None
     if not args.no_encoder and rank == 0:
         try:
@@ -656,7 +663,7 @@ def run_b200(args):
             "dp_parity": dp_parity,
             "step_roofline_frac": round(step_frac, 4), "kernels": kernels, "in_graph": in_graph,
             "calls_ms": {k: round(v, 5) for k, v in calls.items()},
-            "stem_infer": stem_inf, "stem_train": stem_train, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
+            "config1_fwd": config1, "stem_infer": stem_inf, "stem_train": stem_train, "encoder_fwd": enc, "encoder_train": enc_train, "launch_count_check": _lib.launch_count() - launches0,
         }
         emit(line)
     if world > 1:
@@ -1025,6 +1032,37 @@ def run_stem_infer(B, K, dev):
             "workload": f"inference stem, batch {B}: mel (B,80,3000) -> (B,1500,384) incl. both GELUs, permute, positional embedding"}
 
 
+def run_config1(dev, K):
+    """BASELINE.json configs[0]: QuantumConv1d(80, 384, 3, padding=1, n_qubits=4) FORWARD ALONE on batch 2 x 80 mel x 3000 frames
+    (6 000 windows) -- the reference's own CPU-runnable parity case (tests/test_qconv_gpu.py::test_config1_full_size_parity is
+    its parity check).  GPU: the C-ABI forward on HBM-resident input, CUDA events.  CPU: the literal-loop restatement of the
+    reference forward on a bounded number of output columns of the same input."""
+    import torch.nn.functional as F  # noqa: F401
+
+    from oracle import qconv_oracle as qo
+    from qasr_ijcnlp_b200 import QuantumConv1d
+
+    torch.manual_seed(0)
+    m = QuantumConv1d(N_MELS, N_STATE, 3, padding=1, n_qubits=Q)
+    x = torch.randn(2, N_MELS, N_FRAMES)
+    md = m.to(dev)
+    xs = [x.to(dev).clone() for _ in range(4)]
+    with torch.no_grad():
+        for i in range(4):
+            md(xs[i])
+        ms = time_events(lambda i: md(xs[i % 4]), max(K, 50)) / max(K, 50)
+    p64 = [t.detach().cpu().double() for t in (m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight, m.post_conv.bias)]
+    cols = 24
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        qo.qconv1d_literal(x.double(), *p64, K=3, S=1, P=1, max_windows=cols)
+    dt = time.perf_counter() - t0
+    return {"gpu_ms": round(ms, 5), "gpu_windows_per_s": round(6000 / (ms * 1e-3), 1),
+            "cpu_windows_per_s": round(2 * cols / dt, 2), "cpu_kind": _reference_kind(),
+            "cpu_sample": f"literal-loop forward, first {cols} of 3000 output columns x batch 2 in {dt:.2f} s, torch threads={torch.get_num_threads()}",
+            "workload": "QuantumConv1d(80,384,3,padding=1,n_qubits=4) forward alone, batch 2 x 80 x 3000 (6 000 windows), nn.Module call"}
+
+
 def run_stem_train(B, K, dev, nsets=4):
     """SURVEY.md 8-f1 at training time: the encoder stem AS THE MODEL RUNS IT (whisper/whisper/model.py:193-194:
     gelu(conv1(x)), gelu(conv2(x))) forward + backward through the nn.Module API, inputs resident in HBM, whole step captured as
@@ -1074,7 +1112,7 @@ def run_stem_train(B, K, dev, nsets=4):
             ref = flat
         out["fused_gelu" if fused else "op_by_op"] = {"ms_per_step": round(ms, 5), "utt_per_s": round(B / ms * 1e3, 1)}
         if not fused:
-            out["max_rel_diff_loss_and_grads"] = float(((flat - ref).abs() / ref.abs().clamp(min=1.0)).max())
+            out["max_rel_diff_loss_and_grads"] = float(((flat - ref).abs() / ref.abs().clamp(min=1.0)).max().detach())
     out["speedup"] = round(out["op_by_op"]["ms_per_step"] / out["fused_gelu"]["ms_per_step"], 3)
     out["workload"] = (f"stem training step incl. both GELUs, batch {B}: mel (B,80,3000) -> gelu(conv1) -> gelu(conv2) -> loss, backward to all "
                        f"ten parameter gradients; nn.Module API, one CUDA graph per input set, {nsets} rotating sets")
