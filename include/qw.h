@@ -172,8 +172,12 @@ int qw_log_mel(const float* audio, const float* filters, float* mel, void* works
                int n_samples, int n_mels, void* stream);
 /* The same in two steps, for callers that keep the filterbank (mel_filters(), audio.py:91-107, is a constant asset):
  * qw_log_mel_prepare analyses `filters` once into `prep` (qw_log_mel_prep_bytes(n_mels) bytes, 256-byte aligned, caller-owned);
- * qw_log_mel_prepared then needs only B floats of workspace and skips the analysis kernel on every call. */
+ * qw_log_mel_prepared then skips the analysis kernel on every call.  Its workspace is qw_log_mel_call_workspace_bytes(B, n_samples)
+ * bytes, 256-byte aligned: B floats for the utterance maxima plus per-tile (min, max) statistics that let the second pass
+ * (audio.py:155-156) skip every tile the clamp cannot touch.  A caller that passes only the B floats (>= 4 B bytes, the first
+ * version of this interface) still gets the same result through an unconditional second pass. */
 size_t qw_log_mel_prep_bytes(int n_mels);
+size_t qw_log_mel_call_workspace_bytes(int B, int n_samples);
 int qw_log_mel_prepare(const float* filters, int n_mels, void* prep, size_t prep_bytes, void* stream);
 int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B,
                         int n_samples, int n_mels, void* stream);
@@ -181,7 +185,8 @@ int qw_log_mel_prepared(const float* audio, const void* prep, float* mel, void* 
  * clip to 480 000 samples on the CPU inside Dataset.__getitem__, train_quantum_whisper.py:52-77): audio is (B, n_in) with row
  * stride n_in; utterance b holds lengths[b] valid samples (lengths == NULL: all n_in); the result is exactly
  * log_mel_spectrogram(pad_or_trim(audio[b, :lengths[b]], n_samples)): zero padding up to n_samples, or the first n_samples samples of
- * a longer clip.  Tiles that lie entirely in the padding skip the FFT.  mel (B, n_mels, n_samples/160); workspace: B floats. */
+ * a longer clip.  Tiles that lie entirely in the padding skip the FFT.  mel (B, n_mels, n_samples/160); workspace as for
+ * qw_log_mel_prepared (sized with the OUTPUT length n_samples). */
 int qw_log_mel_padded(const float* audio, const int* lengths, const void* prep, float* mel, void* workspace, size_t ws_bytes, int B,
                       int n_in, int n_samples, int n_mels, void* stream);
 

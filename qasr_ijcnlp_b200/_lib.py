@@ -61,6 +61,7 @@ _SIGNATURES = {
     "qw_log_mel_workspace_bytes": (_SZ, [_I, _I, _I]),
     "qw_log_mel": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _P]),
     "qw_log_mel_prep_bytes": (_SZ, [_I]),
+    "qw_log_mel_call_workspace_bytes": (_SZ, [_I, _I]),
     "qw_log_mel_prepare": (_I, [_P, _I, _P, _SZ, _P]),
     "qw_log_mel_prepared": (_I, [_P, _P, _P, _P, _SZ, _I, _I, _I, _P]),
     "qw_log_mel_padded": (_I, [_P, _P, _P, _P, _P, _SZ, _I, _I, _I, _I, _P]),

@@ -152,11 +152,12 @@ def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80
     T = n // HOP_LENGTH
     prep = _prepared_filters(a.device, n_mels)
     mel = torch.empty(B, n_mels, T, device=a.device, dtype=torch.float32)
-    ws = torch.empty(B, device=a.device, dtype=torch.float32)
+    ws_bytes = lib.qw_log_mel_call_workspace_bytes(B, n)
+    ws = torch.empty(ws_bytes, device=a.device, dtype=torch.uint8)
     P = ctypes.c_void_p
     with torch.cuda.device(a.device):
         st = lib.qw_log_mel_padded(P(a.data_ptr()), P(lengths.data_ptr()) if lengths is not None else None, P(prep.data_ptr()),
-                                   P(mel.data_ptr()), P(ws.data_ptr()), 4 * B, B, n_in, n, n_mels,
+                                   P(mel.data_ptr()), P(ws.data_ptr()), ws_bytes, B, n_in, n, n_mels,
                                    P(torch.cuda.current_stream().cuda_stream))
     _lib.check(st, "qw_log_mel_padded")
     return mel[0] if single else mel

@@ -1,20 +1,19 @@
 // Per-frame arithmetic of the fused log-mel kernel: Hann window -> 400-point real FFT -> power, written so the
-// same code runs per lane on the device (one STFT frame per lane, the frame's 400 work floats in a
-// shared-memory column) and on the host inside tests/native/logmel_host_check.cu.
+// same code runs on the device and on the host inside tests/native/logmel_host_check.cpp.
 //
 // Replaces torch.stft(n_fft=400, hop=160, window=hann(400)) + abs()**2 of
 // /root/reference/whisper/whisper/audio.py:147-149.
 //
-// 400-point real FFT = 200-point complex FFT of z[n] = x[2n] + i x[2n+1], then untangling.
-// 200 = 8 x 25 Cooley-Tukey:  n = 25 n1 + n2,  k = k1 + 8 k2:
-//    pass A (per n2):  Y[k1] = sum_n1 z[25 n1 + n2] W8^(n1 k1);  A[k1][n2] = Y[k1] W200^(n2 k1)
-//    pass B (per k1):  Z[k1 + 8 k2] = sum_n2 A[k1][n2] W25^(n2 k2)          (25 = 5 x 5 in registers)
-// Work-column layout (floats): complex slot s holds re at 2s, im at 2s+1.  Pass A stores A[k1][n2] at slot
-// n2*8 + k1; pass B reads slots {n2*8 + k1} and writes Z[k1 + 8 k2] to slot k2*8 + k1 -- the same set, so it is in
-// place per k1 and leaves the spectrum in NATURAL order (slot k = Z[k]).  The untangle pass overwrites re-slots with
-// the power spectrum: P[k] at float 2k for k < 200, P[200] at float 1 (the im part of Z[0]'s slot).
-// The G warps of a CTA split every pass by index (n2, k1, k, mel row = g, g+G, ...); a __syncthreads()
-// separates the passes.  Every table index is uniform across a warp -> constant-cache broadcasts.
+// 400 = 16 x 25 Cooley-Tukey on the REAL frame, n = 25 n1 + n2, k = k1 + 16 k2:
+//    pass A (per n2):  Y[k1] = sum_n1 w[n] x[n] W16^(n1 k1)  -- a 16-point real-input FFT, so only k1 = 0..8 exist
+//                      (Y[16 - k1] = conj Y[k1]; Y[0], Y[8] real);  A[k1][n2] = Y[k1] W400^(n2 k1)
+//    pass B (per k1):  X[k1 + 16 k2] = sum_n2 A[k1][n2] W25^(n2 k2)        (25 = 5 x 5 in registers)
+// k1 = 0..8 and k2 = 0..24 give the bins k = k1 + 16 k2; for k2 <= 12 that is k <= 200 directly, for k2 >= 13 the bin
+// is > 200 and its power is that of the mirror bin 400 - k (X[400 - k] = conj X[k]), which fills the residues
+// 9..15 (mod 16): all 201 bins, no separate real-FFT untangling pass, and only |X|^2 is ever written.
+// (The first version packed the frame into a 200-point complex FFT, 8 x 25, plus an untangling pass: 2 000 more
+// instructions per frame and a second trip through the work array.)
+// Work layout: 17 float planes of 25 (n2) values: plane 0 = Re A[0] (real), planes 2 k1 - 1 / 2 k1 = Re / Im A[k1].
 #pragma once
 #include "qw_logmel_tables.h"
 
@@ -30,26 +29,20 @@ namespace lm {
 constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kNfreq = 201;
-// audio staging skew: sample s of the tile sits at float s + (s >> 5).  Frames are 160 samples apart, so lane f reads
-// 165 f + j + (j >> 5): 165 is odd -> the 32 lanes hit 32 distinct banks for every tap j.
-constexpr int kLanePitch = 165;
-
 #if defined(__CUDACC__)
-__constant__ float c_win[400] = QW_TBL_WIN;
-__constant__ float c_tw200_re[200] = QW_TBL_TW200_RE;
-__constant__ float c_tw200_im[200] = QW_TBL_TW200_IM;
+// Hann weights and W400 twiddles are read once per CTA with one n2 per LANE (divergent index): global memory, not the
+// constant bank.  The 5 x 5 twiddles are indexed uniformly: constant bank.
+__device__ const float d_win[400] = QW_TBL_WIN;
+__device__ const float d_tw400_re[200] = QW_TBL_TW400_RE;  // [k1 - 1][n2]
+__device__ const float d_tw400_im[200] = QW_TBL_TW400_IM;
 __constant__ float c_tw25_re[25] = QW_TBL_TW25_RE;
 __constant__ float c_tw25_im[25] = QW_TBL_TW25_IM;
-__constant__ float c_un_re[101] = QW_TBL_UN_RE;
-__constant__ float c_un_im[101] = QW_TBL_UN_IM;
 #endif
 static const float h_win[400] = QW_TBL_WIN;
-static const float h_tw200_re[200] = QW_TBL_TW200_RE;
-static const float h_tw200_im[200] = QW_TBL_TW200_IM;
+static const float h_tw400_re[200] = QW_TBL_TW400_RE;
+static const float h_tw400_im[200] = QW_TBL_TW400_IM;
 static const float h_tw25_re[25] = QW_TBL_TW25_RE;
 static const float h_tw25_im[25] = QW_TBL_TW25_IM;
-static const float h_un_re[101] = QW_TBL_UN_RE;
-static const float h_un_im[101] = QW_TBL_UN_IM;
 
 #if defined(__CUDA_ARCH__)
 #define QW_TBL(name, i) (c_##name[i])
@@ -57,46 +50,54 @@ static const float h_un_im[101] = QW_TBL_UN_IM;
 #define QW_TBL(name, i) (h_##name[i])
 #endif
 
-QW_HD int pslot(int k) { return k < 200 ? 2 * k : 1; }  // float slot of P[k], k <= 200
-QW_HD int skew(int s) { return s + (s >> 5); }           // staging index of tile sample s
-// staging index of tap j of the tile's frame f (frame f starts at tile sample 160 f)
-QW_HD int tap_index(int f, int j) { return kLanePitch * f + j + (j >> 5); }
-
-// ---- forward 8-point DFT (e^{-2 pi i nk/8}), natural order in and out
-QW_HD void dft8(float (&r)[8], float (&i)[8]) {
+// ---- 8-point DFT of the REAL sequence x_j w_j: Y[0..4] (Y[8 - k] = conj Y[k]); yi[0] = yi[4] = 0 are not written.
+// The Hann weights ride in the first butterflies: (x_j w_j) +- (x_{j+4} w_{j+4}) is one FMUL and two FFMAs.
+QW_HD void rdft8w(float x0, float x1, float x2, float x3, float x4, float x5, float x6, float x7, float w0, float w1, float w2,
+                  float w3, float w4, float w5, float w6, float w7, float (&yr)[5], float (&yi)[5]) {
   const float h = 0.70710678118654752440f;
-  float ar[4], ai[4], br[4], bi[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    ar[j] = r[j] + r[j + 4];
-    ai[j] = i[j] + i[j + 4];
-    br[j] = r[j] - r[j + 4];
-    bi[j] = i[j] - i[j + 4];
-  }
-  // b_j *= W8^j : W8^1 = (1 - i) h, W8^2 = -i, W8^3 = (-1 - i) h
+  const float t0 = x4 * w4, t1 = x5 * w5, t2 = x6 * w6, t3 = x7 * w7;
+  const float a0 = x0 * w0 + t0, a1 = x1 * w1 + t1, a2 = x2 * w2 + t2, a3 = x3 * w3 + t3;
+  const float b0 = x0 * w0 - t0, b1 = x1 * w1 - t1, b2 = x2 * w2 - t2, b3 = x3 * w3 - t3;
+  const float c0 = a0 + a2, c1 = a1 + a3;
+  yr[0] = c0 + c1;
+  yr[4] = c0 - c1;
+  yr[2] = a0 - a2;
+  yi[2] = a3 - a1;                 // Y[2] = (a0 - a2) - i (a1 - a3)
+  const float s = b1 - b3, t = b1 + b3;
+  yr[1] = b0 + h * s;              // Y[1] = b0 + W8 b1 + W8^2 b2 + W8^3 b3
+  yi[1] = -(b2 + h * t);
+  yr[3] = b0 - h * s;              // Y[3] = b0 + W8^3 b1 + W8^6 b2 + W8^9 b3
+  yi[3] = b2 - h * t;
+}
+
+// ---- 16-point DFT of the REAL sequence x_j w_j: X[0..8]; xi[0] = xi[8] = 0 are not written.
+// X[k] = E[k] + W16^k O[k] with E / O the real 8-point DFTs of the even / odd samples; X[8 - k] = conj(E[k] - W16^k O[k]).
+QW_HD void rfft16w(const float (&x)[16], const float (&w)[16], float (&xr)[9], float (&xi)[9]) {
+  float er[5], ei[5], orr[5], oi[5];
+  rdft8w(x[0], x[2], x[4], x[6], x[8], x[10], x[12], x[14], w[0], w[2], w[4], w[6], w[8], w[10], w[12], w[14], er, ei);
+  rdft8w(x[1], x[3], x[5], x[7], x[9], x[11], x[13], x[15], w[1], w[3], w[5], w[7], w[9], w[11], w[13], w[15], orr, oi);
+  xr[0] = er[0] + orr[0];
+  xr[8] = er[0] - orr[0];
+  xr[4] = er[4];                   // W16^4 = -i, E[4] and O[4] real
+  xi[4] = -orr[4];
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;  // cos, sin (pi / 8)
+  const float h = 0.70710678118654752440f;
+  // W16^k = (c, -s):  T = W16^k O[k] = (c Or + s Oi, c Oi - s Or)
   {
-    const float t1r = (br[1] + bi[1]) * h, t1i = (bi[1] - br[1]) * h;
-    br[1] = t1r; bi[1] = t1i;
-    const float t2r = bi[2], t2i = -br[2];
-    br[2] = t2r; bi[2] = t2i;
-    const float t3r = (bi[3] - br[3]) * h, t3i = -(br[3] + bi[3]) * h;
-    br[3] = t3r; bi[3] = t3i;
+    const float tr = c1 * orr[1] + s1 * oi[1], ti = c1 * oi[1] - s1 * orr[1];
+    xr[1] = er[1] + tr; xi[1] = ei[1] + ti;
+    xr[7] = er[1] - tr; xi[7] = ti - ei[1];
   }
-  // 4-point DFTs: a -> even outputs, b -> odd outputs
-#define QW_DFT4(xr, xi, o0, o1, o2, o3)                                            \
-  {                                                                                \
-    const float c0r = xr[0] + xr[2], c0i = xi[0] + xi[2];                          \
-    const float c1r = xr[1] + xr[3], c1i = xi[1] + xi[3];                          \
-    const float d0r = xr[0] - xr[2], d0i = xi[0] - xi[2];                          \
-    const float d1r = xi[1] - xi[3], d1i = -(xr[1] - xr[3]); /* (x1 - x3) * (-i) */ \
-    r[o0] = c0r + c1r; i[o0] = c0i + c1i;                                          \
-    r[o2] = c0r - c1r; i[o2] = c0i - c1i;                                          \
-    r[o1] = d0r + d1r; i[o1] = d0i + d1i;                                          \
-    r[o3] = d0r - d1r; i[o3] = d0i - d1i;                                          \
+  {
+    const float tr = h * (orr[2] + oi[2]), ti = h * (oi[2] - orr[2]);
+    xr[2] = er[2] + tr; xi[2] = ei[2] + ti;
+    xr[6] = er[2] - tr; xi[6] = ti - ei[2];
   }
-  QW_DFT4(ar, ai, 0, 2, 4, 6)
-  QW_DFT4(br, bi, 1, 3, 5, 7)
-#undef QW_DFT4
+  {
+    const float tr = s1 * orr[3] + c1 * oi[3], ti = s1 * oi[3] - c1 * orr[3];
+    xr[3] = er[3] + tr; xi[3] = ei[3] + ti;
+    xr[5] = er[3] - tr; xi[5] = ti - ei[3];
+  }
 }
 
 // ---- forward 5-point DFT in place on (r[o], r[o+s], ..., r[o+4s])
@@ -159,75 +160,51 @@ QW_HD void dft25(float (&r)[25], float (&i)[25]) {
   Dft5Rows<0>::run(r, i);  // element 5c + d holds X[c + 5d]
 }
 
-// Col: float& at(int e) -- the frame's work column.  Aud: float tap(int j) -- windowless sample j of the frame.
-template <typename Col, typename Aud>
-QW_HD void pass_a(int g, int G, const Aud& aud, Col& col) {
-  for (int n2 = g; n2 < 25; n2 += G) {
-    float xr[8], xi[8];
+constexpr int kPlanes = 17;  // work planes per frame: Re A[0], then Re / Im of A[1..8]
+
+// Pass A for one (frame, n2): 16 taps x Hann -> real FFT16 -> twiddle -> 17 plane values.
+//   x[n1]       the frame's sample 25 n1 + n2;  w[n1] its Hann weight (on the device the weights and twiddles of a lane's
+//               n2 sit in registers for the whole kernel)
+//   twr / twi   W400^(n2 k1) for k1 = 1..8
+//   put(pl, v)  stores plane pl of this (frame, n2)
+template <typename Put>
+QW_HD void pass_a_one(const float (&x)[16], const float (&w)[16], const float (&twr)[8], const float (&twi)[8], Put&& put) {
+  float xr[9], xi[9];
+  rfft16w(x, w, xr, xi);
+  put(0, xr[0]);
 #pragma unroll
-    for (int n1 = 0; n1 < 8; ++n1) {
-      const int j = 2 * (25 * n1 + n2);
-      xr[n1] = aud.tap(j) * QW_TBL(win, j);
-      xi[n1] = aud.tap(j + 1) * QW_TBL(win, j + 1);
-    }
-    dft8(xr, xi);
-#pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) {
-      float yr = xr[k1], yi = xi[k1];
-      if (k1 > 0) {
-        const float wr = QW_TBL(tw200_re, n2 * 8 + k1), wi = QW_TBL(tw200_im, n2 * 8 + k1);
-        const float tr = yr * wr - yi * wi;
-        yi = yr * wi + yi * wr;
-        yr = tr;
-      }
-      col.at(2 * (n2 * 8 + k1)) = yr;
-      col.at(2 * (n2 * 8 + k1) + 1) = yi;
-    }
+  for (int k1 = 1; k1 < 8; ++k1) {
+    const float wr = twr[k1 - 1], wi = twi[k1 - 1];
+    put(2 * k1 - 1, xr[k1] * wr - xi[k1] * wi);
+    put(2 * k1, xr[k1] * wi + xi[k1] * wr);
   }
+  put(15, xr[8] * twr[7]);
+  put(16, xr[8] * twi[7]);
 }
 
-template <typename Col>
-QW_HD void pass_b(int g, int G, Col& col) {
-  for (int k1 = g; k1 < 8; k1 += G) {
-    float r[25], i[25];
+// Pass B for one (frame, k1): 25-point DFT over n2 of plane pair k1 -> power of the bins k1 + 16 k2.
+//   getr(n2) / geti(n2)   Re / Im A[k1][n2] (geti is not called for k1 == 0: A[0] is real)
+//   putp(k, v)            stores P[k], k <= 200
+// k1 == 0 and k1 == 8 produce each of their bins twice (k2 and 25 - k2 resp. 24 - k2 mirror onto each other): the
+// mirrored copies are skipped.
+template <typename GetR, typename GetI, typename PutP>
+QW_HD void pass_b_one(int k1, GetR&& getr, GetI&& geti, PutP&& putp) {
+  float r[25], i[25];
 #pragma unroll
-    for (int n2 = 0; n2 < 25; ++n2) {
-      r[n2] = col.at(2 * (n2 * 8 + k1));
-      i[n2] = col.at(2 * (n2 * 8 + k1) + 1);
-    }
-    dft25(r, i);
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-#pragma unroll
-      for (int d = 0; d < 5; ++d) {
-        const int k2 = c + 5 * d;
-        col.at(2 * (k2 * 8 + k1)) = r[5 * c + d];
-        col.at(2 * (k2 * 8 + k1) + 1) = i[5 * c + d];
-      }
-    }
+  for (int n2 = 0; n2 < 25; ++n2) {
+    r[n2] = getr(n2);
+    i[n2] = k1 == 0 ? 0.f : geti(n2);
   }
-}
-
-// Z (200-point complex spectrum of the packed frame) -> power spectrum of the 400-point real FFT, in place.
-template <typename Col>
-QW_HD void untangle_power(int g, int G, Col& col) {
-  for (int k = g; k <= 100; k += G) {
-    if (k == 0) {
-      const float zr = col.at(0), zi = col.at(1);
-      const float a = zr + zi, b = zr - zi;  // X[0] = Zr + Zi, X[200] = Zr - Zi (both real)
-      col.at(0) = a * a;
-      col.at(1) = b * b;
-    } else {
-      const int s0 = 2 * k, s1 = 2 * (200 - k);
-      const float ar = col.at(s0), ai = col.at(s0 + 1), br = col.at(s1), bi = col.at(s1 + 1);
-      const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);   // (Z[k] + conj Z[200-k]) / 2
-      const float orr = 0.5f * (ai + bi), oi = -0.5f * (ar - br);  // (Z[k] - conj Z[200-k]) / (2i)
-      const float wr = QW_TBL(un_re, k), wi = QW_TBL(un_im, k);
-      const float tr = orr * wr - oi * wi, ti = orr * wi + oi * wr;
-      const float pr = er + tr, pi = ei + ti;  // X[k]
-      const float qr = er - tr, qi = ei - ti;  // conj X[200-k]
-      col.at(s0) = pr * pr + pi * pi;
-      if (k != 100) col.at(s1) = qr * qr + qi * qi;
+  dft25(r, i);
+  const bool mirror = k1 != 0 && k1 != 8;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const int k2 = c + 5 * d;
+      const float p = r[5 * c + d] * r[5 * c + d] + i[5 * c + d] * i[5 * c + d];
+      if (k2 <= 12) putp(k1 + 16 * k2, p);
+      else if (mirror) putp(400 - 16 * k2 - k1, p);
     }
   }
 }

@@ -176,3 +176,36 @@ def test_ragged_batch_with_lengths_and_collate(cuda):
     _close(got[1].cpu().numpy(), lo.log_mel_spectrogram(lo.pad_or_trim(clips[1])))
     with pytest.raises(ValueError):
         qa.log_mel_spectrogram(batch, pad_to=qa.N_SAMPLES, lengths=lens[:2])
+
+
+def test_selective_second_pass_equals_unconditional(cuda):
+    """audio.py:155-156 in two forms.  With the full per-call workspace the stft kernel stores (v + 4) / 4 and the second pass only
+    touches tiles whose minimum lies below max - 8; with the B-float workspace of the first interface it stores v and an
+    unconditional pass applies the formula.  Same bits -- on noise (no tile touched), on a clip whose quiet tail / zero padding
+    sits below the floor (write-only and read-modify-write tiles), and against the oracle."""
+    import ctypes
+    from qasr_ijcnlp_b200 import _lib
+    from qasr_ijcnlp_b200 import audio as qa
+    lib = _lib.load()
+    rs = np.random.RandomState(11)
+    n = 160 * 320
+    a = (0.1 * rs.standard_normal((4, n))).astype(np.float32)
+    a[1, n // 3:] *= 1e-6                      # 120 dB down: below max - 8 -> clamped
+    a[2, n // 2:] = 0.0                        # digital silence: tiles entirely on the floor
+    a[3] *= np.linspace(1.0, 1e-5, n, dtype=np.float32)   # a slow fade: tiles that straddle the floor
+    dev = torch.from_numpy(a).to(cuda)
+    prep = qa._prepared_filters(cuda, 80)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    outs = []
+    for nbytes in (4 * 4, lib.qw_log_mel_call_workspace_bytes(4, n)):
+        mel = torch.empty(4, 80, n // 160, device=cuda)
+        ws = torch.empty(max(nbytes, 256), device=cuda, dtype=torch.uint8)
+        st = lib.qw_log_mel_prepared(p(dev), p(prep), p(mel), p(ws), nbytes, 4, n, 80,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(st, "qw_log_mel_prepared")
+        outs.append(mel)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[1], qa.log_mel_spectrogram(dev))
+    ref = lo.log_mel_spectrogram(a)
+    _close(outs[1].cpu().numpy(), ref)
+    assert (ref[1:] == ref[1:].min(axis=(1, 2), keepdims=True)).mean() > 0.2   # the clamp really is active in these clips
