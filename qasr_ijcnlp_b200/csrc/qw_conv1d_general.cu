@@ -130,9 +130,22 @@ __global__ void __launch_bounds__(kT) gen_postconv_bwd_kernel(const GArgs<T> a) 
 #pragma unroll
     for (int j = 0; j < QP; ++j) gacc[j] = T(0);
     const T* __restrict__ gyb = a.gy + (size_t)b * d.O * d.Lout + i;
+    // the next chunk's 32 values per thread are fetched into registers while the current chunk is contracted: with the loads issued
+    // right before their first use every chunk paid a full memory round trip between two barriers (116 us per launch)
+    T nx[kOC / 4];
+#pragma unroll
+    for (int u = 0; u < kOC / 4; ++u) nx[u] = (valid && warp + 4 * u < d.O) ? __ldg(gyb + (size_t)(warp + 4 * u) * d.Lout) : T(0);
     for (int oc = 0; oc < d.O; oc += kOC) {
-      for (int r = warp; r < kOC; r += 4) gys[r * 33 + lane] = (valid && oc + r < d.O) ? __ldg(gyb + (size_t)(oc + r) * d.Lout) : T(0);
+#pragma unroll
+      for (int u = 0; u < kOC / 4; ++u) gys[(warp + 4 * u) * 33 + lane] = nx[u];
       __syncthreads();
+      if (oc + kOC < d.O) {
+#pragma unroll
+        for (int u = 0; u < kOC / 4; ++u) {
+          const int r = oc + kOC + warp + 4 * u;
+          nx[u] = (valid && r < d.O) ? __ldg(gyb + (size_t)r * d.Lout) : T(0);
+        }
+      }
       for (int r = warp; r < kOC && oc + r < d.O; r += 4) {
         const T g = gys[r * 33 + lane];
 #pragma unroll
@@ -268,21 +281,172 @@ __global__ void __launch_bounds__(kT) gen_preconv_bwd_gw_kernel(const GArgs<T> a
   }
 }
 
-// out0[e] (e < n0) / out1[e - n0] = sum_g part[g][e], fixed order, fp64 accumulation
+// ---------------------------------------------------------------- backward: pre_conv^T in ONE pass over x (kernel_size 3)
+// grad_x and the partials of grad pre_conv.{weight,bias} from a single read of x -- the general path's counterpart of
+// fast_bwd_pre_kernel.  The two kernels above cost 229 us per launch at the stem's conv2 shape (every (b, c, l) thread of the gx
+// kernel fetched K * q gpre values, every CTA of the gw kernel walked all 24 000 windows at 2.6 CTAs per SM).  Here:
+//   * lanes = 32 consecutive CHANNELS: a lane keeps its channel's pre_conv weights w[q][3] and gradient accumulators gw[q][3] in
+//     registers for the CTA lifetime -> one partial row per CTA column, no atomics;
+//   * each of the 4 warps owns 32 consecutive positions of the CTA's 128-position tile: the 32 x 32 block of x is read with
+//     coalesced 128-byte rows, turned through a pitch-33 shared-memory block (warp-private: __syncwarp only), grad_x is written
+//     back over it in place and leaves by coalesced rows again;
+//   * the <= 3 windows that touch a position have a warp-uniform index: the <= 36 gpre rows a warp's 32 positions can touch are
+//     staged once per tile in a warp-private shared-memory block (coalesced read, rows of windows outside [0, L_out) zeroed, so the
+//     inner loop carries no bounds checks) and read back as broadcast vector loads -- uniform GLOBAL loads, 18 per position at
+//     q = 6, made the first version of this kernel load/store-unit bound (94 us per launch);
+//   * per lane and position 2 q K FMAs against ~12 other instructions.
+// grid: (position CTAs, channel chunks); partial row bx: [q * C * 3 grad weight, j-major][q grad bias] (as gen_reduce_rows expects).
+// SS: compile-time stride (1, 2) or 0 = any (run-time division per tap).
+template <typename T, int QP, int SS>
+__global__ void __launch_bounds__(kT) gen_preconv_bwd_k3_kernel(const GArgs<T> a) {
+  constexpr int RW = QP * 3 + 1, GR = 36;
+  constexpr int kStream = 4 * 32 * 33 + 4 * GR * QP, kRed = 4 * 32 * RW;
+  // while streaming: the warps' x blocks [4][32][33] and gpre rows [4][GR][QP]; afterwards the reduction buffer [4][32][RW]
+  __shared__ __align__(16) T sbuf[kStream > kRed ? kStream : kRed];
+  T(*xt)[32][33] = reinterpret_cast<T(*)[32][33]>(sbuf);
+  T(*gsa)[GR][QP] = reinterpret_cast<T(*)[GR][QP]>(sbuf + 4 * 32 * 33);
+  T(*red)[32][RW] = reinterpret_cast<T(*)[32][RW]>(sbuf);
+  const ConvDims d = a.d;
+  const int q = a.q, CK = d.C * 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.y * 32, c = c0 + lane;
+  T w[QP][3], gw[QP][3];
+#pragma unroll
+  for (int j = 0; j < QP; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      w[j][k] = (j < q && c < d.C) ? a.w_pre[(size_t)j * CK + c * 3 + k] : T(0);
+      gw[j][k] = T(0);
+    }
+  T gb[QP];  // grad pre_conv.bias: lane j of warp 0 in chunk 0 sums gpre[:, j] over the windows this tile owns
+#pragma unroll
+  for (int j = 0; j < QP; ++j) gb[j] = T(0);
+  const int lt = (d.L + 127) / 128;  // position tiles per utterance
+  const int total = d.B * lt;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int b = t / lt, l0 = (t - b * lt) * 128, lw = l0 + warp * 32;
+    const T* __restrict__ xb = a.x + ((size_t)b * d.C + c0) * d.L;
+    T(*blk)[33] = xt[warp];
+    T(*gs)[QP] = gsa[warp];
+    if (lw < d.L) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) blk[r][lane] = (c0 + r < d.C && lw + lane < d.L) ? __ldg(xb + (size_t)r * d.L + lw + lane) : T(0);
+      // gpre rows of the windows i_lo .. i_lo + GR - 1 (floor division: the first tile reaches windows < 0, which are zero rows)
+      const int nlo = lw + d.P - 2;
+      const int i_lo = SS == 1 ? nlo : SS == 2 ? (nlo >> 1) : (nlo >= 0 ? nlo / d.S : -((-nlo + d.S - 1) / d.S));
+      {
+        const T* __restrict__ gpb = a.gpre_c + (size_t)b * d.Lout * q;
+        for (int e = lane; e < GR * QP; e += 32) {
+          const int row = e / QP, j = e - row * QP, i = i_lo + row;
+          gs[row][j] = (j < q && i >= 0 && i < d.Lout) ? __ldg(gpb + (size_t)i * q + j) : T(0);
+        }
+      }
+      __syncwarp();
+#pragma unroll 2
+      for (int p = 0; p < 32; ++p) {
+        const T xv = blk[lane][p];
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int num = lw + p + d.P - k;  // window i touches column l with tap k iff i * S - P + k == l
+          const int i = SS == 1 ? num : SS == 2 ? (num >> 1) : (num >= 0 ? num / d.S : -((-num + d.S - 1) / d.S));
+          const bool hit = SS == 1 ? true : SS == 2 ? (num & 1) == 0 : i * d.S == num;
+          if (hit) {  // warp-uniform; i - i_lo lies in [0, GR)
+            const T* gp = gs[i - i_lo];
+#pragma unroll
+            for (int j = 0; j < QP; ++j) {
+              const T g = gp[j];
+              gw[j][k] = fma(g, xv, gw[j][k]);
+              acc = fma(g, w[j][k], acc);
+            }
+          }
+        }
+        blk[lane][p] = acc;
+      }
+      __syncwarp();
+      if (a.gx) {
+        T* __restrict__ gxb = a.gx + ((size_t)b * d.C + c0) * d.L;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+          if (c0 + r < d.C && lw + lane < d.L) gxb[(size_t)r * d.L + lw + lane] = blk[r][lane];
+      }
+      __syncwarp();
+    }
+    if (blockIdx.y == 0) {
+      // windows owned by this tile: tap-0 column i * S - P in [l0, l0 + 128) (the first tile also takes the negative columns)
+      const int lo = l0 == 0 ? 0 : (l0 + d.P + d.S - 1) / d.S;
+      int hi = (l0 + 128 + d.P + d.S - 1) / d.S;
+      hi = hi < d.Lout ? hi : d.Lout;
+      if (l0 + 128 >= d.L) hi = d.Lout;
+      for (int i = lo + tid; i < hi; i += kT) {
+        const T* gp = a.gpre_c + ((size_t)b * d.Lout + i) * q;
+#pragma unroll
+        for (int j = 0; j < QP; ++j)
+          if (j < q) gb[j] += gp[j];
+      }
+    }
+  }
+  // ---- cross-warp reduction (fixed order) -> this CTA's columns of partial row blockIdx.x
+  __syncthreads();  // every warp is done with its x block: the buffer becomes `red`
+#pragma unroll
+  for (int j = 0; j < QP; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) red[warp][lane][j * 3 + k] = gw[j][k];
+  __syncthreads();
+  T* prow = a.part + (size_t)blockIdx.x * a.PA;
+  for (int e = tid; e < 32 * q * 3; e += kT) {
+    const int ln = e / (q * 3), jk = e - ln * (q * 3);
+    const int j = jk / 3, k = jk - j * 3;
+    if (c0 + ln < d.C) prow[(size_t)j * CK + (c0 + ln) * 3 + k] = red[0][ln][jk] + red[1][ln][jk] + red[2][ln][jk] + red[3][ln][jk];
+  }
+  if (blockIdx.y == 0) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < QP; ++j) {
+      const T v = warp_sum<T>(gb[j]);
+      if (lane == 0) red[warp][0][j] = v;
+    }
+    __syncthreads();
+    if (tid < q) prow[(size_t)q * CK + tid] = red[0][0][tid] + red[1][0][tid] + red[2][0][tid] + red[3][0][tid];
+  }
+}
+
+// out0[e] (e < n0) / out1[e - n0] = sum_g part[g][e], fixed order, fp64 accumulation.
+// A CTA owns 32 columns; its 8 warps take the rows g = warp, warp + 8, ... (128-byte coalesced reads, chains 8 x shorter than one
+// thread per column walking all G rows: 592 rows took 33 us per launch that way) and meet in shared memory in warp order.
 template <typename T>
 __global__ void __launch_bounds__(256) gen_reduce_rows_kernel(const T* __restrict__ part, int G, int P, T* __restrict__ out0, int n0,
                                                               T* __restrict__ out1, int n1) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= n0 + n1) return;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int g = 0; g < G; ++g) s += (double)part[(size_t)g * P + e];
-  if (e < n0) out0[e] = (T)s;
-  else out1[e - n0] = (T)s;
+  if (e < n0 + n1) {
+    // 8 independent loads in flight per thread (the partial rows come from HBM / L2: a chain of dependent loads is pure latency)
+    int g = warp;
+    for (; g + 56 < G; g += 64) {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(size_t)(g + 8 * u) * P + e];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; g < G; g += 8) s += (double)part[(size_t)g * P + e];
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && e < n0 + n1) {
+    double t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    if (e < n0) out0[e] = (T)t;
+    else out1[e - n0] = (T)t;
+  }
 }
 
 // =============================================================================================== host
 struct GenPlan {
-  int tiles_per_utt, num_tiles, gridT, gridA, PA, NS, PB, gridX;
+  int tiles_per_utt, num_tiles, gridT, gridA, PA, NS, PB, gridX, gridP;
   size_t off_gout, off_gpre, off_pa, off_pb, off_circ, total;
 };
 
@@ -292,12 +456,20 @@ static GenPlan make_plan(const ConvDims& d, int elem) {
   p.tiles_per_utt = (d.Lout + kTW - 1) / kTW;
   p.num_tiles = d.B * p.tiles_per_utt;
   p.gridT = p.num_tiles < sms * 8 ? p.num_tiles : sms * 8;
-  p.gridA = p.num_tiles < sms * 2 ? p.num_tiles : sms * 2;
+  p.gridA = p.num_tiles < sms * 4 ? p.num_tiles : sms * 4;  // 2 CTAs per SM left the gy pass latency-bound (116 us per launch)
   p.PA = (int)align_up((size_t)d.O * (d.Q + 1), 32);
-  p.NS = 4 * sms / d.C;
+  p.NS = 16 * sms / d.C;  // C * NS CTAs of 128 threads: ~16 per SM (4 * sms / C left conv2, C = 384, with ONE slice: 2.6 CTAs per SM)
   p.NS = p.NS < 1 ? 1 : p.NS > 64 ? 64 : p.NS;
   const long long W = (long long)d.B * d.Lout;
   if (p.NS > W) p.NS = (int)W;
+  {
+    // fused pre_conv^T kernel (kernel_size 3): gridP position CTAs per 32-channel chunk, ~8 CTAs per SM in total
+    const int chunks = (d.C + 31) / 32, tiles = d.B * ((d.L + 127) / 128);
+    int gp = 8 * sms / chunks;
+    gp = gp < 1 ? 1 : gp;
+    p.gridP = gp < tiles ? gp : tiles;
+    if (d.K == 3 && p.gridP > p.NS) p.NS = p.gridP;  // partial rows of either form fit
+  }
   p.PB = (int)align_up((size_t)d.Q * d.C * d.K + d.Q, 32);
   {
     const long long t = (long long)d.B * d.C * ((d.L + kT - 1) / kT);
@@ -358,7 +530,7 @@ int general_forward(const T* x, const T* w_pre, const T* b_pre, const T* qwts, c
   a.qout = pre_save + W * d.Q;
   a.y = y; a.pre_w = pre_save;
   a.d = d; a.tiles_per_utt = p.tiles_per_utt; a.num_tiles = p.num_tiles; a.q = d.Q;
-  return d.Q <= 4 ? forward_qp<T, 4>(a, p, qwts, st) : d.Q <= 8 ? forward_qp<T, 8>(a, p, qwts, st) : forward_qp<T, 12>(a, p, qwts, st);
+  return d.Q <= 4 ? forward_qp<T, 4>(a, p, qwts, st) : d.Q <= 6 ? forward_qp<T, 6>(a, p, qwts, st) : d.Q <= 8 ? forward_qp<T, 8>(a, p, qwts, st) : forward_qp<T, 12>(a, p, qwts, st);
 }
 
 template <typename T, int QP>
@@ -380,7 +552,15 @@ static int backward_qp(GArgs<T> a, const GenPlan& p, const T* qwts, T* gqw, T* g
   if (int e = wc::wcirc_backward<T>(a.pre, qwts, a.gout_c, const_cast<T*>(a.gpre_c), gqw, ws + p.off_circ, (long long)W, d.Q, d.Lq,
                                     d.emb, st))
     return e;
-  if (a.gx) {
+  if (d.K == 3) {
+    a.part = partB; a.PA = p.PB;
+    KernelTimer kt(kKBwdPre, st);
+    const dim3 grid(p.gridP, (d.C + 31) / 32);
+    if (d.S == 1) gen_preconv_bwd_k3_kernel<T, QP, 1><<<grid, kT, 0, st>>>(a);
+    else if (d.S == 2) gen_preconv_bwd_k3_kernel<T, QP, 2><<<grid, kT, 0, st>>>(a);
+    else gen_preconv_bwd_k3_kernel<T, QP, 0><<<grid, kT, 0, st>>>(a);
+    QW_CUDA_OK(cudaGetLastError());
+  } else if (a.gx) {
     const size_t smem = (size_t)d.C * d.K * QP * sizeof(T);
     auto k = gen_preconv_bwd_gx_kernel<T, QP>;
     if (int e = set_smem(k, smem)) return e;
@@ -388,7 +568,7 @@ static int backward_qp(GArgs<T> a, const GenPlan& p, const T* qwts, T* gqw, T* g
     k<<<p.gridX, kT, smem, st>>>(a);
     QW_CUDA_OK(cudaGetLastError());
   }
-  {
+  if (d.K != 3) {
     a.part = partB; a.PA = p.PB; a.NS = p.NS;
     KernelTimer kt(kKBwdPre, st);
     gen_preconv_bwd_gw_kernel<T, QP><<<dim3(d.C, p.NS), kT, 0, st>>>(a);
@@ -397,13 +577,13 @@ static int backward_qp(GArgs<T> a, const GenPlan& p, const T* qwts, T* gqw, T* g
   {
     KernelTimer kt(kKBwdFinalize, st);
     const int nA = d.O * d.Q + d.O;
-    gen_reduce_rows_kernel<T><<<(nA + 255) / 256, 256, 0, st>>>(partA, p.gridA, p.PA, gw_post, d.O * d.Q, gb_post, d.O);
+    gen_reduce_rows_kernel<T><<<(nA + 31) / 32, 256, 0, st>>>(partA, p.gridA, p.PA, gw_post, d.O * d.Q, gb_post, d.O);
   }
   QW_CUDA_OK(cudaGetLastError());
   {
     KernelTimer kt(kKBwdFinalize, st);
     const int nB = d.Q * d.C * d.K + d.Q;
-    gen_reduce_rows_kernel<T><<<(nB + 255) / 256, 256, 0, st>>>(partB, p.NS, p.PB, gw_pre, d.Q * d.C * d.K, gb_pre, d.Q);
+    gen_reduce_rows_kernel<T><<<(nB + 31) / 32, 256, 0, st>>>(partB, d.K == 3 ? p.gridP : p.NS, p.PB, gw_pre, d.Q * d.C * d.K, gb_pre, d.Q);
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;
@@ -424,6 +604,7 @@ int general_backward(const T* gy, const T* x, const T* pre_save, const T* w_pre,
   a.gx = gx;
   a.d = d; a.tiles_per_utt = p.tiles_per_utt; a.num_tiles = p.num_tiles; a.q = d.Q;
   return d.Q <= 4 ? backward_qp<T, 4>(a, p, qwts, gqw, gw_pre, gb_pre, gw_post, gb_post, ws, st)
+       : d.Q <= 6 ? backward_qp<T, 6>(a, p, qwts, gqw, gw_pre, gb_pre, gw_post, gb_post, ws, st)
        : d.Q <= 8 ? backward_qp<T, 8>(a, p, qwts, gqw, gw_pre, gb_pre, gw_post, gb_post, ws, st)
                   : backward_qp<T, 12>(a, p, qwts, gqw, gw_pre, gb_pre, gw_post, gb_post, ws, st);
 }

@@ -85,6 +85,8 @@ GEN_GEOMS = [
     (2, 16, 50, 3, 1, 1, 40, 4, 1, "angle"),
     (2, 7, 37, 4, 2, 3, 130, 5, 2, "angle"),
     (1, 6, 40, 3, 2, 0, 12, 12, 1, "amplitude"),
+    (2, 40, 70, 3, 3, 1, 24, 6, 1, "amplitude"),    # kernel_size 3 with a stride the one-pass pre_conv^T kernel divides at run time
+    (1, 384, 260, 3, 2, 1, 384, 7, 1, "amplitude"),  # conv2 channel counts: 12 channel chunks, 3 position tiles (one ragged)
 ]
 
 
