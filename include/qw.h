@@ -55,7 +55,7 @@ int qw_timeline_set(unsigned long long* dev_buf, int nslots);
  * O%4==0, O<=576, 16-byte aligned tensors; the forward additionally needs padding==1); 0: always use the generic kernels (used by the parity tests). */
 void qw_set_fast_path(int enable);
 /* Kernel-selection switches (A/B experiments and parity tests ONLY: they choose between equivalent kernels and are not part of
- * the reference-facing contract).  name = "FAST_PATH", "GY_MMA", "BWD_FUSED", "FWD_MMA", ... (csrc/qw_common.cuh, enum Option); each
+ * the reference-facing contract).  name = "FAST_PATH", "GY_MMA", "BWD_FUSED", "FWD_ETMA", ... (csrc/qw_common.cuh, enum Option); each
  * is initialised from the environment variable QW_<name> on first use.  Process-global and NOT re-entrant: do not change an
  * option while another thread is inside a qw_* call.  Returns 0, or -1 for an unknown name. */
 int qw_set_option(const char* name, int value);

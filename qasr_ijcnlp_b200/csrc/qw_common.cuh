@@ -14,7 +14,6 @@ enum Option {
   kOptFastPath = 0,  // FAST_PATH  1: TMA fast path when the shape qualifies; 0: generic kernels
   kOptGyMma,         // GY_MMA     1: gy pass on the tensor pipe (mma.sync 3xTF32); 0: FFMA form
   kOptBwdFused,      // BWD_FUSED  0 (default): gy / adjoint / pre_conv^T kernels; 1: adjoint (+ pre_conv^T of a data layer) inside the gy kernel; 2: adjoint only
-  kOptFwdMma,        // FWD_MMA    1: post_conv of the forward kernel on the tensor pipe; 0: FFMA form
   kOptFwdEtma,       // FWD_ETMA   1: forward requests its first x tiles before staging parameters
   kOptFinEarly,      // FIN_EARLY  1: finalize segments 1-2 run before the dependency wait (split backward only)
   kOptAdjTrig,       // ADJ_TRIG   1: adjoint kernel triggers its dependent right after its wait
