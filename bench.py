@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true")
     ap.add_argument("--e2e-eager", action="store_true", help="do not wrap the e2e module in torch.cuda.make_graphed_callables")
+    ap.add_argument("--stem-forward", default="fused", choices=["fused", "split"],
+                    help="fused: conv1 + conv2 forward in one kernel (qw_stem_train_forward); split: one qw_conv1d_forward per layer")
     ap.add_argument("--collective", default="hybrid", choices=["hybrid", "fused", "p2p", "nccl"],
                     help="gradient all-reduce at N > 1: fused into the backward's last kernel / own one-shot NVLink kernel / NCCL")
     return ap.parse_args()
@@ -224,6 +226,19 @@ class StemRunner:
                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         self._lib.check(st, "qw_conv1d_forward")
 
+    fused_fwd = True                 # conv1 + conv2 forward as ONE kernel (qw_stem_train_forward): conv1's output lands in conv2's x buffer
+
+    def fwd_stem(self, s):
+        """Both forwards in one kernel: y1 = conv1(x) is written straight into the buffer conv2's backward reads as its x (in the
+        split form conv1 writes its own y buffer and conv2 reads an equally large x buffer: same bytes written, one read fewer)."""
+        t1, t2 = self.sets[s].t["conv1"], self.sets[s].t["conv2"]
+        p1, p2 = self.params.p["conv1"], self.params.p["conv2"]
+        c1, c2 = LAYERS["conv1"], LAYERS["conv2"]
+        st = self.lib.qw_stem_train_forward(_p(t1["x"]), *[_p(w) for w in p1], *[_p(w) for w in p2], _p(t2["x"]), _p(t1["pre"]),
+                                            _p(t2["y"]), _p(t2["pre"]), self.B, c1["C"], c1["L"], c1["O"], c2["O"], 1, 0,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check(st, "qw_stem_train_forward")
+
     hybrid = None                    # (P2P reducer of conv2's bucket, side stream) with fused_dp = {"conv1": ...}
     fused_dp = None                  # {layer: dp.FusedLayerGradAllReduce}: the all-reduce rides in the backward's finalize kernel
 
@@ -244,8 +259,11 @@ class StemRunner:
 
     def step(self, s):
         # training order of the stem: conv1 fwd, conv2 fwd, [rest of the model], conv2 bwd, conv1 bwd, gradient all-reduce
-        self.fwd("conv1", s)
-        self.fwd("conv2", s)
+        if self.fused_fwd:
+            self.fwd_stem(s)
+        else:
+            self.fwd("conv1", s)
+            self.fwd("conv2", s)
         self.bwd("conv2", s)
         if self.hybrid is not None:
             # conv2's gradients: own one-shot NVLink all-reduce kernel on a side stream, hidden under conv1's backward;
@@ -291,6 +309,8 @@ class StemRunner:
 
 def algorithmic_bytes(kernel, layer, B):
     """Algorithmic HBM bytes of ONE launch (SURVEY.md 8d per-window figures x windows per launch)."""
+    if layer == "stem":  # fused forward of both layers: the SURVEY figure is per layer, so the sum of the two forwards
+        return algorithmic_bytes(kernel, "conv1", B) + algorithmic_bytes(kernel, "conv2", B) if kernel == "qconv_fwd_kernel" else 0.0
     cfg = LAYERS[layer]
     W = B * cfg["Lout"]
     x_per_win = 4.0 * cfg["C"] * cfg["L"] / cfg["Lout"]
@@ -304,6 +324,12 @@ def algorithmic_bytes(kernel, layer, B):
     if kernel == "qconv_bwd_fused_kernel":
         return W * (y_per_win + x_per_win * (2.0 if cfg["need_gx"] else 1.0))  # the whole backward of the layer
     return 0.0
+
+
+def stem_fwd_moved_bytes(B):
+    """Bytes the fused forward kernel really moves: x in, y1 out, y2 out, both pre_save buffers (conv2's read of y1 is gone)."""
+    c1, c2 = LAYERS["conv1"], LAYERS["conv2"]
+    return 4.0 * B * (c1["C"] * c1["L"] + c1["O"] * c1["Lout"] + c2["O"] * c2["Lout"] + 8 * (c1["Lout"] + c2["Lout"]))
 
 
 def make_config(B, world, nsets):
@@ -391,6 +417,7 @@ def run_b200(args):
 
     B, K, Wm, nsets = args.batch, args.steps, max(args.warmup, 3), args.nsets
     runner = StemRunner(B, dev, nsets)
+    runner.fused_fwd = args.stem_forward == "fused"
     windows_per_step = B * WINDOWS_PER_UTT
     collective = "none (single GPU)"
     if world > 1:
@@ -520,8 +547,11 @@ def run_b200(args):
     # ---- per-kernel durations (CUDA events inside the library, eager launches, same rotating buffers)
     kern = {}
     calls = {}
-    for layer in ("conv1", "conv2"):
-        for what, fn in (("fwd", runner.fwd), ("bwd", runner.bwd)):
+    todo = [(layer, what, fn) for layer in ("conv1", "conv2") for what, fn in (("fwd", runner.fwd), ("bwd", runner.bwd))]
+    if runner.fused_fwd:  # the step's forward is ONE kernel for both layers
+        todo = [("stem", "fwd", lambda _l, s_: runner.fwd_stem(s_))] + [t for t in todo if t[1] == "bwd"]
+    for layer, what, fn in todo:
+        if True:
             for i in range(3):
                 fn(layer, i % nsets)
             torch.cuda.synchronize()
@@ -544,10 +574,12 @@ def run_b200(args):
     dom_ms, dom_how = kern[dom], "CUDA events around one launch (qw_profile_*)"
     if dom[1] == "qconv_fwd_kernel":
         reps = max(40, K)
+        dom_fn = (lambda s_: runner.fwd_stem(s_)) if dom[0] == "stem" else (lambda s_: runner.fwd(dom[0], s_))
         for i in range(8):
-            runner.fwd(dom[0], i % nsets)
-        dom_ms = time_events(lambda i: runner.fwd(dom[0], i % nsets), reps) / reps
-        dom_how = (f"CUDA events around {reps} back-to-back launches of qw_conv1d_forward[{dom[0]}] over {nsets} rotating buffer sets "
+            dom_fn(i % nsets)
+        dom_ms = time_events(lambda i: dom_fn(i % nsets), reps) / reps
+        call_name = "qw_stem_train_forward" if dom[0] == "stem" else f"qw_conv1d_forward[{dom[0]}]"
+        dom_how = (f"CUDA events around {reps} back-to-back launches of {call_name} over {nsets} rotating buffer sets "
                    f"/ {reps} (average launch duration in stream order)")
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     symbols = {}
@@ -556,6 +588,9 @@ def run_b200(args):
         runner.bwd(layer, 0)
         for kname, sym in _lib.kernel_symbols().items():
             symbols[(layer, kname)] = sym
+    if runner.fused_fwd:
+        runner.fwd_stem(0)
+        symbols[("stem", "qconv_fwd_kernel")] = _lib.kernel_symbols().get("qconv_fwd_kernel", "stem_train_fwd_kernel")
     torch.cuda.synchronize()
     traffic = load_traffic().get(f"{dom[0]}.{dom[1]}")
     roofline = {
@@ -566,6 +601,14 @@ def run_b200(args):
         "kernel_share_of_step": round(kern[dom] / step_kernel_ms, 4), "algorithmic_bytes_per_launch": dom_bytes,
         "peak_source": peak_src,
     }
+    if dom[0] == "stem":
+        # `achieved` follows the contract (SURVEY 8d per-layer bytes x windows): the fused kernel does the work of both forwards.
+        # It MOVES less -- conv2's read of the (B, hidden, L) activation is gone -- and that number is stated beside it.
+        moved = stem_fwd_moved_bytes(B)
+        roofline.update({"moved_bytes_per_launch": moved, "moved_GBps": round(moved / (dom_ms * 1e-3) / 1e9, 1),
+                         "frac_of_moved_bytes": round(moved / (dom_ms * 1e-3) / 1e9 / peak, 4),
+                         "note": "one kernel for conv1 + conv2 forward (qw_stem_train_forward): algorithmic bytes = the two layers' "
+                                 "SURVEY figures (the work it replaces); moved bytes = what this formulation needs"})
     kernels = {}
     for (layer, kname), t in sorted(kern.items()):
         ab = algorithmic_bytes(kname, layer, B)
@@ -676,9 +719,15 @@ def step_kernel_names(runner):
     from qasr_ijcnlp_b200 import _lib
 
     names = []
-    for layer, what in (("conv1", "fwd"), ("conv2", "fwd"), ("conv2", "bwd"), ("conv1", "bwd")):
+    order = (("conv1", "fwd"), ("conv2", "fwd"), ("conv2", "bwd"), ("conv1", "bwd"))
+    if runner.fused_fwd:
+        order = (("stem", "fwd"), ("conv2", "bwd"), ("conv1", "bwd"))
+    for layer, what in order:
         n0 = _lib.launch_count()
-        (runner.fwd if what == "fwd" else runner.bwd)(layer, 0)
+        if layer == "stem":
+            runner.fwd_stem(0)
+        else:
+            (runner.fwd if what == "fwd" else runner.bwd)(layer, 0)
         n = _lib.launch_count() - n0
         if what == "fwd":
             kinds = ["fwd"] * n
@@ -738,7 +787,7 @@ def in_graph_timeline(runner, nsets, dev, B, peak, reps=20, world=1):
         per_step = len(used)
     if per_step != len(names):
         names = [f"k{k}" for k in range(per_step)]
-    algo = {}
+    algo = {"stem.fwd": algorithmic_bytes("qconv_fwd_kernel", "stem", B)}
     for layer in ("conv1", "conv2"):
         algo[f"{layer}.fwd"] = algorithmic_bytes("qconv_fwd_kernel", layer, B)
         algo[f"{layer}.bwd_post(gy)"] = algorithmic_bytes("qconv_bwd_post_kernel", layer, B)

@@ -136,6 +136,18 @@ int qw_stem_forward(const float* x, const float* w_pre1, const float* b_pre1, co
                     const float* b_post2, const float* pos_emb, float* out, void* workspace, size_t ws_bytes, int B, int C,
                     int L, int hidden, int O, int n_layers, void* stream);
 
+/* ---- fused TRAINING forward of the stem: y1 = act(conv1(x)) (B, hidden, L), y2 = act(conv2(y1)) (B, O, L/2) in ONE kernel, with
+ * pre_save1 (2, B*L, 4) and pre_save2 (2, B*L/2, 4) exactly as two qw_conv1d_forward_act calls leave them (same values to fp32
+ * rounding: conv2's pre_conv sums in a different order), so the layers' qw_conv1d_backward[_act] calls follow unchanged.  y1 is
+ * written (the backward needs it) but never read back: conv2's pre_conv is taken from the registers that store it.  conv1 =
+ * (C -> hidden, K=3, S=1, P=1), conv2 = (hidden -> O, K=3, S=2, P=1), n_qubits = 4, amplitude embedding; activation QW_ACT_NONE |
+ * QW_ACT_GELU (both layers).  Regime: C <= 96, L % 8 == 0, hidden % 4 == 0, O % 8 == 0, hidden, O <= 384, 16-byte aligned tensors;
+ * -2 otherwise (run the two layers separately). */
+int qw_stem_train_forward(const float* x, const float* w_pre1, const float* b_pre1, const float* qw1, const float* w_post1,
+                          const float* b_post1, const float* w_pre2, const float* b_pre2, const float* qw2, const float* w_post2,
+                          const float* b_post2, float* y1, float* pre_save1, float* y2, float* pre_save2, int B, int C, int L,
+                          int hidden, int O, int n_layers, int activation, void* stream);
+
 /* ---- the QNode alone (quantum_whisper.py:64-85), batched over W windows: pre (W,q) -> out (W,q);
  * backward: gout (W,q) -> gpre (W,q) and gqw (n_layers,q,3) (overwritten).  BASELINE.json config 4. */
 size_t qw_circuit_workspace_bytes(long long W, int q, int n_layers, int elem_size);

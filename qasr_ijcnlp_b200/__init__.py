@@ -5,6 +5,7 @@ module, the log-mel front end, and the encoder classes that call them.  See DESI
 """
 from .quantum_conv1d import (  # noqa: F401
     QuantumConv1d, quantum_conv1d, quantum_circuit, out_length, fused_stem_forward, fused_stem_eligible,
+    stem_train_forward, stem_train_eligible,
 )
 from .encoder import (  # noqa: F401
     ModelDimensions, AudioEncoder, QuantumAudioEncoder, QuantumWhisper, QuantumWhisperClassifier, QuantumWhisperASR,
@@ -12,7 +13,7 @@ from .encoder import (  # noqa: F401
 )
 
 __all__ = [
-    "QuantumConv1d", "quantum_conv1d", "quantum_circuit", "out_length", "fused_stem_forward", "fused_stem_eligible", "ModelDimensions", "AudioEncoder",
+    "QuantumConv1d", "quantum_conv1d", "quantum_circuit", "out_length", "fused_stem_forward", "fused_stem_eligible", "stem_train_forward", "stem_train_eligible", "ModelDimensions", "AudioEncoder",
     "QuantumAudioEncoder", "QuantumWhisper", "QuantumWhisperClassifier", "QuantumWhisperASR", "CharASRHead",
     "CHAR_VOCAB", "get_whisper_tiny_dims", "freeze_non_quantum_layers",
 ]

@@ -38,7 +38,7 @@ def _units():
     """(object name, source, extra flags)"""
     units = [("qw_api.o", "qw_api.cu", [f'-DQW_BUILD_STAMP="{_source_hash()}"']), ("qw_conv1d.o", "qw_conv1d.cu", []), ("qw_logmel.o", "qw_logmel.cu", []),
              ("qw_conv1d_fast.o", "qw_conv1d_fast.cu", []), ("qw_conv1d_general.o", "qw_conv1d_general.cu", []), ("qw_dp.o", "qw_dp.cu", []),
-             ("qw_stem.o", "qw_stem.cu", []), ("qw_collapsed.o", "qw_collapsed.cu", [])]
+             ("qw_stem.o", "qw_stem.cu", []), ("qw_stem_train.o", "qw_stem_train.cu", []), ("qw_collapsed.o", "qw_collapsed.cu", [])]
     for tname, t in (("f32", "float"), ("f64", "double")):
         for q in (1, 2, 3, 4):
             units.append((f"qw_conv1d_inst_{tname}_q{q}.o", "qw_conv1d_inst.cu", [f"-DQW_T={t}", f"-DQW_Q={q}"]))

@@ -48,6 +48,8 @@ struct FastFwdArgs {
   unsigned long long* tl;
   int dbg;  // experiment switch DBG_FWD (results are garbage): 1 = skip the pre_conv FMAs, 2 = skip the post_conv FMAs, 4 = skip the circuit
   int act;  // 1: store gelu(post_conv(<Z>)) -- the activation that follows the layer in the encoder stem, fused into the epilogue
+  int rev;  // 1: walk the tiles from the last to the first (the input was just written by the previous kernel in ascending order:
+            //    its newest lines are the ones still in the 126 MB L2)
 };
 
 constexpr int kFwdStages = 4;
@@ -102,10 +104,11 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
 
   const int my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total_chunks = my_tiles * a.chunks_per_tile;
+  const int tile0 = a.rev ? a.num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x, tstep = a.rev ? -(int)gridDim.x : (int)gridDim.x;
   // producer (thread 0): chunk g of this CTA -> stage g % kFwdStages
   auto issue = [&](int g) {
     const int n = g / a.chunks_per_tile, ch = g - n * a.chunks_per_tile;
-    const int tile = blockIdx.x + n * gridDim.x;
+    const int tile = tile0 + n * tstep;
     const int b = tile / a.tiles_per_utt;
     const int i0 = (tile - b * a.tiles_per_utt) * a.tw;
     const int s = g % kFwdStages;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
   if (warp == kFwdSW) {
     // ======================================================== circuit warp: one lane per window
     for (int n = 0; n < my_tiles; ++n) {
-      const int tile = blockIdx.x + n * gridDim.x;
+      const int tile = tile0 + n * tstep;
       const int b = tile / a.tiles_per_utt;
       const int i = (tile - b * a.tiles_per_utt) * a.tw + lane;
       const int pb = n & 1, ph = (n >> 1) & 1;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kFwdThreads) fast_fwd_kernel(const __grid_cons
     // ---- post_conv of tile n-1
     if (n >= 1) {
       const int m = n - 1;
-      const int tile = blockIdx.x + m * gridDim.x;
+      const int tile = tile0 + m * tstep;
       const int b = tile / a.tiles_per_utt;
       const int i0 = (tile - b * a.tiles_per_utt) * a.tw;
       const int ob = m & 1;
@@ -581,6 +584,7 @@ struct FastGy3Args {
   int dbg;  // experiment switch DBG_GY: 1 = skip the contractions (streaming floor of the kernel); results are garbage
   const float* b_post;  // act != 0 only
   int act;  // 1: the incoming gradient is that of gelu(post_conv(<Z>)): every stage is multiplied by gelu'(post_conv(<Z>)) in place first
+  int rev;  // 1 (plain form): tiles from the last to the first (gy was just written in ascending order by the next layer's pre_conv^T)
 };
 struct RegGateAcc {
   float m[FQ][8];
@@ -659,8 +663,8 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
     my_tiles = (int)(((long long)(blockIdx.x + 1) * a.num_tiles) / gridDim.x) - tile0;
     tstep = 1;
   } else {
-    tile0 = blockIdx.x;
-    tstep = gridDim.x;
+    tile0 = a.rev ? a.num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    tstep = a.rev ? -(int)gridDim.x : (int)gridDim.x;
     my_tiles = ((int)blockIdx.x < a.num_tiles) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   }
 
@@ -1512,7 +1516,7 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
   if (int e = make_tmap_3d_f32(&tm, x, d.L, d.C, d.B, xw, p.rc, false)) return e;
   const size_t W = (size_t)d.B * d.Lout;
   FastFwdArgs a{w_pre, b_pre, qwts, w_post, b_post, y, pre_save, pre_save ? pre_save + W * FQ : nullptr,
-                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot(), option(kOptDbgFwd), act};
+                d.B, d.C, d.L, d.P, d.O, d.Lq, d.Lout, p.tiles_per_utt, p.num_tiles, p.chunks_per_tile, p.tw, flag_fwd_etma(), timeline_next_slot(), option(kOptDbgFwd), act, option(kOptRevTiles) & 1};
   if (d.S == 1) {
     switch (p.rc) {
       case 32: return launch_fast_fwd<1, 32>(tm, a, p, st);
@@ -1581,7 +1585,7 @@ static int launch_fast_gy3_any(const CUtensorMap& tg, const CUtensorMap& tq, con
 static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, const FastGy2Args& a, const FastPlan& p, cudaStream_t st) {
   // default: the tensor-pipe form (fast_bwd_gy3_kernel); QW_GY_MMA=0 selects the FFMA form for A/B
   if (flag_gy_mma() && p.tw == FTW) {
-    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, nullptr, a.B, 0, a.O, a.Lout, 0, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl, option(kOptDbgGy), a.b_post, a.act};
+    FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, nullptr, a.B, 0, a.O, a.Lout, 0, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl, option(kOptDbgGy), a.b_post, a.act, (option(kOptRevTiles) >> 1) & 1};
     return launch_fast_gy3_any<0>(tg, tq, tq, tq, a3, p, st);
   }
   const int forced = option(kOptGyWarps);

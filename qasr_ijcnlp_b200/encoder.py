@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .quantum_conv1d import QuantumConv1d, fused_stem_eligible, fused_stem_forward
+from .quantum_conv1d import QuantumConv1d, fused_stem_eligible, fused_stem_forward, stem_train_forward
 
 
 @dataclass
@@ -143,10 +143,10 @@ class QuantumAudioEncoder(AudioEncoder):
             return self.ln_post(x)
         if not self.fused_stem:
             return super().forward(x)
-        # training (or a shape outside the fused inference kernel): the two operators with their GELUs fused into them
+        # training (or a shape outside the fused inference kernel): both layers with their GELUs in ONE forward kernel
+        # (qw_stem_train_forward) when the shape is the Whisper stem's, else the two operators with their GELUs fused into them
         # (QuantumConv1d.forward_gelu: no separate activation pass in either direction); the rest as AudioEncoder.forward
-        x = self.conv1.forward_gelu(x)
-        x = self.conv2.forward_gelu(x)
+        x = stem_train_forward(self.conv1, self.conv2, x, gelu=True)
         x = x.permute(0, 2, 1)
         if x.shape[1:] != self.positional_embedding.shape:
             raise AssertionError("incorrect audio shape")  # whisper/model.py:197

@@ -235,6 +235,81 @@ class QuantumConv1d(nn.Module):
                 f"embedding={self.embedding!r}")
 
 
+class _StemTrainFn(torch.autograd.Function):
+    """y2 = act(conv2(act(conv1(x)))) for TRAINING: one forward kernel for both layers (qw_stem_train_forward: the (B, hidden, L)
+    activation is written for the backward but never read back), then each layer's own backward (qw_conv1d_backward[_act])."""
+
+    @staticmethod
+    def forward(ctx, x, act, n_layers, *params):
+        lib = _lib.load()
+        B, C, L = x.shape
+        p1 = [t.contiguous() for t in params[:5]]
+        p2 = [t.contiguous() for t in params[5:]]
+        H, O = p1[3].shape[0], p2[3].shape[0]
+        x = x.contiguous()
+        y1 = torch.empty(B, H, L, device=x.device, dtype=x.dtype)
+        y2 = torch.empty(B, O, L // 2, device=x.device, dtype=x.dtype)
+        ps1 = torch.empty(2, B * L, 4, device=x.device, dtype=x.dtype)
+        ps2 = torch.empty(2, B * (L // 2), 4, device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            st = lib.qw_stem_train_forward(_ptr(x), *[_ptr(t) for t in p1], *[_ptr(t) for t in p2], _ptr(y1), _ptr(ps1), _ptr(y2),
+                                           _ptr(ps2), B, C, L, H, O, n_layers, 1 if act else 0, _stream())
+        _lib.check(st, "qw_stem_train_forward")
+        ctx.save_for_backward(x, y1, ps1, ps2, *p1, *p2)
+        ctx.cfg = (B, C, L, H, O, n_layers, bool(act))
+        return y2
+
+    @staticmethod
+    def backward(ctx, gy2):
+        lib = _lib.load()
+        x, y1, ps1, ps2, *pp = ctx.saved_tensors
+        p1, p2 = pp[:5], pp[5:]
+        B, C, L, H, O, n_layers, act = ctx.cfg
+        dev = x.device
+
+        def layer_backward(gy, xin, ps, prm, Cin, Lin, S, Oout, need_gx):
+            w_pre, b_pre, qw, w_post, b_post = prm
+            gx = torch.empty_like(xin) if need_gx else None
+            grads = [torch.empty_like(t) for t in prm]
+            nbytes = lib.qw_conv1d_workspace_bytes(B, Cin, Lin, 3, S, 1, Oout, 4, n_layers, 4)
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            with torch.cuda.device(dev):
+                st = lib.qw_conv1d_backward_act(_ptr(gy), _ptr(xin), _ptr(ps), _ptr(w_pre), _ptr(qw), _ptr(w_post), _ptr(b_post), _ptr(gx),
+                                                *[_ptr(g) for g in grads], _ptr(ws), nbytes, B, Cin, Lin, 3, S, 1, Oout, 4, n_layers, 0,
+                                                1 if act else 0, _stream())
+            _lib.check(st, "qw_conv1d_backward_act")
+            return gx, grads
+
+        g1, grads2 = layer_backward(gy2.contiguous(), y1, ps2, p2, H, L, 2, O, True)
+        gx, grads1 = layer_backward(g1, x, ps1, p1, C, L, 1, H, ctx.needs_input_grad[0])
+        return (gx, None, None, *grads1, *grads2)
+
+
+def stem_train_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor) -> bool:
+    """Shapes qw_stem_train_forward covers: the Whisper stem (conv1 K=3,S=1,P=1; conv2 K=3,S=2,P=1; n_qubits 4, amplitude)."""
+    def ok(m, S):
+        return (isinstance(m, QuantumConv1d) and m.kernel_size == 3 and m.stride == S and m.padding == 1 and m.n_qubits == 4
+                and m.embedding == "amplitude" and m.n_layers <= 4 and m._grad_allreduce is None)
+    if not (ok(conv1, 1) and ok(conv2, 2) and conv1.n_layers == conv2.n_layers and conv2.in_channels == conv1.out_channels):
+        return False
+    lib = _lib.load()
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[1] == conv1.in_channels and conv1.in_channels <= 96
+            and conv1.in_channels % 4 == 0 and x.shape[2] % 8 == 0 and conv1.out_channels % 4 == 0 and conv2.out_channels % 8 == 0 and conv1.out_channels <= 384
+            and conv2.out_channels <= 384 and lib.qw_get_option(b"FAST_PATH") != 0 and lib.qw_get_option(b"GY_MMA") != 0)
+
+
+def stem_train_forward(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor, gelu: bool = True) -> torch.Tensor:
+    """``gelu(conv2(gelu(conv1(x))))`` (or without the activations) for training, differentiable in x and all ten parameters:
+    the first two lines of AudioEncoder.forward (whisper/whisper/model.py:193-194) as one forward kernel."""
+    if not stem_train_eligible(conv1, conv2, x):
+        if gelu:
+            return conv2.forward_gelu(conv1.forward_gelu(x))
+        return conv2(conv1(x))
+    prm = [conv1.pre_conv.weight, conv1.pre_conv.bias, conv1.quantum_weights, conv1.post_conv.weight, conv1.post_conv.bias,
+           conv2.pre_conv.weight, conv2.pre_conv.bias, conv2.quantum_weights, conv2.post_conv.weight, conv2.post_conv.bias]
+    return _StemTrainFn.apply(x, bool(gelu), conv1.n_layers, *prm)
+
+
 def fused_stem_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor) -> bool:
     """True when ``gelu(conv2(gelu(conv1(x))))`` can run through ``qw_stem_forward`` (inference, fast-path regime)."""
     def ok(m, K, S, P):

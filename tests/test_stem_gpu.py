@@ -75,10 +75,11 @@ def test_encoder_uses_fused_stem_in_inference_only(cuda):
     k_train = names()
     _lib.profile_enable(False)
     assert k_inf.get("stem2_kernel") == 1 and k_inf.get("qconv_fwd_kernel") == 1
-    assert "stem2_kernel" not in k_train and k_train.get("qconv_fwd_kernel") == 2
+    # training: ONE forward kernel for both layers (qw_stem_train_forward; it reports under the forward-kernel timer)
+    assert "stem2_kernel" not in k_train and k_train.get("qconv_fwd_kernel") == 1
     assert y_train.requires_grad and not y_fused.requires_grad
     assert (y_fused - y_train.detach()).abs().max().item() <= 2e-4   # through 1 transformer block + LayerNorm
-    # training path: the two layers run with their GELUs fused (QuantumConv1d.forward_gelu); with fused_stem off the encoder is the
+    # training path: both layers and their GELUs in one forward kernel, each layer's own activation-fused backward; with fused_stem off the encoder is the
     # literal op-by-op sequence of AudioEncoder.forward (separate ATen GELUs): same output and same gradients
     loss = y_train.square().mean()
     qparams = [p for n, p in enc.named_parameters() if "conv1" in n or "conv2" in n]
@@ -125,3 +126,46 @@ def test_quantum_audio_encoder_reproduces_the_vendored_subclass(cuda, golden_dir
     with torch.no_grad():
         y_inf = enc(x)
     assert (y_inf.cpu() - want).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("B,L,gelu", [(2, 3000, True), (1, 3000, False), (3, 96, True), (2, 40, True), (5, 1000, True), (16, 3000, True),
+                                      (40, 1000, False)])
+def test_stem_train_forward_equals_the_two_layers(cuda, B, L, gelu):
+    """qw_stem_train_forward (ONE forward kernel for conv1 -> act -> conv2 -> act, conv2's pre_conv taken from the registers that
+    store conv1's output) against the two activation-fused layer calls: outputs, both pre_save buffers (what the backward
+    consumes) and all ten parameter gradients + grad_x.  Tile ranges that start inside an utterance (halo warp), utterance
+    boundaries inside a CTA's range (zero carry), ragged last tiles (L % 32 != 0) and single-tile inputs are all in the grid."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200.quantum_conv1d import stem_train_forward, stem_train_eligible
+    torch.manual_seed(L + B)
+    c1 = qw.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(cuda)
+    c2 = qw.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    x = torch.randn(B, 80, L, device=cuda, requires_grad=True)
+    assert stem_train_eligible(c1, c2, x)
+    y = stem_train_forward(c1, c2, x, gelu=gelu)
+    ref = c2.forward_gelu(c1.forward_gelu(x)) if gelu else c2(c1(x))
+    assert y.shape == ref.shape == (B, 384, L // 2)
+    assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    cot = torch.randn_like(ref)
+    prm = list(c1.parameters()) + list(c2.parameters())
+    g = torch.autograd.grad(y, [x] + prm, cot)
+    gr = torch.autograd.grad(ref, [x] + prm, cot)
+    for a, b in zip(g, gr):
+        assert (a - b).abs().max().item() <= 5e-5 * max(1.0, b.abs().max().item())
+
+
+def test_stem_train_forward_vs_fp64_oracle(cuda):
+    import qasr_ijcnlp_b200 as qw
+    from oracle import qconv_oracle as qo
+    from qasr_ijcnlp_b200.quantum_conv1d import stem_train_forward
+    torch.manual_seed(3)
+    c1 = qw.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(cuda)
+    c2 = qw.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    x = torch.randn(2, 80, 200, device=cuda)
+    with torch.enable_grad():
+        y = stem_train_forward(c1, c2, x.requires_grad_(True), gelu=True)
+    def prm(m):
+        return [t.detach().cpu().double() for t in (m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight,
+                                                    m.post_conv.bias)]
+    ref = qo.stem_forward(x.detach().cpu().double(), prm(c1), prm(c2)).permute(0, 2, 1)
+    assert (y.detach().cpu().double() - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
