@@ -704,22 +704,36 @@ __global__ void __launch_bounds__(Cfg<Q>::THREADS) wcirc_bwd_kernel(const WArgs<
   }
 }
 
-// sum the per-CTA rows (fp64), N -> M = N conj(G), chain rule -> d/d(phi, theta, omega).  One warp per gate.
+// sum the per-CTA rows (fp64), N -> M = N conj(G), chain rule -> d/d(phi, theta, omega).  One 256-thread CTA per gate: thread t
+// takes the rows t, t + 256, ... (two 16-byte loads per row, independent across threads -- one warp per gate walked ~40 dependent
+// rows per lane and took 17 us for a few hundred KB), then the 8 warps meet in shared memory in a fixed order.
 template <typename T>
-__global__ void __launch_bounds__(128) wcirc_finalize_kernel(const T* __restrict__ part, const T* __restrict__ qw, T* __restrict__ gqw,
+__global__ void __launch_bounds__(256) wcirc_finalize_kernel(const T* __restrict__ part, const T* __restrict__ qw, T* __restrict__ gqw,
                                                              int G, int PA, int ngates) {
-  const int lane = threadIdx.x & 31;
-  const int gate = blockIdx.x * 4 + (threadIdx.x >> 5);
+  __shared__ double red[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gate = blockIdx.x;
   if (gate >= ngates) return;
   double n[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) n[e] = 0.0;
-  for (int g = lane; g < G; g += 32)
+  for (int g = threadIdx.x; g < G; g += 256)
 #pragma unroll
     for (int e = 0; e < 8; ++e) n[e] += (double)part[(size_t)g * PA + gate * 8 + e];
 #pragma unroll
   for (int e = 0; e < 8; ++e) n[e] = warp_sum<double>(n[e]);
-  if (lane != 0) return;
+  if (lane == 0)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][e] = n[e];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    double v = red[0][e];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v += red[w][e];
+    n[e] = v;
+  }
   double w3[3] = {(double)qw[gate * 3], (double)qw[gate * 3 + 1], (double)qw[gate * 3 + 2]};
   double s, c, sp, cp, sm, cm;
   sincos(0.5 * w3[1], &s, &c);

@@ -44,7 +44,7 @@ template <typename T>
 int wcirc_finalize_t(const T* part, const T* qw, T* gqw, int G, int PA, int ngates, cudaStream_t st) {
   {
     KernelTimer kt(kKCircFinalize, st);
-    wcirc_finalize_kernel<T><<<(ngates + 3) / 4, 128, 0, st>>>(part, qw, gqw, G, PA, ngates);
+    wcirc_finalize_kernel<T><<<ngates, 256, 0, st>>>(part, qw, gqw, G, PA, ngates);
   }
   QW_CUDA_OK(cudaGetLastError());
   return 0;

@@ -47,12 +47,19 @@ __global__ void __launch_bounds__(kT) gen_preconv_fwd_kernel(const GArgs<T> a) {
     T acc[QP];
 #pragma unroll
     for (int j = 0; j < QP; ++j) acc[j] = T(0);
-    for (int f = warp; f < CK; f += 4) {
-      const int c = f / d.K, k = f - c * d.K;
-      const int l = i * d.S - d.P + k;  // quantum_whisper.py:107-110: padded column i*S + k = original column i*S - P + k
-      const T xv = (i < d.Lout && l >= 0 && l < d.L) ? __ldg(xb + (size_t)c * d.L + l) : T(0);
+    // channels over the 4 warps, taps inside (no division per feature; the K loads of a channel are issued together)
+    const int l0 = i * d.S - d.P;  // quantum_whisper.py:107-110: padded column i*S + k = original column i*S - P + k
+    const bool iv = i < d.Lout;
+    for (int c = warp; c < d.C; c += 4) {
+      const T* __restrict__ xr = xb + (size_t)c * d.L;
+      const T* __restrict__ wr = wt + (size_t)c * d.K * QP;
+#pragma unroll 3
+      for (int k = 0; k < d.K; ++k) {
+        const int l = l0 + k;
+        const T xv = (iv && l >= 0 && l < d.L) ? __ldg(xr + l) : T(0);
 #pragma unroll
-      for (int j = 0; j < QP; ++j) acc[j] = fma(wt[(size_t)f * QP + j], xv, acc[j]);
+        for (int j = 0; j < QP; ++j) acc[j] = fma(wr[k * QP + j], xv, acc[j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < QP; ++j) part[((size_t)warp * kTW + lane) * QP + j] = acc[j];

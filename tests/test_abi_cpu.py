@@ -70,6 +70,15 @@ def test_argument_validation_without_a_gpu(lib):
     assert st == -2 and b"n_qubits" in lib.qw_last_error()
     st = lib.qw_log_mel(None, None, None, None, 0, 1, 480000, 80, None)
     assert st == -1
+    # fused training forward of the stem: null pointers, then shapes outside its regime (-2: run the two layers separately)
+    st = lib.qw_stem_train_forward(*([None] * 15), 16, 80, 3000, 384, 384, 1, 1, None)
+    assert st == -1 and b"null" in lib.qw_last_error()
+    st = lib.qw_stem_train_forward(*([one] * 15), 16, 128, 3000, 384, 384, 1, 1, None)      # C > 96
+    assert st == -2 and b"fused regime" in lib.qw_last_error()
+    st = lib.qw_stem_train_forward(*([one] * 15), 16, 80, 3004, 384, 384, 1, 1, None)       # L % 8 != 0
+    assert st == -2
+    st = lib.qw_stem_train_forward(*([one] * 15), 16, 80, 3000, 384, 384, 1, 7, None)       # unknown activation
+    assert st == -2 and b"activation" in lib.qw_last_error()
 
 
 def test_workspace_sizes_are_pure_host_arithmetic(lib):
@@ -80,6 +89,11 @@ def test_workspace_sizes_are_pure_host_arithmetic(lib):
     assert lib.qw_conv1d_workspace_bytes(0, 384, 3000, 3, 2, 1, 384, 4, 1, 4) == 0
     assert lib.qw_circuit_workspace_bytes(1 << 20, 4, 1, 4) > 0
     assert lib.qw_log_mel_workspace_bytes(16, 480000, 80) > 0
+    # per-call workspace of the prepared entry points: B utterance maxima + 9 (min, max) pairs per 32-frame tile
+    w = lib.qw_log_mel_call_workspace_bytes(16, 480000)
+    assert w % 256 == 0 and w >= 16 * 4 + 16 * 94 * 9 * 8
+    assert lib.qw_log_mel_call_workspace_bytes(0, 480000) == 0
+    assert lib.qw_log_mel_workspace_bytes(16, 480000, 80) >= w + lib.qw_log_mel_prep_bytes(80)
 
 
 def test_product_path_does_not_import_the_oracle():

@@ -125,3 +125,25 @@ def test_module_with_six_qubits_trains(cuda):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
     with torch.no_grad():
         assert m(x).shape == (2, 384, 300)  # inference (no autograd) goes through the same composed path
+
+
+def test_general_layer_full_size_conv2_geometry(cuda):
+    """The one-pass pre_conv^T kernel, the prefetched gy pass and the 8-way row reduction of the general path at the stem's conv2
+    geometry (384 -> 384, stride 2, 3000 -> 1500 positions: 12 channel chunks x 24 position tiles, 592 + partial rows), n_qubits 6:
+    output and all six gradients against the fp64 oracle."""
+    from qasr_ijcnlp_b200 import quantum_conv1d
+    B, C, L, K, S, P, O, q = 2, 384, 3000, 3, 2, 1, 384, 6
+    params64 = qo.make_params(C, O, K, q, n_layers=1, seed=11)
+    g = torch.Generator().manual_seed(12)
+    x64 = torch.randn(B, C, L, generator=g, dtype=torch.float64)
+    Lo = qo.out_length(L, K, S, P)
+    gy64 = torch.randn(B, O, Lo, generator=g, dtype=torch.float64)
+    ref = qo.qconv1d_grads(x64.float().double(), [p.float().double() for p in params64], gy64.float().double(), K, S, P)
+    x = x64.float().to(cuda).requires_grad_(True)
+    ps = [p.float().to(cuda).requires_grad_(True) for p in params64]
+    y = quantum_conv1d(x, *ps, kernel_size=K, stride=S, padding=P)
+    grads = torch.autograd.grad(y, [x] + ps, gy64.float().to(cuda))
+    rel = lambda a, b: (a - b).abs().max().item() / max(1.0, b.abs().max().item())
+    assert rel(y.detach().cpu().double(), ref["y"]) <= 5e-5
+    for name, gr in zip(["x", "w_pre", "b_pre", "qweights", "w_post", "b_post"], grads):
+        assert rel(gr.cpu().double(), ref[name]) <= 5e-5, name

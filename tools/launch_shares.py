@@ -15,9 +15,10 @@ for r in rows[hdr + 1:]:
         continue
     t = float(r[vi].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1.0)
     name = re.sub(r"\(.*$", "", r[ki]).replace("void ", "").replace("qw::", "")
+    name = re.sub(r"^(st|lm|gen|wc)::", "", name)  # kernels of the library's nested namespaces
     agg.setdefault(name, []).append(t)
     seq.append((name, t))
-own = {k: v for k, v in agg.items() if k.startswith(("fast_", "qconv_", "logmel_", "wcirc", "circuit_", "gen_", "grads_"))}
+own = {k: v for k, v in agg.items() if k.startswith(("fast_", "qconv_", "logmel_", "wcirc", "circuit_", "gen_", "grads_", "stem"))}
 tot = sum(sum(v) for v in own.values())
 print(f"# {sys.argv[1]}: {len(seq)} launches, {sum(len(v) for v in own.values())} from libqw_b200.so; times in us (ncu, cold cache, serialised)")
 print(f"{'kernel':58s} {'launches':>8s} {'mean us':>9s} {'share of own time':>18s}")

@@ -26,6 +26,8 @@ for r in rows[2:]:
     m = re.search(r"fast_bwd_pre_kernel<\(?int\)?(\d)", name) or re.search(r"fast_bwd_pre_kernel<(\d)", name)
     if m:
         key = f"conv{m.group(1)}.qconv_bwd_pre_kernel"
+    if "stem_train_fwd_kernel" in name:
+        key = "stem.qconv_fwd_kernel"
     if "fast_bwd_gy2_kernel" in name or "fast_bwd_gy_kernel" in name or "fast_bwd_gy3_kernel" in name:
         key = "gy"
     if key:
