@@ -835,20 +835,32 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
         // ~0.4 IPC these kernels run at (the arithmetic of gelu' is only 9 us of it; the rest is the loads, z and the in-place store)
         // -- against ~45 us for ATen's separate gelu_backward pass (two reads + a write of the tensor) plus the 28 us kernel.
         float* gmut = stages + (size_t)s * SE;
-        for (int u = tid; u < kGy3Rows * 8; u += kGy3Threads) {
-          const int rl = u >> 3, c = u & 7, r = h * kGy3Rows + rl;
-          if (r < a.O) {
+        // a thread keeps its 16-byte chunk column (c = tid & 7: the same four windows in every row it visits), so the <Z> of those
+        // windows are loaded once per stage, and the post_conv rows it needs (straight from global memory, 7.7 KB, L1-resident:
+        // keeping them in shared memory pushed the CTA past 98 KB) are all requested before the first is used
+        constexpr int NIT = kGy3Rows * 8 / kGy3Threads;  // 6 rows per thread and stage
+        const int c = tid & 7;
+        float4 q4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q4[e] = ld4(os + (4 * c + e) * FQ);
+        float4 wv[NIT];
+        float bv[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int r = h * kGy3Rows + (tid >> 3) + it * (kGy3Threads / 8);
+          wv[it] = r < a.O ? __ldg(reinterpret_cast<const float4*>(a.w_post) + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bv[it] = r < a.O ? __ldg(a.b_post + r) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int rl = (tid >> 3) + it * (kGy3Threads / 8);
+          if (h * kGy3Rows + rl < a.O) {
             float* p = gmut + swz128(rl, c);
             float4 gv = ld4(p);
-            // post_conv weights / bias straight from global memory (7.7 KB, L1-resident): keeping them in shared memory pushed the
-            // CTA past 98 KB and the SM to ONE resident CTA (the 196 KB carve-out), which doubled the kernel time
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w_post) + r);
-            const float bv = __ldg(a.b_post + r);
             float* ge = reinterpret_cast<float*>(&gv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float4 q4 = ld4(os + (4 * c + e) * FQ);
-              const float z = fmaf(wv.w, q4.w, fmaf(wv.z, q4.z, fmaf(wv.y, q4.y, fmaf(wv.x, q4.x, bv))));
+              const float z = fmaf(wv[it].w, q4[e].w, fmaf(wv[it].z, q4[e].z, fmaf(wv[it].y, q4[e].y, fmaf(wv[it].x, q4[e].x, bv[it]))));
               ge[e] *= gelu_erf_grad(z);
             }
             st4(p, gv);
