@@ -68,8 +68,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true")
     ap.add_argument("--e2e-eager", action="store_true", help="do not wrap the e2e module in torch.cuda.make_graphed_callables")
-    ap.add_argument("--stem-forward", default="fused", choices=["fused", "split"],
-                    help="fused: conv1 + conv2 forward in one kernel (qw_stem_train_forward); split: one qw_conv1d_forward per layer")
+    ap.add_argument("--stem-forward", default="auto", choices=["auto", "fused", "split"],
+                    help="fused: conv1 + conv2 forward in one kernel (qw_stem_train_forward); split: one qw_conv1d_forward per layer; "
+                         "auto: whichever the library prefers for this batch (qw_stem_train_forward_preferred)")
+    ap.add_argument("--stem-backward", default="chained", choices=["chained", "split"],
+                    help="chained: conv2's backward writes no grad_x, conv1's gy kernel rebuilds it from conv2's gpre rows "
+                         "(qw_conv1d_backward_chained); split: the gradient goes through HBM between the two layers' backwards")
     ap.add_argument("--collective", default="hybrid", choices=["hybrid", "fused", "p2p", "nccl"],
                     help="gradient all-reduce at N > 1: fused into the backward's last kernel / own one-shot NVLink kernel / NCCL")
     return ap.parse_args()
@@ -242,9 +246,28 @@ class StemRunner:
     hybrid = None                    # (P2P reducer of conv2's bucket, side stream) with fused_dp = {"conv1": ...}
     fused_dp = None                  # {layer: dp.FusedLayerGradAllReduce}: the all-reduce rides in the backward's finalize kernel
 
+    chained = True                   # conv1's backward rebuilds its incoming gradient from conv2's gpre rows (qw_conv1d_backward_chained):
+                                     # conv2's backward writes no grad_x and conv1's gy kernel reads none
+
     def bwd(self, name, s):
         cfg, t, p, g = LAYERS[name], self.sets[s].t[name], self.params.p[name], self.params.g[name]
         ws, n = self.ws[name]
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.chained and name == "conv2":
+            # no gradient for conv2's input is written: conv1's chained backward does not need it
+            st = self.lib.qw_conv1d_backward(_p(t["gy"]), _p(t["x"]), _p(t["pre"]), _p(p[0]), _p(p[2]), _p(p[3]), None,
+                                             _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(ws), n, *self._dims(cfg), stream)
+            self._lib.check(st, "qw_conv1d_backward")
+            return
+        if self.chained and name == "conv1":
+            ws2, _ = self.ws["conv2"]
+            p2 = self.params.p["conv2"]
+            dp = self.fused_dp[name].args() if (self.fused_dp is not None and name in self.fused_dp) else (None, None, 0, 1, 1.0)
+            st = self.lib.qw_conv1d_backward_chained(_p(ws2), _p(p2[0]), LAYERS["conv2"]["O"], _p(t["x"]), _p(t["pre"]), _p(p[0]), _p(p[2]),
+                                                     _p(p[3]), _p(p[4]), _p(t["gx"]), _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]),
+                                                     _p(ws), n, *self._dims(cfg), 0, *dp, stream)
+            self._lib.check(st, "qw_conv1d_backward_chained")
+            return
         if self.fused_dp is not None and name in self.fused_dp:
             st = self.lib.qw_conv1d_backward_dp(_p(t["gy"]), _p(t["x"]), _p(t["pre"]), _p(p[0]), _p(p[2]), _p(p[3]), _p(t["gx"]),
                                                 _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]), _p(ws), n, *self._dims(cfg),
@@ -307,6 +330,9 @@ class StemRunner:
     allreduce_split = None           # or (reducer conv1, reducer conv2, side stream): per-layer buckets, conv2's overlapped
 
 
+CHAINED = False  # set by run_b200: the step uses qw_conv1d_backward_chained
+
+
 def algorithmic_bytes(kernel, layer, B):
     """Algorithmic HBM bytes of ONE launch (SURVEY.md 8d per-window figures x windows per launch)."""
     if layer == "stem":  # fused forward of both layers: the SURVEY figure is per layer, so the sum of the two forwards
@@ -320,7 +346,8 @@ def algorithmic_bytes(kernel, layer, B):
     if kernel == "qconv_bwd_post_kernel":
         return W * y_per_win  # reads gy once
     if kernel == "qconv_bwd_pre_kernel":
-        return W * x_per_win * (2.0 if cfg["need_gx"] else 1.0)  # re-read x (+ write grad_x)
+        # re-read x (+ write grad_x -- not in the chained backward, where conv2's gradient for its input is never written)
+        return W * x_per_win * (2.0 if (cfg["need_gx"] and not (CHAINED and layer == "conv2")) else 1.0)
     if kernel == "qconv_bwd_fused_kernel":
         return W * (y_per_win + x_per_win * (2.0 if cfg["need_gx"] else 1.0))  # the whole backward of the layer
     return 0.0
@@ -376,7 +403,8 @@ def check_dp_parity(runner, world, dev):
     t = torch.tensor([err, 0.0 if bitwise else 1.0, float(status)], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"max_rel_err": float(t[0].item()), "bitwise_equal_across_ranks": bool(t[1].item() == 0.0), "status_word": int(t[2].item()),
-            "reference": "qw_conv1d_backward + torch.distributed.all_reduce(AVG) (NCCL) on the same inputs",
+            "reference": "the same step with every gradient collective removed (qw_conv1d_backward[_chained], world = 1 arguments) + "
+                         "torch.distributed.all_reduce(AVG) (NCCL) on the same inputs",
             "tolerance": 1e-6, "grad_floats": int(got.numel()), "local_grad_absmax": local_max}
 
 
@@ -417,7 +445,11 @@ def run_b200(args):
 
     B, K, Wm, nsets = args.batch, args.steps, max(args.warmup, 3), args.nsets
     runner = StemRunner(B, dev, nsets)
-    runner.fused_fwd = args.stem_forward == "fused"
+    runner.fused_fwd = (args.stem_forward == "fused" or
+                        (args.stem_forward == "auto" and bool(runner.lib.qw_stem_train_forward_preferred(B, LAYERS["conv1"]["L"]))))
+    runner.chained = args.stem_backward == "chained"
+    global CHAINED
+    CHAINED = runner.chained
     windows_per_step = B * WINDOWS_PER_UTT
     collective = "none (single GPU)"
     if world > 1:

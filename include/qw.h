@@ -106,6 +106,22 @@ int qw_conv1d_backward_dp(const float* gy, const float* x, const float* pre_save
                           int q, int n_layers, int embedding, void* const* peer_bufs, void* const* peer_flags, int rank,
                           int world, float scale, void* stream);
 
+/* ---- CHAINED backward: this layer's incoming gradient is the grad_x of the layer that FOLLOWS it in the stem -- a QuantumConv1d
+ * with kernel_size 3, stride 2, padding 1, in_channels = this O, input length = this L_out (conv2 of quantum_whisper.py:137 after
+ * conv1 of :136).  Run the following layer's backward first with gx = NULL (it then writes no (B, O, L_out) gradient at all), keep
+ * its workspace, and call this instead of qw_conv1d_backward[_act | _dp]: the gy kernel rebuilds every 32-window tile of the
+ * gradient from the following layer's gpre rows (16 bytes per window, inside next_workspace) and its pre_conv weights next_w_pre
+ * (4, O*3), so the 4*B*O*L_out bytes are neither written nor read.  activation: QW_ACT_NONE | QW_ACT_GELU -- the activation between
+ * the two layers (its derivative is applied to the rebuilt tile); b_post may be NULL without it.  world > 1: gradient mean over the
+ * ranks as in qw_conv1d_backward_dp (peer tables may be NULL for world == 1).  Same outputs as the unchained calls up to fp32
+ * summation order.  -2 outside the regime (fast path, n_qubits 4, option GY_MMA). */
+int qw_conv1d_backward_chained(const void* next_workspace, const float* next_w_pre, int next_O, const float* x, const float* pre_save,
+                               const float* w_pre, const float* qw, const float* w_post, const float* b_post, float* gx,
+                               float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post, void* workspace,
+                               size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int embedding,
+                               int activation, void* const* peer_bufs, void* const* peer_flags, int rank, int world, float scale,
+                               void* stream);
+
 /* ---- the layer with the activation that follows it in the encoder stem FUSED (whisper/whisper/model.py:193-194:
  * x = F.gelu(self.conv1(x)); x = F.gelu(self.conv2(x)), exact-erf GELU): training-time counterpart of qw_stem_forward.
  * forward:  y = gelu(post_conv(<Z>)) is what gets stored (the pre-activation never exists in HBM); pre_save as qw_conv1d_forward.
@@ -143,6 +159,9 @@ int qw_stem_forward(const float* x, const float* w_pre1, const float* b_pre1, co
  * (C -> hidden, K=3, S=1, P=1), conv2 = (hidden -> O, K=3, S=2, P=1), n_qubits = 4, amplitude embedding; activation QW_ACT_NONE |
  * QW_ACT_GELU (both layers).  Regime: C <= 96, L % 8 == 0, hidden % 4 == 0, O % 8 == 0, hidden, O <= 384, 16-byte aligned tensors;
  * -2 otherwise (run the two layers separately). */
+/* 1 when the one-kernel forward is expected to beat two qw_conv1d_forward_act calls for this batch (few tiles per CTA: launches are
+ * latency-dominated), 0 when the two leaner kernels win (measured crossover between batch 16 and 32 of 30 s audio on B200). */
+int qw_stem_train_forward_preferred(int B, int L);
 int qw_stem_train_forward(const float* x, const float* w_pre1, const float* b_pre1, const float* qw1, const float* w_post1,
                           const float* b_post1, const float* w_pre2, const float* b_pre2, const float* qw2, const float* w_post2,
                           const float* b_post2, float* y1, float* pre_save1, float* y2, float* pre_save2, int B, int C, int L,

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "qw_stem_workspace_bytes": (_SZ, [_I, _I]),
     "qw_stem_forward": (_I, [_P] * 13 + [_P, _SZ] + [_I] * 6 + [_P]),
     "qw_stem_train_forward": (_I, [_P] * 15 + [_I] * 7 + [_P]),
+    "qw_stem_train_forward_preferred": (_I, [_I, _I]),
+    "qw_conv1d_backward_chained": (_I, [_P, _P, _I] + [_P] * 13 + [_SZ] + _CONV_DIMS + [_I] + [ctypes.POINTER(_P), ctypes.POINTER(_P), _I, _I, ctypes.c_float, _P]),
     "qw_circuit_workspace_bytes": (_SZ, [_LL, _I, _I, _I]),
     "qw_circuit_forward": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),
     "qw_circuit_forward_f64": (_I, [_P, _P, _P, _LL, _I, _I, _I, _P]),

@@ -35,7 +35,7 @@ struct OptDef {
   int dflt;
 };
 static const OptDef kOptDefs[kOptCount] = {{"FAST_PATH", 1}, {"GY_MMA", 1}, {"BWD_FUSED", 0}, {"FWD_ETMA", 1}, {"FIN_EARLY", 1},
-                                           {"ADJ_TRIG", 1}, {"PRE_EX", 1}, {"ADJ_SPEC", 1}, {"PRE_CTAS", 4}, {"GY_WARPS", 0}, {"DP_TIMEOUT_MS", 600000}, {"DBG_FWD", 0}, {"DBG_GY", 0}, {"REV_TILES", 0}};
+                                           {"ADJ_TRIG", 1}, {"PRE_EX", 1}, {"ADJ_SPEC", 1}, {"PRE_CTAS", 4}, {"GY_WARPS", 0}, {"DP_TIMEOUT_MS", 600000}, {"DBG_FWD", 0}, {"DBG_GY", 0}, {"STEM_CHAIN", 1}, {"REV_TILES", 0}};
 static std::atomic<int> g_opt[kOptCount];
 static std::once_flag g_opt_once;
 static void opt_init() {

@@ -24,6 +24,7 @@ enum Option {
   kOptDpTimeoutMs,   // DP_TIMEOUT_MS  how long the NVLink gradient all-reduce kernels wait for a peer before trapping (default 600 000; 0 = forever)
   kOptDbgFwd,        // DBG_FWD    bit mask: forward kernel skips pre_conv FMAs (1) / post_conv FMAs (2) / circuit (4); results are garbage
   kOptDbgGy,         // DBG_GY     1: gy kernel skips its contractions (measures the streaming floor; results are garbage)
+  kOptStemChain,     // STEM_CHAIN 1 (default): the stem-level backward (Python _StemTrainFn, bench) chains conv1's gy pass to conv2's gpre rows; 0: grad_x through HBM
   kOptRevTiles,      // REV_TILES  bit 0: forward kernels, bit 1: gy kernel walk their tiles from the last to the first (L2 reuse of the producer's newest lines)
   kOptCount
 };

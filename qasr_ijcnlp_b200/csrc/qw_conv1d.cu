@@ -113,8 +113,8 @@ template <typename T>
 static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, const T* w_pre, const T* qwts, const T* w_post,
                                 T* gx, T* gw_pre, T* gb_pre, T* gqw, T* gw_post, T* gb_post, void* workspace,
                                 size_t ws_bytes, ConvDims d, void* stream, const FastDp* dp = nullptr, const T* b_post = nullptr,
-                                int act = 0) {
-  QW_CHECK_ARG(gy && x && pre_save && w_pre && qwts && w_post && gw_pre && gb_pre && gqw && gw_post && gb_post && workspace,
+                                int act = 0, const FastChain* chain = nullptr) {
+  QW_CHECK_ARG((gy || chain) && x && pre_save && w_pre && qwts && w_post && gw_pre && gb_pre && gqw && gw_post && gb_post && workspace,
                -1, "null pointer argument");
   if (int e = check_dims(d)) return e;
   QW_CHECK_ARG(((uintptr_t)workspace & 255) == 0, -1, "workspace must be 256-byte aligned");
@@ -126,6 +126,7 @@ static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, cons
   QW_CHECK_ARG(!act || b_post, -1, "the fused activation needs post_conv.bias");
   if (is_general(d)) {
     QW_CHECK_ARG(!act, -2, "the fused activation needs the fast-path regime (n_qubits=4, amplitude embedding)");
+    QW_CHECK_ARG(!chain, -2, "the chained backward needs the fast-path regime (n_qubits=4, amplitude embedding)");
     return gen::general_backward<T>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, ws_bytes, d, st);
   }
   QW_CHECK_ARG(d.K <= 8, -2, "backward supports kernel_size <= 8 (got %d)", d.K);
@@ -133,9 +134,10 @@ static int conv1d_backward_impl(const T* gy, const T* x, const T* pre_save, cons
     if (fast_eligible(d, x, gy, gx, false) && (((uintptr_t)pre_save) & 15) == 0) {
       const FastPlan fp = make_fast_plan(d);
       QW_CHECK_ARG(ws_bytes >= fp.ws_bytes, -3, "workspace too small: %zu < %zu", ws_bytes, fp.ws_bytes);
-      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st, dp, b_post, act);
+      return fast_backward(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, ws, d, st, dp, b_post, act, chain);
     }
   }
+  QW_CHECK_ARG(!chain, -2, "the chained backward needs the fast-path regime (fp32, K=3, stride 1|2, L %% 4 == 0, O %% 4 == 0, aligned tensors)");
   QW_CHECK_ARG(!act, -2, "the fused activation needs the fast-path regime (fp32, K=3, stride 1|2, L %% 4 == 0, O %% 4 == 0, aligned tensors)");
   QW_CHECK_ARG(!want_dp, -2, "the fused gradient all-reduce needs the fast-path regime (fp32, K=3, stride 1|2, L %% 4 == 0, O %% 4 == 0, aligned tensors)");
   const Plan p = make_plan(d);
@@ -307,6 +309,44 @@ int qw_conv1d_backward_dp(const float* gy, const float* x, const float* pre_save
   dp.timeout_ns = (unsigned long long)(qw::option(qw::kOptDpTimeoutMs) > 0 ? qw::option(qw::kOptDpTimeoutMs) : 0) * 1000000ull;
   return qw::conv1d_backward_impl<float>(gy, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post,
                                          workspace, ws_bytes, d, stream, &dp);
+}
+
+int qw_conv1d_backward_chained(const void* next_workspace, const float* next_w_pre, int next_O, const float* x, const float* pre_save,
+                               const float* w_pre, const float* qwts, const float* w_post, const float* b_post, float* gx,
+                               float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post, void* workspace,
+                               size_t ws_bytes, int B, int C, int L, int K, int S, int P, int O, int q, int n_layers, int embedding,
+                               int activation, void* const* peer_bufs, void* const* peer_flags, int rank, int world, float scale,
+                               void* stream) {
+  using namespace qw;
+  ConvDims d{B, C, L, K, S, P, O, q, n_layers, embedding, 0};
+  QW_CHECK_ARG(next_workspace && next_w_pre, -1, "qw_conv1d_backward_chained: null pointer argument");
+  if (int e = check_dims(d)) return e;
+  // the following layer: in_channels = this O, input length = this L_out, kernel_size 3, stride 2, padding 1, same circuit size
+  ConvDims d2{B, O, d.Lout, 3, 2, 1, next_O, q, n_layers, embedding, 0};
+  if (int e = check_dims(d2)) return e;
+  QW_CHECK_ARG(q == 4 && embedding == kEmbAmplitude && option(kOptGyMma) && option(kOptFastPath) && (O * 3) % 4 == 0 &&
+                   (((uintptr_t)next_w_pre) & 15) == 0 && (((uintptr_t)next_workspace) & 255) == 0 && d.Lout % 2 == 0 &&
+                   fast_eligible(d2, x, x, x, false),
+               -2, "qw_conv1d_backward_chained: outside the chained regime (n_qubits 4, amplitude embedding, tensor-pipe gy kernel, the "
+                   "following layer a fast-path kernel_size-3 / stride-2 / padding-1 layer on this layer's output)");
+  const FastPlan p2 = make_fast_plan(d2);
+  FastChain chain{reinterpret_cast<const float*>(static_cast<const unsigned char*>(next_workspace) + p2.off_gpre), next_w_pre, p2.LP};
+  QW_CHECK_ARG(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, -1, "qw_conv1d_backward_chained: bad rank/world %d/%d", rank, world);
+  FastDp dp{};
+  if (world > 1) {
+    QW_CHECK_ARG(peer_bufs && peer_flags, -1, "qw_conv1d_backward_chained: null peer pointer tables");
+    for (int r = 0; r < world; ++r) {
+      QW_CHECK_ARG(peer_bufs[r] && peer_flags[r], -1, "qw_conv1d_backward_chained: null peer pointer for rank %d", r);
+      dp.bufs[r] = (float*)peer_bufs[r];
+      dp.flags[r] = (unsigned*)peer_flags[r];
+    }
+  }
+  dp.rank = rank;
+  dp.world = world;
+  dp.scale = scale;
+  dp.timeout_ns = (unsigned long long)(option(kOptDpTimeoutMs) > 0 ? option(kOptDpTimeoutMs) : 0) * 1000000ull;
+  return conv1d_backward_impl<float>(nullptr, x, pre_save, w_pre, qwts, w_post, gx, gw_pre, gb_pre, gqw, gw_post, gb_post, workspace, ws_bytes,
+                                     d, stream, world > 1 ? &dp : nullptr, b_post, activation, &chain);
 }
 
 size_t qw_circuit_workspace_bytes(long long W, int q, int n_layers, int elem_size) {

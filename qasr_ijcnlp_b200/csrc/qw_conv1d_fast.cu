@@ -340,6 +340,9 @@ struct FastGy2Args {
   unsigned long long* tl;
   const float* b_post = nullptr;  // fused activation (tensor-pipe kernel only)
   int act = 0;
+  const float* gen_gpre = nullptr;  // chained backward (tensor-pipe kernel only): see FastGy3Args
+  const float* gen_w = nullptr;
+  int gen_LP = 0;
 };
 // NW warps, one thread per stage row (stage = 32*NW output channels x 32 windows), NST-deep ring
 __host__ __device__ constexpr size_t fast_gy2_smem_bytes(int O, int NW, int NST) {
@@ -533,8 +536,9 @@ __global__ void __launch_bounds__(32 * NW, 2) fast_bwd_gy2_kernel(const __grid_c
 constexpr int kGy3Warps = 8, kGy3Threads = 32 * kGy3Warps, kGy3Rows = 192, kGy3Stages = 3;
 constexpr int kGy3Bpw = kGy3Rows / 8 / kGy3Warps;  // 8-channel blocks of a stage per warp (24 blocks over 8 warps: an even load on the 4 sub-partitions)
 static_assert(kGy3Bpw * kGy3Warps * 8 == kGy3Rows, "stage rows must split evenly over the warps");
-__host__ __device__ constexpr size_t fast_gy3_smem_bytes() {
+__host__ __device__ constexpr size_t fast_gy3_smem_bytes(int gen_O = 0) {
   return 1024 + (size_t)kGy3Stages * kGy3Rows * 32 * 4 + (size_t)3 * FTW * FQ * 4 + (size_t)2 * kGy3Warps * FTW * 8 * 4 +
+         (size_t)gen_O * 3 * FQ * 4 +            // GEN form: the following layer's pre_conv weights, [O*3][4]
          (3 * kGy3Stages + 2 * 6 + 1) * 8;  // barrier block laid out as in the fused forms
 }
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
@@ -585,6 +589,12 @@ struct FastGy3Args {
   const float* b_post;  // act != 0 only
   int act;  // 1: the incoming gradient is that of gelu(post_conv(<Z>)): every stage is multiplied by gelu'(post_conv(<Z>)) in place first
   int rev;  // 1 (plain form): tiles from the last to the first (gy was just written in ascending order by the next layer's pre_conv^T)
+  // GEN form: the incoming gradient is NOT read -- it is the grad_x of the FOLLOWING QuantumConv1d (kernel_size 3, stride 2,
+  // padding 1, in_channels = this O, input length = this L_out), rebuilt tile by tile from that layer's gpre rows (16 bytes per
+  // window, halo-padded, L2-resident) and its pre_conv weights; the following layer's pre_conv^T then never writes grad_x.
+  const float* gen_gpre = nullptr;  // [B][gen_LP][4], window i of the following layer at row kHaloL + i
+  const float* gen_w = nullptr;     // the following layer's pre_conv.weight (4, O*3)
+  int gen_LP = 0;
 };
 struct RegGateAcc {
   float m[FQ][8];
@@ -610,7 +620,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 }
 __device__ __forceinline__ void bar_sync_streaming() { asm volatile("bar.sync 1, %0;" ::"n"(kGy3Threads) : "memory"); }
 
-template <int NHALF, int FUSED, bool ACT>
+template <int NHALF, int FUSED, bool ACT, bool GEN>
 __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
     fast_bwd_gy3_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_qout,
                         const __grid_constant__ CUtensorMap tm_pre, const __grid_constant__ CUtensorMap tm_x, const FastGy3Args a) {
@@ -625,7 +635,8 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
   float* gpre_s = gout_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);       // fused: [kFbMaxTiles][32][4]
   float* gred = gpre_s + (FUSED ? kFbMaxTiles * FTW * FQ : 0);         // [2][6 warps][32 windows][8]
   float* gates = gred + 2 * kGy3Warps * FTW * 8;                       // fused: [4][16]
-  uint64_t* full = reinterpret_cast<uint64_t*>(gates + (FUSED ? FQ * kGateStride : 0));
+  float* w2t = gates + (FUSED ? FQ * kGateStride : 0);                 // GEN: [O*3][4] pre_conv weights of the following layer
+  uint64_t* full = reinterpret_cast<uint64_t*>(w2t + (GEN ? (size_t)a.O * 3 * FQ : 0));
   uint64_t* empty = full + kGy3Stages;
   uint64_t* xfull = empty + kGy3Stages;                                // FUSED = 1: x tiles of the pre_conv^T phase
   uint64_t* pqfull = xfull + kGy3Stages;                               // fused: [kFbMaxTiles] <Z> + pre_conv outputs of tile n landed
@@ -736,6 +747,17 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
         split_tf32(v, hi, lo);
         bw[h][i][e] = g < 4 ? hi : lo;
       }
+  if (GEN) {  // (4, O*3) -> [O*3][4], 4 features x 4 qubits per step (a parameter: readable before the dependency wait)
+    const int CK2 = a.O * 3;
+    for (int u = tid; u < CK2 / 4; u += kGy3Threads) {
+      const float4 r0 = ld4(a.gen_w + 0 * (size_t)CK2 + 4 * u), r1 = ld4(a.gen_w + 1 * (size_t)CK2 + 4 * u);
+      const float4 r2 = ld4(a.gen_w + 2 * (size_t)CK2 + 4 * u), r3 = ld4(a.gen_w + 3 * (size_t)CK2 + 4 * u);
+      st4(w2t + (size_t)(4 * u + 0) * FQ, make_float4(r0.x, r1.x, r2.x, r3.x));
+      st4(w2t + (size_t)(4 * u + 1) * FQ, make_float4(r0.y, r1.y, r2.y, r3.y));
+      st4(w2t + (size_t)(4 * u + 2) * FQ, make_float4(r0.z, r1.z, r2.z, r3.z));
+      st4(w2t + (size_t)(4 * u + 3) * FQ, make_float4(r0.w, r1.w, r2.w, r3.w));
+    }
+  }
   // lane offsets (floats) inside a stage
   int off1[4], off2[2][2];
 #pragma unroll
@@ -772,10 +794,12 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
     const int b = tile / a.tiles_per_utt;
     const int i0 = (tile - b * a.tiles_per_utt) * FTW;
     const int s = gs % kGy3Stages;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(SE + ((h == 0 && !FUSED) ? FTW * FQ : 0)) * 4);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)((GEN ? 0 : SE) + ((h == 0 && !FUSED) ? FTW * FQ : 0)) * 4);
+    if (!GEN) {
 #pragma unroll
-    for (int bx = 0; bx < kGy3Rows / 64; ++bx)
-      tma_load_3d(stages + (size_t)s * SE + bx * 64 * 32, &tm_gy, i0, h * kGy3Rows + bx * 64, b, &full[s]);
+      for (int bx = 0; bx < kGy3Rows / 64; ++bx)
+        tma_load_3d(stages + (size_t)s * SE + bx * 64 * 32, &tm_gy, i0, h * kGy3Rows + bx * 64, b, &full[s]);
+    }
     if (h == 0) {
       if (FUSED) {
         mbar_arrive_expect_tx(&pqfull[n], (uint32_t)(2 * FTW * FQ) * 4);
@@ -798,6 +822,15 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
       for (int j = 0; j < 4; ++j) d2[m][j] = 0.f;
     uint32_t aq[4][4];
     const float* os = outs + (n % NQT) * FTW * FQ;
+    float4 gq[3];  // GEN: gpre rows of the following layer's windows m, m + 1, m + 2 that touch this thread's four positions
+    if (GEN) {
+      const int tile = tile0 + n * tstep;
+      const int b = tile / a.tiles_per_utt;
+      const int i0 = (tile - b * a.tiles_per_utt) * FTW;
+      const float4* gp = reinterpret_cast<const float4*>(a.gen_gpre) + ((size_t)b * a.gen_LP + kHaloL + (i0 >> 1) + 2 * (tid & 7));
+#pragma unroll
+      for (int e = 0; e < 3; ++e) gq[e] = __ldg(gp + e);  // rows past the utterance are the zeroed halo: positions >= L_out come out 0
+    }
 #pragma unroll
     for (int h = 0; h < NHALF; ++h, ++gs) {
       if (tid == 0) {
@@ -806,7 +839,7 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
           if (gn >= kGy3Stages) mbar_wait(&empty[gn % kGy3Stages], ((gn / kGy3Stages) - 1) & 1);
           // the slot was rewritten in place by generic-proxy stores (fused activation) that the empty barrier has ordered before
           // this point: one proxy fence in the issuing thread orders them before the TMA engine's refill
-          if (ACT) fence_proxy_async();
+          if (ACT && !GEN) fence_proxy_async();
           issue(gn);
         }
       }
@@ -828,7 +861,50 @@ __global__ void __launch_bounds__(FUSED ? kGy3Threads + 32 : kGy3Threads, 2)
           }
         }
       }
-      if (ACT) {
+      if (GEN) {
+        // The stage is COMPUTED, not loaded: gy[r][l] = grad_x of the following layer = sum_k sum_j w2[j][r*3+k] gpre2[i(l,k)][j]
+        // with l = 2 i - 1 + k (stride 2, padding 1).  A thread owns the positions l0 .. l0 + 3, l0 = i0 + 4 c = 2 m:
+        //   l0 (even): tap 1 of window m;  l0+1: tap 0 of m+1 and tap 2 of m;  l0+2: tap 1 of m+1;  l0+3: tap 0 of m+2 and tap 2 of m+1.
+        // 24 FMAs + three LDS.128 of weights per 16 bytes of the tile instead of a 73.7 MB tensor written by one kernel and read by
+        // the next.  full[s] only guards the <Z> rows here; it cannot complete before every warp has released the slot's previous
+        // contents (the issuing thread waits for empty[s] first), so the slot is free to write.  With ACT the gelu' factor of THIS
+        // layer is applied before the store (no separate in-place pass).
+        float* gmut = stages + (size_t)s * SE;
+        constexpr int NIT = kGy3Rows * 8 / kGy3Threads;
+        const int c = tid & 7;
+        float4 q4[4];
+        if (ACT) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q4[e] = ld4(os + (4 * c + e) * FQ);
+        }
+        auto dot4 = [](const float4& w, const float4& g_) { return fmaf(w.w, g_.w, fmaf(w.z, g_.z, fmaf(w.y, g_.y, w.x * g_.x))); };
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int rl = (tid >> 3) + it * (kGy3Threads / 8);
+          const int r = h * kGy3Rows + rl;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < a.O) {
+            const float* wr = w2t + (size_t)(r * 3) * FQ;
+            const float4 W0 = ld4(wr), W1 = ld4(wr + FQ), W2 = ld4(wr + 2 * FQ);
+            v.x = dot4(W1, gq[0]);
+            v.y = dot4(W0, gq[1]) + dot4(W2, gq[0]);
+            v.z = dot4(W1, gq[1]);
+            v.w = dot4(W0, gq[2]) + dot4(W2, gq[1]);
+            if (ACT) {
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w_post) + r);
+              const float bv = __ldg(a.b_post + r);
+              float* ve = reinterpret_cast<float*>(&v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float z = fmaf(wv.w, q4[e].w, fmaf(wv.z, q4[e].z, fmaf(wv.y, q4[e].y, fmaf(wv.x, q4[e].x, bv))));
+                ve[e] *= gelu_erf_grad(z);
+              }
+            }
+          }
+          st4(gmut + swz128(rl, c), v);
+        }
+        __syncthreads();
+      } else if (ACT) {
         // fused activation backward: g <- g * gelu'(z), z = post_conv(<Z>) rebuilt from the 16 bytes per window the forward saved
         // (the pre-activation itself is never stored).  In place on the stage, one pass, 128-byte rows; then everybody syncs.
         // Measured on B200 (batch 16, conv1): this pass takes the kernel from 28 to 70 us -- 27 instructions per element at the
@@ -1564,13 +1640,14 @@ static int launch_fast_gy2(const CUtensorMap& tg, const CUtensorMap& tq, const F
 // gy 14.7 / 23.2 vs 12.9 / 21.8 us) -- the extra warps do not raise the issue rate of the two contractions, the 2-deep ring
 // loses a stage of prefetch, and the fatter CTAs leave less room for the early-resident adjoint CTAs.  Also measured and dropped:
 // 3 CTAs per SM of the 6-warp form with a 2-deep ring (444 CTAs): 139.2 us.
-template <int NHALF, int FUSED, bool ACT>
+template <int NHALF, int FUSED, bool ACT, bool GEN = false>
 static int launch_fast_gy3_t(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
                              const FastPlan& p, cudaStream_t st) {
-  const size_t smem = FUSED ? fast_gy3_fused_smem_bytes() : fast_gy3_smem_bytes();
-  auto k = fast_bwd_gy3_kernel<NHALF, FUSED, ACT>;
+  const size_t smem = FUSED ? fast_gy3_fused_smem_bytes() : fast_gy3_smem_bytes(GEN ? a.O : 0);
+  QW_CHECK_ARG(smem <= 113 * 1024, -2, "chained backward: %zu bytes of shared memory per CTA (out_channels too large)", smem);
+  auto k = fast_bwd_gy3_kernel<NHALF, FUSED, ACT, GEN>;
   QW_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  note_symbol(FUSED ? kKBwdFused : kKBwdPost, "fast_bwd_gy3_kernel<%d, %d, %d>", NHALF, FUSED, (int)ACT);
+  note_symbol(FUSED ? kKBwdFused : kKBwdPost, "fast_bwd_gy3_kernel<%d, %d, %d, %d>", NHALF, FUSED, (int)ACT, (int)GEN);
   {
     KernelTimer kt(FUSED ? kKBwdFused : kKBwdPost, st);
     QW_CUDA_OK(launch_pdl(p.small, k, dim3(p.gridGy), dim3(FUSED ? kGy3Threads + 32 : kGy3Threads), smem, st, tg, tq, tp, tx, a));
@@ -1582,6 +1659,7 @@ template <int NHALF, int FUSED>
 static int launch_fast_gy3(const CUtensorMap& tg, const CUtensorMap& tq, const CUtensorMap& tp, const CUtensorMap& tx, const FastGy3Args& a,
                            const FastPlan& p, cudaStream_t st) {
   if constexpr (FUSED == 0) {
+    if (a.gen_gpre) return a.act ? launch_fast_gy3_t<NHALF, 0, true, true>(tg, tq, tp, tx, a, p, st) : launch_fast_gy3_t<NHALF, 0, false, true>(tg, tq, tp, tx, a, p, st);
     if (a.act) return launch_fast_gy3_t<NHALF, 0, true>(tg, tq, tp, tx, a, p, st);
   }
   return launch_fast_gy3_t<NHALF, FUSED, false>(tg, tq, tp, tx, a, p, st);
@@ -1598,8 +1676,12 @@ static int launch_fast_gy2_any(const CUtensorMap& tg, const CUtensorMap& tq, con
   // default: the tensor-pipe form (fast_bwd_gy3_kernel); QW_GY_MMA=0 selects the FFMA form for A/B
   if (flag_gy_mma() && p.tw == FTW) {
     FastGy3Args a3{a.w_post, nullptr, a.gout, a.part, nullptr, nullptr, nullptr, a.B, 0, a.O, a.Lout, 0, a.tiles_per_utt, a.num_tiles, a.PA1, 0, 0, a.tl, option(kOptDbgGy), a.b_post, a.act, (option(kOptRevTiles) >> 1) & 1};
+    a3.gen_gpre = a.gen_gpre;
+    a3.gen_w = a.gen_w;
+    a3.gen_LP = a.gen_LP;
     return launch_fast_gy3_any<0>(tg, tq, tq, tq, a3, p, st);
   }
+  QW_CHECK_ARG(a.gen_gpre == nullptr, -2, "the chained backward needs the tensor-pipe gy kernel (option GY_MMA=1)");
   const int forced = option(kOptGyWarps);
   const bool wide = forced == 12;
   if (wide) {
@@ -1628,15 +1710,16 @@ static int launch_fast_pre(const CUtensorMap& tx, const CUtensorMap& tgx, const 
 
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
-                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp, const float* b_post, int act) {
+                  unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp, const float* b_post, int act, const FastChain* chain) {
   const FastPlan p = make_fast_plan(d);
   const size_t W = (size_t)d.B * d.Lout;
   float* gpre = reinterpret_cast<float*>(ws + p.off_gpre);
   float* part1 = reinterpret_cast<float*>(ws + p.off_p1);
   float* part3 = reinterpret_cast<float*>(ws + p.off_p3);
   alignas(64) CUtensorMap tm_gy, tm_qout, tm_x, tm_gx;
-  if (int e = make_tmap_3d_f32(&tm_gy, gy, d.Lout, d.O, d.B, 32, 64, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_qout, pre_save + W * FQ, FQ, d.Lout, d.B, FQ, p.tw, false)) return e;
+  if (chain) tm_gy = tm_qout;  // never dereferenced: the chained gy kernel rebuilds its tiles from the following layer's gpre rows
+  else if (int e = make_tmap_3d_f32(&tm_gy, gy, d.Lout, d.O, d.B, 32, 64, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_x, x, d.L, d.C, d.B, 32, 32, true)) return e;
   if (int e = make_tmap_3d_f32(&tm_gx, gx ? gx : x, d.L, d.C, d.B, 32, 32, true)) return e;
   float* gout = reinterpret_cast<float*>(ws + p.off_gout);
@@ -1646,7 +1729,7 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   // mode 2 = gpre goes to the workspace for the pre_conv^T kernel below.
   int fused = 0;
   QW_CHECK_ARG(!act || (flag_gy_mma() && b_post), -2, "the fused activation needs the tensor-pipe gy kernel (option GY_MMA=1) and post_conv.bias");
-  if (!act && flag_bwd_fused() && flag_gy_mma() && d.Lq == 1 && p.tw == FTW && (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy)
+  if (!chain && !act && flag_bwd_fused() && flag_gy_mma() && d.Lq == 1 && p.tw == FTW && (long long)p.num_tiles <= (long long)kFbMaxTiles * p.gridGy)
     fused = (gx == nullptr && d.S == 1 && d.P == 1 && d.C <= kFbXRows && flag_bwd_fused() == 1) ? 1 : 2;
   if (fused) {
     alignas(64) CUtensorMap tm_pre, tm_xf;
@@ -1679,6 +1762,11 @@ int fast_backward(const float* gy, const float* x, const float* pre_save, const 
   // 1) stream gy: gout + partial rows of grad post_conv.{weight,bias}
   if (!fused) {
     FastGy2Args a{w_post, gout, part1, d.B, d.O, d.Lout, p.tiles_per_utt, p.num_tiles, p.PA1, p.tw, timeline_next_slot(), b_post, act};
+    if (chain) {
+      a.gen_gpre = chain->gpre_pad;
+      a.gen_w = chain->w_pre;
+      a.gen_LP = chain->LP;
+    }
     if (int e = launch_fast_gy2_any(tm_gy, tm_qout, a, p, st)) return e;
   }
   // 2) adjoint differentiation of the circuit, one window per thread

@@ -65,6 +65,13 @@ struct FastAdjArgs {
   int early_trigger;  // experiment switch QW_ADJ_TRIG: trigger the dependent launch right after the wait
   unsigned long long* tl;
 };
+// chained backward: this layer's incoming gradient is the grad_x of the FOLLOWING layer (kernel_size 3, stride 2, padding 1), which
+// its own backward did not write (gx = NULL); the gy kernel rebuilds it from that layer's gpre rows and pre_conv weights
+struct FastChain {
+  const float* gpre_pad;  // the following layer's halo-padded gpre, [B][LP][4] (inside ITS backward workspace)
+  const float* w_pre;     // the following layer's pre_conv.weight (4, O*3)
+  int LP;
+};
 bool fast_eligible(const ConvDims& d, const void* x, const void* y_or_gy, const void* gx, bool fwd);
 FastPlan make_fast_plan(const ConvDims& d);
 int fast_forward(const float* x, const float* w_pre, const float* b_pre, const float* qwts, const float* w_post,
@@ -72,7 +79,7 @@ int fast_forward(const float* x, const float* w_pre, const float* b_pre, const f
 int fast_backward(const float* gy, const float* x, const float* pre_save, const float* w_pre, const float* qwts,
                   const float* w_post, float* gx, float* gw_pre, float* gb_pre, float* gqw, float* gw_post, float* gb_post,
                   unsigned char* ws, const ConvDims& d, cudaStream_t st, const FastDp* dp = nullptr, const float* b_post = nullptr,
-                  int act = 0);
+                  int act = 0, const FastChain* chain = nullptr);
 
 // fused inference stem (qw_stem.cu)
 size_t stem_workspace_bytes(int B, int L);

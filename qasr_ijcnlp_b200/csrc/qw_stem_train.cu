@@ -494,6 +494,16 @@ static int launch(const CUtensorMap& tm, const Args& a, int grid, bool small, cu
 }  // namespace st
 }  // namespace qw
 
+// Measured on B200 (bench.py --stem-forward fused|split, ms per stem step): batch 16 (5.1 tiles per CTA) 0.1163 vs 0.1198, batch 32
+// (10.2) 0.2111 vs 0.2091, batch 64 0.3954 vs 0.3737, batch 256 1.482 vs 1.343 -- the fused kernel saves a kernel boundary and
+// conv2's read of the activation, which pays while launches are latency-dominated; with many tiles per CTA its longer per-tile
+// instruction stream (both layers' epilogues in one warp role) loses to two leaner kernels.
+extern "C" int qw_stem_train_forward_preferred(int B, int L) {
+  if (B <= 0 || L <= 0) return 0;
+  const long long tiles = (long long)B * ((L + qw::st::FTW - 1) / qw::st::FTW);
+  return tiles <= 8LL * 2 * qw::num_sms() ? 1 : 0;
+}
+
 extern "C" int qw_stem_train_forward(const float* x, const float* w_pre1, const float* b_pre1, const float* qw1, const float* w_post1,
                                      const float* b_post1, const float* w_pre2, const float* b_pre2, const float* qw2,
                                      const float* w_post2, const float* b_post2, float* y1, float* pre_save1, float* y2,

@@ -252,9 +252,18 @@ class _StemTrainFn(torch.autograd.Function):
         ps1 = torch.empty(2, B * L, 4, device=x.device, dtype=x.dtype)
         ps2 = torch.empty(2, B * (L // 2), 4, device=x.device, dtype=x.dtype)
         with torch.cuda.device(x.device):
-            st = lib.qw_stem_train_forward(_ptr(x), *[_ptr(t) for t in p1], *[_ptr(t) for t in p2], _ptr(y1), _ptr(ps1), _ptr(y2),
-                                           _ptr(ps2), B, C, L, H, O, n_layers, 1 if act else 0, _stream())
-        _lib.check(st, "qw_stem_train_forward")
+            if lib.qw_stem_train_forward_preferred(B, L):
+                st = lib.qw_stem_train_forward(_ptr(x), *[_ptr(t) for t in p1], *[_ptr(t) for t in p2], _ptr(y1), _ptr(ps1), _ptr(y2),
+                                               _ptr(ps2), B, C, L, H, O, n_layers, 1 if act else 0, _stream())
+                _lib.check(st, "qw_stem_train_forward")
+            else:  # many tiles per CTA: two leaner forward kernels win; the saved tensors are the same, so is the chained backward
+                a = 1 if act else 0
+                st = lib.qw_conv1d_forward_act(_ptr(x), *[_ptr(t) for t in p1], _ptr(y1), _ptr(ps1), B, C, L, 3, 1, 1, H, 4, n_layers, 0, a,
+                                               _stream())
+                _lib.check(st, "qw_conv1d_forward_act")
+                st = lib.qw_conv1d_forward_act(_ptr(y1), *[_ptr(t) for t in p2], _ptr(y2), _ptr(ps2), B, H, L, 3, 2, 1, O, 4, n_layers, 0, a,
+                                               _stream())
+                _lib.check(st, "qw_conv1d_forward_act")
         ctx.save_for_backward(x, y1, ps1, ps2, *p1, *p2)
         ctx.cfg = (B, C, L, H, O, n_layers, bool(act))
         return y2
@@ -280,8 +289,30 @@ class _StemTrainFn(torch.autograd.Function):
             _lib.check(st, "qw_conv1d_backward_act")
             return gx, grads
 
-        g1, grads2 = layer_backward(gy2.contiguous(), y1, ps2, p2, H, L, 2, O, True)
-        gx, grads1 = layer_backward(g1, x, ps1, p1, C, L, 1, H, ctx.needs_input_grad[0])
+        if lib.qw_get_option(b"STEM_CHAIN") == 0:
+            g1, grads2 = layer_backward(gy2.contiguous(), y1, ps2, p2, H, L, 2, O, True)
+            gx, grads1 = layer_backward(g1, x, ps1, p1, C, L, 1, H, ctx.needs_input_grad[0])
+            return (gx, None, None, *grads1, *grads2)
+        # chained: conv2's backward writes NO gradient for its input; conv1's gy kernel rebuilds that gradient tile by tile from conv2's
+        # gpre rows (inside conv2's workspace) and pre_conv weights (qw_conv1d_backward_chained)
+        w_pre2, b_pre2, qw2, w_post2, b_post2 = p2
+        grads2 = [torch.empty_like(t) for t in p2]
+        n2 = lib.qw_conv1d_workspace_bytes(B, H, L, 3, 2, 1, O, 4, n_layers, 4)
+        ws2 = torch.empty(n2, device=dev, dtype=torch.uint8)
+        w_pre1, b_pre1, qw1, w_post1, b_post1 = p1
+        grads1 = [torch.empty_like(t) for t in p1]
+        n1 = lib.qw_conv1d_workspace_bytes(B, C, L, 3, 1, 1, H, 4, n_layers, 4)
+        ws1 = torch.empty(n1, device=dev, dtype=torch.uint8)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        a = 1 if act else 0
+        with torch.cuda.device(dev):
+            st = lib.qw_conv1d_backward_act(_ptr(gy2.contiguous()), _ptr(y1), _ptr(ps2), _ptr(w_pre2), _ptr(qw2), _ptr(w_post2), _ptr(b_post2),
+                                            None, *[_ptr(g) for g in grads2], _ptr(ws2), n2, B, H, L, 3, 2, 1, O, 4, n_layers, 0, a, _stream())
+            _lib.check(st, "qw_conv1d_backward_act")
+            st = lib.qw_conv1d_backward_chained(_ptr(ws2), _ptr(w_pre2), O, _ptr(x), _ptr(ps1), _ptr(w_pre1), _ptr(qw1), _ptr(w_post1),
+                                                _ptr(b_post1), _ptr(gx), *[_ptr(g) for g in grads1], _ptr(ws1), n1, B, C, L, 3, 1, 1, H, 4,
+                                                n_layers, 0, a, None, None, 0, 1, 1.0, _stream())
+            _lib.check(st, "qw_conv1d_backward_chained")
         return (gx, None, None, *grads1, *grads2)
 
 

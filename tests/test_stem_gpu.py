@@ -129,12 +129,14 @@ def test_quantum_audio_encoder_reproduces_the_vendored_subclass(cuda, golden_dir
 
 
 @pytest.mark.parametrize("B,L,gelu", [(2, 3000, True), (1, 3000, False), (3, 96, True), (2, 40, True), (5, 1000, True), (16, 3000, True),
-                                      (40, 1000, False)])
+                                      (40, 1000, False), (80, 1000, True)])
 def test_stem_train_forward_equals_the_two_layers(cuda, B, L, gelu):
     """qw_stem_train_forward (ONE forward kernel for conv1 -> act -> conv2 -> act, conv2's pre_conv taken from the registers that
     store conv1's output) against the two activation-fused layer calls: outputs, both pre_save buffers (what the backward
     consumes) and all ten parameter gradients + grad_x.  Tile ranges that start inside an utterance (halo warp), utterance
-    boundaries inside a CTA's range (zero carry), ragged last tiles (L % 32 != 0) and single-tile inputs are all in the grid."""
+    boundaries inside a CTA's range (zero carry), ragged last tiles (L % 32 != 0) and single-tile inputs are all in the grid.  The
+    backward is the CHAINED one (conv2 writes no grad_x, conv1's gy kernel rebuilds it from conv2's gpre rows); the largest case
+    has more tiles per CTA than qw_stem_train_forward_preferred accepts, so its forward is two kernels with the same backward."""
     import qasr_ijcnlp_b200 as qw
     from qasr_ijcnlp_b200.quantum_conv1d import stem_train_forward, stem_train_eligible
     torch.manual_seed(L + B)
