@@ -79,6 +79,13 @@ def test_argument_validation_without_a_gpu(lib):
     assert st == -2
     st = lib.qw_stem_train_forward(*([one] * 15), 16, 80, 3000, 384, 384, 1, 7, None)       # unknown activation
     assert st == -2 and b"activation" in lib.qw_last_error()
+    # chained backward: null pointers, then a circuit size outside the chained regime
+    args = lambda q: ([one, one, 384] + [one] * 13 + [1 << 30] + [16, 80, 3000, 3, 1, 1, 384, q, 1, 0] + [0, None, None, 0, 1, ctypes.c_float(1.0), None])
+    st = lib.qw_conv1d_backward_chained(None, None, 384, *args(4)[3:])
+    assert st == -1 and b"null" in lib.qw_last_error()
+    st = lib.qw_conv1d_backward_chained(*args(3))
+    assert st == -2 and b"chained regime" in lib.qw_last_error()
+    assert lib.qw_stem_train_forward_preferred(16, 3000) == 1 and lib.qw_stem_train_forward_preferred(0, 3000) == 0
 
 
 def test_workspace_sizes_are_pure_host_arithmetic(lib):
