@@ -42,3 +42,25 @@ for shape in ((B, 384, 3000), (B, 384, 1500)):
         e[0].record(); y = F.gelu(t); e[1].record(); y.backward(g); e[2].record(); torch.cuda.synchronize()
         tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
     print(f"ATen gelu {shape}: fwd {tf * 100:.1f} us, bwd {tb * 100:.1f} us (event brackets)")
+# the whole training stem through stem_train_forward (one forward kernel at this batch + the chained backward), per launch in order
+from qasr_ijcnlp_b200 import stem_train_forward
+c1 = QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(dev)
+c2 = QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(dev)
+xs = [torch.rand(B, 80, 3000, device=dev) * 3 - 1.5 for _ in range(4)]
+gys = [torch.randn(B, 384, 1500, device=dev) for _ in range(4)]
+prm = list(c1.parameters()) + list(c2.parameters())
+def sstep(i):
+    y = stem_train_forward(c1, c2, xs[i % 4], gelu=True)
+    torch.autograd.grad(y, prm, gys[i % 4])
+for i in range(3):
+    sstep(i)
+torch.cuda.synchronize()
+_lib.profile_read(True); _lib.profile_enable(True)
+for i in range(20):
+    sstep(i)
+torch.cuda.synchronize()
+_lib.profile_enable(False)
+prof = _lib.profile_read(True)
+print("stem_train_forward (gelu) + chained backward, mean us per launch (launches per step): " +
+      ", ".join(f"{k.replace('qconv_', '')} {v[0] / v[1] * 1e3:.1f} ({v[1] // 20})" for k, v in sorted(prof.items())) +
+      f"; sum {sum(v[0] for v in prof.values()) / 20 * 1e3:.1f} us per step")
