@@ -13,7 +13,10 @@ python tools/prof_act.py > $R/r2_gelu_fused_kernels.txt 2>&1
 python tools/bench_general.py > $R/r2_general_path_stem_b16.jsonl 2> $R/r2_general.err
 python tools/prof_general.py --q 6 8 10 > $R/r2_general_path_kernels_b16.jsonl 2>> $R/r2_general.err
 python tools/prof_general.py --q 4 --embedding angle >> $R/r2_general_path_kernels_b16.jsonl 2>> $R/r2_general.err
+# the probe binaries are not shipped to the GPU box (.gpurunignore): build them there
+nvcc -cudart shared -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/probe/mma_probe.cu -o tools/probe/mma_probe 2> $R/probe_build.err && \
 ./tools/probe/mma_probe > $R/r2_mma_probe.txt 2>&1
+nvcc -cudart shared -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/probe/stream_probe.cu -o tools/probe/stream_probe -lcuda 2>> $R/probe_build.err && \
 tools/probe/run_stream_probe.sh > $R/r2_stream_probe.txt 2>&1
 python bench.py --steps 4 --warmup 4 --no-cpu-baseline --no-encoder > $R/b_plain2.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $R/r2_launches_bench_b16.csv python bench.py --steps 4 --warmup 4 --no-cpu-baseline --no-encoder > $R/ncu_launches2.log 2>&1
