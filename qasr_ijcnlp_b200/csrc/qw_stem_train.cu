@@ -19,7 +19,7 @@
 //                          hidden x 4 FMAs).  Then C2(m): conv2's circuit on lanes 0-15 for every tile of the range
 // A tile's 16 conv2 windows need 33 columns of y1: its own 32 and the one to their LEFT (tap 0 of its first window).  That term
 // flows forward as a "carry": the last (odd) column of tile n contributes tap 0 to the first window of tile n + 1, which the same
-// CTA handles next; only the first tile of a CTA's range needs the halo warp.  All hand-offs are mbarriers; there is no CTA-wide
+// CTA handles next; only the first tile of a CTA's range needs the recomputed halo column.  All hand-offs are mbarriers; there is no CTA-wide
 // barrier in the loop.
 #include "../../include/qw.h"
 #include "qw_act.cuh"
@@ -32,7 +32,7 @@ namespace st {
 
 constexpr int FQ = 4, FTW = 32;
 constexpr int kSW = 8;                        // streaming warps
-constexpr int kThreadsT = (kSW + 2) * 32;     // + circuit warp + halo warp
+constexpr int kThreadsT = (kSW + 2) * 32;     // + the two circuit warps
 constexpr int kStages = 3;
 constexpr int XW = 40;                        // x tile columns (stride 1): tap k of local window w = column 3 + w + k
 constexpr int kP2 = 17;                       // conv2 windows a tile contributes to: its own 16 + the carry
@@ -83,8 +83,7 @@ __global__ void __launch_bounds__(kThreadsT, 2) stem_train_fwd_kernel(const __gr
   float* outs = part + 2 * kSW * FTW * FQ;                         // [2][32][4]
   float* part2 = outs + 2 * FTW * FQ;                              // [2][kSW][17][4]
   float* outs2 = part2 + 2 * kSW * kP2 * FQ;                       // [2][16][4]
-  float* halo = outs2 + 2 * 16 * FQ;                               // [4]
-  uint64_t* full = reinterpret_cast<uint64_t*>(halo + 4);          // [kStages]
+  uint64_t* full = reinterpret_cast<uint64_t*>(outs2 + 2 * 16 * FQ + 4);  // [kStages]
   uint64_t* empty = full + kStages;
   uint64_t* pfull = empty + kStages;   // [2] each below
   uint64_t* pempty = pfull + 2;
@@ -94,7 +93,6 @@ __global__ void __launch_bounds__(kThreadsT, 2) stem_train_fwd_kernel(const __gr
   uint64_t* p2empty = p2full + 2;
   uint64_t* o2full = p2empty + 2;
   uint64_t* o2empty = o2full + 2;
-  uint64_t* hfull = o2empty + 2;       // [1]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 3, tl = lane & 7;
@@ -128,7 +126,6 @@ __global__ void __launch_bounds__(kThreadsT, 2) stem_train_fwd_kernel(const __gr
       mbar_init(&o2full[s], 1);
       mbar_init(&o2empty[s], kSW);
     }
-    mbar_init(hfull, 1);
     fence_mbar_init();
     pdl_wait();
     for (int n = 0; n < kStages - 1 && n < my_tiles; ++n) issue(n);
@@ -171,7 +168,7 @@ __global__ void __launch_bounds__(kThreadsT, 2) stem_train_fwd_kernel(const __gr
   pdl_launch();
 
   if (warp == kSW + 1) {
-    // ======================================================== halo warp: tap-0 term of the range's first conv2 window
+    // ======================================================== circuit warp 2: first the tap-0 term of the range's first conv2 window
     if (my_tiles > 0) {
       const int b = tile0 / a.tiles_per_utt;
       const int i0 = (tile0 - b * a.tiles_per_utt) * FTW;
