@@ -171,3 +171,25 @@ def test_stem_train_forward_vs_fp64_oracle(cuda):
                                                     m.post_conv.bias)]
     ref = qo.stem_forward(x.detach().cpu().double(), prm(c1), prm(c2)).permute(0, 2, 1)
     assert (y.detach().cpu().double() - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("C,H,O,n_layers,L", [(80, 384, 384, 2, 256), (32, 128, 64, 1, 200), (96, 96, 384, 3, 96), (80, 512, 384, 1, 128)])
+def test_stem_train_forward_other_shapes(cuda, C, H, O, n_layers, L):
+    """Multi-layer circuits, small / unequal channel counts, and a hidden width outside the fused regime (512 > 384: the helper
+    must fall back to the two activation-fused layers and give the same numbers)."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200.quantum_conv1d import stem_train_forward, stem_train_eligible
+    torch.manual_seed(C + H + O + n_layers)
+    c1 = qw.QuantumConv1d(C, H, 3, padding=1, n_qubits=4, n_layers=n_layers).to(cuda)
+    c2 = qw.QuantumConv1d(H, O, 3, stride=2, padding=1, n_qubits=4, n_layers=n_layers).to(cuda)
+    x = torch.randn(3, C, L, device=cuda, requires_grad=True)
+    assert stem_train_eligible(c1, c2, x) == (H <= 384)
+    y = stem_train_forward(c1, c2, x, gelu=True)
+    ref = c2.forward_gelu(c1.forward_gelu(x))
+    assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    cot = torch.randn_like(ref)
+    prm = list(c1.parameters()) + list(c2.parameters())
+    g = torch.autograd.grad(y, [x] + prm, cot)
+    gr = torch.autograd.grad(ref, [x] + prm, cot)
+    for a, b in zip(g, gr):
+        assert (a - b).abs().max().item() <= 5e-5 * max(1.0, b.abs().max().item())
