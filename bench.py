@@ -915,6 +915,24 @@ def run_e2e(runner, B, K, Wm, world, dev, graphed=True):
     stem = torch.nn.Sequential(conv1, torch.nn.GELU(), conv2)
     api = "QuantumConv1d nn.Module x2 + GELU (nn.Sequential), eager autograd"
     call = stem
+    stem_helper = False
+    if world == 1 and os.environ.get("QW_E2E_PLAIN", "0") != "1":
+        # the package's stem helper on the same two modules: conv1 -> GELU -> conv2 with the GELU inside conv1's kernels and the
+        # gradient between the layers never written (stem_train_forward; falls back to the plain modules outside its regime)
+        from qasr_ijcnlp_b200 import stem_train_forward
+
+        class _Stem(torch.nn.Module):
+            def __init__(self, c1, c2):
+                super().__init__()
+                self.conv1, self.conv2 = c1, c2
+
+            def forward(self, x):
+                return stem_train_forward(self.conv1, self.conv2, x, gelu=(True, False))
+
+        stem = _Stem(conv1, conv2)
+        call = stem
+        stem_helper = True
+        api = "stem_train_forward(conv1, conv2, x, gelu=(True, False)) on two QuantumConv1d nn.Modules, eager autograd"
     # data parallel: the two layers average their parameter gradients inside their own backward (qw_conv1d_backward_dp), so the
     # step needs no collective call at all; NCCL all_reduce of the flat gradient vector if symmetric memory is unavailable
     dp_note = ""
@@ -954,8 +972,9 @@ def run_e2e(runner, B, K, Wm, world, dev, graphed=True):
                     flat_static = step_math(dev_in[slot])
                 step_graphs.append((gph, flat_static))
             torch.cuda.synchronize()
-            api = ("QuantumConv1d nn.Module x2 + GELU (nn.Sequential), loss and torch.autograd backward captured as one CUDA graph "
-                   "per input slot (torch.cuda.graph)")
+            api = (("stem_train_forward(conv1, conv2, x, gelu=(True, False)) on two QuantumConv1d nn.Modules" if stem_helper else
+                    "QuantumConv1d nn.Module x2 + GELU (nn.Sequential)") +
+                   ", loss and torch.autograd backward captured as one CUDA graph per input slot (torch.cuda.graph)")
         except Exception as e:
             step_graphs = None
             api += f" [whole-step capture failed: {type(e).__name__}: {str(e)[:80]}]"

@@ -242,6 +242,7 @@ class _StemTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, act, n_layers, *params):
         lib = _lib.load()
+        act1, act2 = (bool(act[0]), bool(act[1])) if isinstance(act, tuple) else (bool(act), bool(act))
         B, C, L = x.shape
         p1 = [t.contiguous() for t in params[:5]]
         p2 = [t.contiguous() for t in params[5:]]
@@ -252,20 +253,20 @@ class _StemTrainFn(torch.autograd.Function):
         ps1 = torch.empty(2, B * L, 4, device=x.device, dtype=x.dtype)
         ps2 = torch.empty(2, B * (L // 2), 4, device=x.device, dtype=x.dtype)
         with torch.cuda.device(x.device):
-            if lib.qw_stem_train_forward_preferred(B, L):
+            if act1 == act2 and lib.qw_stem_train_forward_preferred(B, L):
                 st = lib.qw_stem_train_forward(_ptr(x), *[_ptr(t) for t in p1], *[_ptr(t) for t in p2], _ptr(y1), _ptr(ps1), _ptr(y2),
-                                               _ptr(ps2), B, C, L, H, O, n_layers, 1 if act else 0, _stream())
+                                               _ptr(ps2), B, C, L, H, O, n_layers, 1 if act1 else 0, _stream())
                 _lib.check(st, "qw_stem_train_forward")
-            else:  # many tiles per CTA: two leaner forward kernels win; the saved tensors are the same, so is the chained backward
-                a = 1 if act else 0
-                st = lib.qw_conv1d_forward_act(_ptr(x), *[_ptr(t) for t in p1], _ptr(y1), _ptr(ps1), B, C, L, 3, 1, 1, H, 4, n_layers, 0, a,
-                                               _stream())
+            else:  # many tiles per CTA (two leaner forward kernels win) or different activations after the two layers: the saved
+                   # tensors are the same, so is the chained backward
+                st = lib.qw_conv1d_forward_act(_ptr(x), *[_ptr(t) for t in p1], _ptr(y1), _ptr(ps1), B, C, L, 3, 1, 1, H, 4, n_layers, 0,
+                                               1 if act1 else 0, _stream())
                 _lib.check(st, "qw_conv1d_forward_act")
-                st = lib.qw_conv1d_forward_act(_ptr(y1), *[_ptr(t) for t in p2], _ptr(y2), _ptr(ps2), B, H, L, 3, 2, 1, O, 4, n_layers, 0, a,
-                                               _stream())
+                st = lib.qw_conv1d_forward_act(_ptr(y1), *[_ptr(t) for t in p2], _ptr(y2), _ptr(ps2), B, H, L, 3, 2, 1, O, 4, n_layers, 0,
+                                               1 if act2 else 0, _stream())
                 _lib.check(st, "qw_conv1d_forward_act")
         ctx.save_for_backward(x, y1, ps1, ps2, *p1, *p2)
-        ctx.cfg = (B, C, L, H, O, n_layers, bool(act))
+        ctx.cfg = (B, C, L, H, O, n_layers, act1, act2)
         return y2
 
     @staticmethod
@@ -273,10 +274,10 @@ class _StemTrainFn(torch.autograd.Function):
         lib = _lib.load()
         x, y1, ps1, ps2, *pp = ctx.saved_tensors
         p1, p2 = pp[:5], pp[5:]
-        B, C, L, H, O, n_layers, act = ctx.cfg
+        B, C, L, H, O, n_layers, act1, act2 = ctx.cfg
         dev = x.device
 
-        def layer_backward(gy, xin, ps, prm, Cin, Lin, S, Oout, need_gx):
+        def layer_backward(gy, xin, ps, prm, Cin, Lin, S, Oout, need_gx, act):
             w_pre, b_pre, qw, w_post, b_post = prm
             gx = torch.empty_like(xin) if need_gx else None
             grads = [torch.empty_like(t) for t in prm]
@@ -290,8 +291,8 @@ class _StemTrainFn(torch.autograd.Function):
             return gx, grads
 
         if lib.qw_get_option(b"STEM_CHAIN") == 0:
-            g1, grads2 = layer_backward(gy2.contiguous(), y1, ps2, p2, H, L, 2, O, True)
-            gx, grads1 = layer_backward(g1, x, ps1, p1, C, L, 1, H, ctx.needs_input_grad[0])
+            g1, grads2 = layer_backward(gy2.contiguous(), y1, ps2, p2, H, L, 2, O, True, act2)
+            gx, grads1 = layer_backward(g1, x, ps1, p1, C, L, 1, H, ctx.needs_input_grad[0], act1)
             return (gx, None, None, *grads1, *grads2)
         # chained: conv2's backward writes NO gradient for its input; conv1's gy kernel rebuilds that gradient tile by tile from conv2's
         # gpre rows (inside conv2's workspace) and pre_conv weights (qw_conv1d_backward_chained)
@@ -304,10 +305,11 @@ class _StemTrainFn(torch.autograd.Function):
         n1 = lib.qw_conv1d_workspace_bytes(B, C, L, 3, 1, 1, H, 4, n_layers, 4)
         ws1 = torch.empty(n1, device=dev, dtype=torch.uint8)
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        a = 1 if act else 0
+        a = 1 if act1 else 0
         with torch.cuda.device(dev):
             st = lib.qw_conv1d_backward_act(_ptr(gy2.contiguous()), _ptr(y1), _ptr(ps2), _ptr(w_pre2), _ptr(qw2), _ptr(w_post2), _ptr(b_post2),
-                                            None, *[_ptr(g) for g in grads2], _ptr(ws2), n2, B, H, L, 3, 2, 1, O, 4, n_layers, 0, a, _stream())
+                                            None, *[_ptr(g) for g in grads2], _ptr(ws2), n2, B, H, L, 3, 2, 1, O, 4, n_layers, 0,
+                                            1 if act2 else 0, _stream())
             _lib.check(st, "qw_conv1d_backward_act")
             st = lib.qw_conv1d_backward_chained(_ptr(ws2), _ptr(w_pre2), O, _ptr(x), _ptr(ps1), _ptr(w_pre1), _ptr(qw1), _ptr(w_post1),
                                                 _ptr(b_post1), _ptr(gx), *[_ptr(g) for g in grads1], _ptr(ws1), n1, B, C, L, 3, 1, 1, H, 4,
@@ -329,16 +331,18 @@ def stem_train_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch
             and conv2.out_channels <= 384 and lib.qw_get_option(b"FAST_PATH") != 0 and lib.qw_get_option(b"GY_MMA") != 0)
 
 
-def stem_train_forward(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor, gelu: bool = True) -> torch.Tensor:
+def stem_train_forward(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor, gelu=True) -> torch.Tensor:
     """``gelu(conv2(gelu(conv1(x))))`` (or without the activations) for training, differentiable in x and all ten parameters:
-    the first two lines of AudioEncoder.forward (whisper/whisper/model.py:193-194) as one forward kernel."""
+    the first two lines of AudioEncoder.forward (whisper/whisper/model.py:193-194) as one forward kernel (when that is the faster
+    form for the batch) and a backward in which the gradient between the two layers never touches HBM.  ``gelu`` may be a pair
+    ``(after_conv1, after_conv2)``, e.g. ``(True, False)`` for conv1 -> GELU -> conv2."""
+    g1, g2 = (bool(gelu[0]), bool(gelu[1])) if isinstance(gelu, (tuple, list)) else (bool(gelu), bool(gelu))
     if not stem_train_eligible(conv1, conv2, x):
-        if gelu:
-            return conv2.forward_gelu(conv1.forward_gelu(x))
-        return conv2(conv1(x))
+        h = conv1.forward_gelu(x) if g1 else conv1(x)
+        return conv2.forward_gelu(h) if g2 else conv2(h)
     prm = [conv1.pre_conv.weight, conv1.pre_conv.bias, conv1.quantum_weights, conv1.post_conv.weight, conv1.post_conv.bias,
            conv2.pre_conv.weight, conv2.pre_conv.bias, conv2.quantum_weights, conv2.post_conv.weight, conv2.post_conv.bias]
-    return _StemTrainFn.apply(x, bool(gelu), conv1.n_layers, *prm)
+    return _StemTrainFn.apply(x, (g1, g2), conv1.n_layers, *prm)
 
 
 def fused_stem_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor) -> bool:

@@ -193,3 +193,21 @@ def test_stem_train_forward_other_shapes(cuda, C, H, O, n_layers, L):
     gr = torch.autograd.grad(ref, [x] + prm, cot)
     for a, b in zip(g, gr):
         assert (a - b).abs().max().item() <= 5e-5 * max(1.0, b.abs().max().item())
+
+
+def test_stem_train_forward_gelu_between_only(cuda):
+    """conv1 -> GELU -> conv2 (no activation after conv2): what bench.py's e2e leg runs.  Against nn.Sequential(conv1, GELU, conv2)."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200.quantum_conv1d import stem_train_forward
+    torch.manual_seed(21)
+    c1 = qw.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(cuda)
+    c2 = qw.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    x = torch.randn(4, 80, 3000, device=cuda)
+    prm = list(c1.parameters()) + list(c2.parameters())
+    y = stem_train_forward(c1, c2, x, gelu=(True, False))
+    ref = torch.nn.Sequential(c1, torch.nn.GELU(), c2)(x)
+    assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    g = torch.autograd.grad(y.square().mean(), prm)
+    gr = torch.autograd.grad(ref.square().mean(), prm)
+    for a, b in zip(g, gr):
+        assert (a - b).abs().max().item() <= 5e-5 * max(1.0, b.abs().max().item())
