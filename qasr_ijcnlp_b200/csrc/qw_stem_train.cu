@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(kThreadsT, 2) stem_train_fwd_kernel(const __gr
   // chunks with one named barrier per chunk 45.9 us (40.5 with the stores themselves disabled: the barriers), 1.5 KB per-warp
   // chunks with __syncwarp only 45.8 us (36.4 without the stores).  Two small staging buffers cannot decouple a warp from a
   // saturated memory system, and a tile's worth of staging (73 KB) does not fit beside the parameters at two CTAs per SM.
+  // De-phasing the two CTAs of every SM (the upper half of the grid starting 1-5 us late, so that store bursts of one CTA meet the
+  // compute phases of the other) changes nothing either: 42.5 -> 42.8 ... 44.6 us -- the stall is inside each warp's own issue order.
   for (int n = 0; n <= my_tiles + 1; ++n) {
     // ---- A(n): pre_conv1 partial sums of tile n
     if (n < my_tiles) {
