@@ -916,7 +916,8 @@ def run_e2e(runner, B, K, Wm, world, dev, graphed=True):
     api = "QuantumConv1d nn.Module x2 + GELU (nn.Sequential), eager autograd"
     call = stem
     stem_helper = False
-    if world == 1 and os.environ.get("QW_E2E_PLAIN", "0") != "1":
+    use_helper = os.environ.get("QW_E2E_PLAIN", "0") != "1"
+    if use_helper:
         # the package's stem helper on the same two modules: conv1 -> GELU -> conv2 with the GELU inside conv1's kernels and the
         # gradient between the layers never written (stem_train_forward; falls back to the plain modules outside its regime)
         from qasr_ijcnlp_b200 import stem_train_forward
@@ -942,7 +943,8 @@ def run_e2e(runner, B, K, Wm, world, dev, graphed=True):
             conv1.fuse_grad_allreduce()
             conv2.fuse_grad_allreduce()
             fused_grads = True
-            dp_note = "; gradient mean over ranks fused into each layer's backward (NVLink peer memory), loss kept per rank"
+            dp_note = "; gradient mean over ranks fused into each layer's backward (NVLink peer memory; the stem helper passes the "\
+                      "layers' contexts to qw_conv1d_backward_dp / _chained), loss kept per rank"
         except Exception as e:
             conv1._grad_allreduce = conv2._grad_allreduce = None
             dp_note = f"; NCCL all_reduce(AVG) of loss + gradients ({type(e).__name__})"

@@ -240,9 +240,10 @@ class _StemTrainFn(torch.autograd.Function):
     activation is written for the backward but never read back), then each layer's own backward (qw_conv1d_backward[_act])."""
 
     @staticmethod
-    def forward(ctx, x, act, n_layers, *params):
+    def forward(ctx, x, act, n_layers, dpctx, *params):
         lib = _lib.load()
         act1, act2 = (bool(act[0]), bool(act[1])) if isinstance(act, tuple) else (bool(act), bool(act))
+        ctx.dpctx = dpctx  # None, or (conv1's, conv2's) dp.FusedLayerGradAllReduce: gradients leave the backward averaged over the ranks
         B, C, L = x.shape
         p1 = [t.contiguous() for t in params[:5]]
         p2 = [t.contiguous() for t in params[5:]]
@@ -290,10 +291,11 @@ class _StemTrainFn(torch.autograd.Function):
             _lib.check(st, "qw_conv1d_backward_act")
             return gx, grads
 
-        if lib.qw_get_option(b"STEM_CHAIN") == 0:
+        dpctx = ctx.dpctx
+        if lib.qw_get_option(b"STEM_CHAIN") == 0 and dpctx is None:
             g1, grads2 = layer_backward(gy2.contiguous(), y1, ps2, p2, H, L, 2, O, True, act2)
             gx, grads1 = layer_backward(g1, x, ps1, p1, C, L, 1, H, ctx.needs_input_grad[0], act1)
-            return (gx, None, None, *grads1, *grads2)
+            return (gx, None, None, None, *grads1, *grads2)
         # chained: conv2's backward writes NO gradient for its input; conv1's gy kernel rebuilds that gradient tile by tile from conv2's
         # gpre rows (inside conv2's workspace) and pre_conv weights (qw_conv1d_backward_chained)
         w_pre2, b_pre2, qw2, w_post2, b_post2 = p2
@@ -307,23 +309,35 @@ class _StemTrainFn(torch.autograd.Function):
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         a = 1 if act1 else 0
         with torch.cuda.device(dev):
-            st = lib.qw_conv1d_backward_act(_ptr(gy2.contiguous()), _ptr(y1), _ptr(ps2), _ptr(w_pre2), _ptr(qw2), _ptr(w_post2), _ptr(b_post2),
-                                            None, *[_ptr(g) for g in grads2], _ptr(ws2), n2, B, H, L, 3, 2, 1, O, 4, n_layers, 0,
-                                            1 if act2 else 0, _stream())
-            _lib.check(st, "qw_conv1d_backward_act")
+            if dpctx is not None:  # (act2 is False here: the data-parallel backward has no activation form)
+                st = lib.qw_conv1d_backward_dp(_ptr(gy2.contiguous()), _ptr(y1), _ptr(ps2), _ptr(w_pre2), _ptr(qw2), _ptr(w_post2), None,
+                                               *[_ptr(g) for g in grads2], _ptr(ws2), n2, B, H, L, 3, 2, 1, O, 4, n_layers, 0,
+                                               *dpctx[1].args(), _stream())
+                _lib.check(st, "qw_conv1d_backward_dp")
+            else:
+                st = lib.qw_conv1d_backward_act(_ptr(gy2.contiguous()), _ptr(y1), _ptr(ps2), _ptr(w_pre2), _ptr(qw2), _ptr(w_post2),
+                                                _ptr(b_post2), None, *[_ptr(g) for g in grads2], _ptr(ws2), n2, B, H, L, 3, 2, 1, O, 4,
+                                                n_layers, 0, 1 if act2 else 0, _stream())
+                _lib.check(st, "qw_conv1d_backward_act")
+            dp1 = dpctx[0].args() if dpctx is not None else (None, None, 0, 1, 1.0)
             st = lib.qw_conv1d_backward_chained(_ptr(ws2), _ptr(w_pre2), O, _ptr(x), _ptr(ps1), _ptr(w_pre1), _ptr(qw1), _ptr(w_post1),
                                                 _ptr(b_post1), _ptr(gx), *[_ptr(g) for g in grads1], _ptr(ws1), n1, B, C, L, 3, 1, 1, H, 4,
-                                                n_layers, 0, a, None, None, 0, 1, 1.0, _stream())
+                                                n_layers, 0, a, *dp1, _stream())
             _lib.check(st, "qw_conv1d_backward_chained")
-        return (gx, None, None, *grads1, *grads2)
+        return (gx, None, None, None, *grads1, *grads2)
 
 
-def stem_train_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor) -> bool:
-    """Shapes qw_stem_train_forward covers: the Whisper stem (conv1 K=3,S=1,P=1; conv2 K=3,S=2,P=1; n_qubits 4, amplitude)."""
+def stem_train_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor, allow_dp: bool = False) -> bool:
+    """Shapes qw_stem_train_forward covers: the Whisper stem (conv1 K=3,S=1,P=1; conv2 K=3,S=2,P=1; n_qubits 4, amplitude).
+    ``allow_dp``: layers with ``fuse_grad_allreduce()`` on BOTH of them qualify too (the chained backward then averages the
+    gradients over the ranks inside its finalize kernels)."""
     def ok(m, S):
         return (isinstance(m, QuantumConv1d) and m.kernel_size == 3 and m.stride == S and m.padding == 1 and m.n_qubits == 4
-                and m.embedding == "amplitude" and m.n_layers <= 4 and m._grad_allreduce is None)
+                and m.embedding == "amplitude" and m.n_layers <= 4)
     if not (ok(conv1, 1) and ok(conv2, 2) and conv1.n_layers == conv2.n_layers and conv2.in_channels == conv1.out_channels):
+        return False
+    has_dp = (conv1._grad_allreduce is not None, conv2._grad_allreduce is not None)
+    if any(has_dp) and not (allow_dp and all(has_dp)):
         return False
     lib = _lib.load()
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[1] == conv1.in_channels and conv1.in_channels <= 96
@@ -337,12 +351,13 @@ def stem_train_forward(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.
     form for the batch) and a backward in which the gradient between the two layers never touches HBM.  ``gelu`` may be a pair
     ``(after_conv1, after_conv2)``, e.g. ``(True, False)`` for conv1 -> GELU -> conv2."""
     g1, g2 = (bool(gelu[0]), bool(gelu[1])) if isinstance(gelu, (tuple, list)) else (bool(gelu), bool(gelu))
-    if not stem_train_eligible(conv1, conv2, x):
+    if not stem_train_eligible(conv1, conv2, x, allow_dp=not g2):
         h = conv1.forward_gelu(x) if g1 else conv1(x)
         return conv2.forward_gelu(h) if g2 else conv2(h)
     prm = [conv1.pre_conv.weight, conv1.pre_conv.bias, conv1.quantum_weights, conv1.post_conv.weight, conv1.post_conv.bias,
            conv2.pre_conv.weight, conv2.pre_conv.bias, conv2.quantum_weights, conv2.post_conv.weight, conv2.post_conv.bias]
-    return _StemTrainFn.apply(x, (g1, g2), conv1.n_layers, *prm)
+    dpctx = (conv1._grad_allreduce, conv2._grad_allreduce) if conv1._grad_allreduce is not None else None
+    return _StemTrainFn.apply(x, (g1, g2), conv1.n_layers, dpctx, *prm)
 
 
 def fused_stem_eligible(conv1: "QuantumConv1d", conv2: "QuantumConv1d", x: torch.Tensor) -> bool:

@@ -217,3 +217,59 @@ def test_two_gpu_fused_backward_allreduce_matches_nccl():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def _worker_stem(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import qasr_ijcnlp_b200 as qw
+        from qasr_ijcnlp_b200 import stem_train_forward
+        torch.manual_seed(5)  # same parameters on every rank
+        c1 = qw.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(dev)
+        c2 = qw.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(dev)
+        prm = list(c1.parameters()) + list(c2.parameters())
+        x = torch.randn(2, 80, 640, device=dev, generator=torch.Generator(device=dev).manual_seed(10 + rank))  # a different shard per rank
+        # reference: the helper without any collective, then NCCL mean
+        ref = torch.autograd.grad(stem_train_forward(c1, c2, x, gelu=(True, False)).square().mean(), prm)
+        ref = [g.clone() for g in ref]
+        for g in ref:
+            dist.all_reduce(g, op=dist.ReduceOp.AVG)
+        # the layers' fused gradient all-reduce contexts handed to the chained backward by the helper
+        c1.fuse_grad_allreduce()
+        c2.fuse_grad_allreduce()
+        ok = True
+        for _ in range(3):  # several epochs of the exchange
+            got = torch.autograd.grad(stem_train_forward(c1, c2, x, gelu=(True, False)).square().mean(), prm)
+            for a, b in zip(got, ref):
+                ok = ok and (a - b).abs().max().item() <= 1e-6 * max(1.0, b.abs().max().item())
+        flat = torch.cat([g.reshape(-1) for g in got])
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        ok = ok and torch.equal(both[0], both[1])  # bitwise identical on the two ranks
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_stem_helper_with_fused_gradient_allreduce():
+    """stem_train_forward on layers with fuse_grad_allreduce(): conv2's backward (no grad_x) through qw_conv1d_backward_dp, conv1's
+    through qw_conv1d_backward_chained with the peer tables -- gradients equal the NCCL mean of the single-rank gradients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_stem, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
