@@ -1355,6 +1355,11 @@ def run_reference(args):
     if rank != 0:
         return
     K, Wm = args.steps, args.warmup
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the other ranks have exited, so rank 0 may use the whole host
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     cores = torch.get_num_threads()
     cols = {"conv1": 32, "conv2": 16}
     # keep the whole run within a few minutes: calibrate the per-step sample on the first warm-up step
