@@ -159,3 +159,56 @@ def test_log_mel_stays_inside_its_buffers(cuda, B, n_in, n):
         _lib.check(st, "qw_log_mel_padded")
     ar.assert_guards_intact("log-mel")
     assert torch.isfinite(mel).all() and mel.abs().max().item() < 10.0
+
+
+@pytest.mark.parametrize("B,L", [(1, 3000), (3, 96), (2, 40), (5, 1000)])
+def test_inference_stem_stays_inside_its_buffers(cuda, B, L):
+    from qasr_ijcnlp_b200 import _lib
+    import qasr_ijcnlp_b200 as qw
+    lib = _lib.load()
+    torch.manual_seed(B + L)
+    C, H, O, nl = 80, 384, 384, 1
+    c1 = qw.QuantumConv1d(C, H, 3, padding=1, n_qubits=4).to(cuda)
+    c2 = qw.QuantumConv1d(H, O, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    prm = lambda m: [t.detach().contiguous() for t in (m.pre_conv.weight, m.pre_conv.bias, m.quantum_weights, m.post_conv.weight,
+                                                       m.post_conv.bias)]
+    n = lib.qw_stem_workspace_bytes(B, L)
+    ar = Arena(cuda, 4 * (B * C * L + 2 * (L // 2) * O + B * (L // 2) * O) + n + (1 << 20))
+    x = ar.f32(B, C, L)
+    x.copy_(torch.randn(B, C, L, device=cuda))
+    pos = ar.f32(L // 2, O)
+    pos.copy_(torch.randn(L // 2, O, device=cuda))
+    out = ar.f32(B, L // 2, O)
+    ws = ar.take(max(n, 16))
+    with torch.cuda.device(cuda):
+        st = lib.qw_stem_forward(_p(x), *[_p(t) for t in prm(c1)], *[_p(t) for t in prm(c2)], _p(pos), _p(out), _p(ws), n,
+                                 B, C, L, H, O, nl, _stream())
+        _lib.check(st, "qw_stem_forward")
+    ar.assert_guards_intact("inference stem")
+    assert out.abs().max().item() < 1e12
+
+
+@pytest.mark.parametrize("W,q,nl,emb", [(333, 4, 1, 0), (515, 6, 2, 0), (41, 10, 1, 0), (37, 12, 1, 1), (1000, 5, 4, 1), (1, 4, 1, 0)])
+def test_circuit_entry_points_stay_inside_their_buffers(cuda, W, q, nl, emb):
+    from qasr_ijcnlp_b200 import _lib
+    lib = _lib.load()
+    n = lib.qw_circuit_workspace_bytes(W, q, nl, 4)
+    ar = Arena(cuda, 4 * (4 * W * q + 2 * nl * q * 3) + n + (1 << 20))
+    pre = ar.f32(W, q)
+    pre.copy_(torch.randn(W, q, device=cuda))
+    w = ar.f32(nl, q, 3)
+    w.copy_(torch.randn(nl, q, 3, device=cuda))
+    out = ar.f32(W, q)
+    with torch.cuda.device(cuda):
+        _lib.check(lib.qw_circuit_forward(_p(pre), _p(w), _p(out), W, q, nl, emb, _stream()), "qw_circuit_forward")
+    ar.assert_guards_intact("circuit forward")
+    assert out.abs().max().item() <= 1.0 + 1e-5
+    gout = ar.f32(W, q)
+    gout.copy_(torch.randn(W, q, device=cuda))
+    gpre, gw = ar.f32(W, q), ar.f32(nl, q, 3)
+    ws = ar.take(max(n, 16))
+    with torch.cuda.device(cuda):
+        _lib.check(lib.qw_circuit_backward(_p(pre), _p(w), _p(gout), _p(gpre), _p(gw), _p(ws), n, W, q, nl, emb, _stream()),
+                   "qw_circuit_backward")
+    ar.assert_guards_intact("circuit backward")
+    assert gpre.abs().max().item() < 1e12 and gw.abs().max().item() < 1e12
