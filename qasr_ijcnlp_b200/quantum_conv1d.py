@@ -236,8 +236,10 @@ class QuantumConv1d(nn.Module):
 
 
 class _StemTrainFn(torch.autograd.Function):
-    """y2 = act(conv2(act(conv1(x)))) for TRAINING: one forward kernel for both layers (qw_stem_train_forward: the (B, hidden, L)
-    activation is written for the backward but never read back), then each layer's own backward (qw_conv1d_backward[_act])."""
+    """y2 = act2(conv2(act1(conv1(x)))) for TRAINING: one forward kernel for both layers (qw_stem_train_forward: the (B, hidden, L)
+    activation is written for the backward but never read back by the forward), then the CHAINED backward: conv2's
+    qw_conv1d_backward_act / _dp without grad_x, conv1's qw_conv1d_backward_chained, whose gy kernel rebuilds conv2's input gradient
+    from conv2's gpre rows (the STEM_CHAIN option set to 0 restores the two independent backward calls with grad_x through HBM)."""
 
     @staticmethod
     def forward(ctx, x, act, n_layers, dpctx, *params):
