@@ -211,3 +211,29 @@ def test_stem_train_forward_gelu_between_only(cuda):
     gr = torch.autograd.grad(ref.square().mean(), prm)
     for a, b in zip(g, gr):
         assert (a - b).abs().max().item() <= 5e-5 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("B", [24, 256])
+def test_stem_train_large_batch_last_utterance_matches_single(cuda, B):
+    """Batch independence at sizes whose byte offsets pass 2^31 (batch 256: the (B, 384, 3000) activation is 1.18 GB): the output and
+    grad_x of the LAST utterance must equal those of the same utterance run alone.  Batch 24 is the largest batch the one-kernel
+    forward takes at 3000 frames (qw_stem_train_forward_preferred), batch 256 runs the two-kernel forward; both use the chained
+    backward."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200 import _lib
+    from qasr_ijcnlp_b200.quantum_conv1d import stem_train_forward
+    torch.manual_seed(B)
+    L = 3000
+    assert bool(_lib.load().qw_stem_train_forward_preferred(B, L)) == (B == 24)
+    c1 = qw.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(cuda)
+    c2 = qw.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    x = torch.randn(B, 80, L, device=cuda, requires_grad=True)
+    cot = torch.randn(B, 384, L // 2, device=cuda)
+    y = stem_train_forward(c1, c2, x, gelu=True)
+    (gx,) = torch.autograd.grad(y, [x], cot)
+    for b in (0, B - 1):
+        xb = x[b:b + 1].detach().clone().requires_grad_(True)
+        yb = stem_train_forward(c1, c2, xb, gelu=True)
+        (gxb,) = torch.autograd.grad(yb, [xb], cot[b:b + 1].contiguous())
+        assert (y[b:b + 1] - yb).abs().max().item() <= 2e-6 * max(1.0, yb.abs().max().item()), b
+        assert (gx[b:b + 1] - gxb).abs().max().item() <= 2e-6 * max(1.0, gxb.abs().max().item()), b
