@@ -209,3 +209,17 @@ def test_selective_second_pass_equals_unconditional(cuda):
     ref = lo.log_mel_spectrogram(a)
     _close(outs[1].cpu().numpy(), ref)
     assert (ref[1:] == ref[1:].min(axis=(1, 2), keepdims=True)).mean() > 0.2   # the clamp really is active in these clips
+
+
+def test_batch_512_full_length_equals_single_utterances(cuda):
+    """BASELINE config 5's largest point (batch 512 x 480 000 samples: 983 MB of audio, byte offsets past 2^31): utterances 0, 255 and
+    511 of the batched call must be BIT-identical to the same utterance run alone (the per-utterance maximum and every frame are
+    computed independently of the batch)."""
+    from qasr_ijcnlp_b200 import audio as qa
+    g = torch.Generator(device=cuda).manual_seed(512)
+    a = torch.randn(512, qa.N_SAMPLES, device=cuda, generator=g) * 0.05
+    a[511, 100000:] = 0.0  # silent tail: the selective second pass has to leave those tiles at the clamp floor
+    mel = qa.log_mel_spectrogram(a)
+    assert mel.shape == (512, 80, 3000) and torch.isfinite(mel).all()
+    for b in (0, 255, 511):
+        assert torch.equal(mel[b], qa.log_mel_spectrogram(a[b].clone())), b
