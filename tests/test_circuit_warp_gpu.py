@@ -147,3 +147,21 @@ def test_general_layer_full_size_conv2_geometry(cuda):
     assert rel(y.detach().cpu().double(), ref["y"]) <= 5e-5
     for name, gr in zip(["x", "w_pre", "b_pre", "qweights", "w_post", "b_post"], grads):
         assert rel(gr.cpu().double(), ref[name]) <= 5e-5, name
+
+
+def test_general_layer_batch_512_last_utterance_matches_single(cuda):
+    """General path (n_qubits 6) at conv1's geometry and batch 512: the (B, 384, 3000) output is 2.36 GB, so element byte offsets pass
+    2^31 in every streaming kernel of the path.  Output and grad_x of utterances 0 and 511 must equal those of the utterance alone."""
+    from qasr_ijcnlp_b200 import QuantumConv1d
+    torch.manual_seed(512)
+    m = QuantumConv1d(80, 384, 3, padding=1, n_qubits=6).to(cuda)
+    B, L = 512, 3000
+    x = torch.randn(B, 80, L, device=cuda, requires_grad=True)
+    y = m(x)
+    (gx,) = torch.autograd.grad(y, [x], torch.ones_like(y))
+    for b in (0, B - 1):
+        xb = x[b:b + 1].detach().clone().requires_grad_(True)
+        yb = m(xb)
+        (gxb,) = torch.autograd.grad(yb, [xb], torch.ones_like(yb))
+        assert (y[b:b + 1] - yb).abs().max().item() <= 2e-6 * max(1.0, yb.abs().max().item()), b
+        assert (gx[b:b + 1] - gxb).abs().max().item() <= 2e-6 * max(1.0, gxb.abs().max().item()), b
