@@ -237,3 +237,33 @@ def test_stem_train_large_batch_last_utterance_matches_single(cuda, B):
         (gxb,) = torch.autograd.grad(yb, [xb], cot[b:b + 1].contiguous())
         assert (y[b:b + 1] - yb).abs().max().item() <= 2e-6 * max(1.0, yb.abs().max().item()), b
         assert (gx[b:b + 1] - gxb).abs().max().item() <= 2e-6 * max(1.0, gxb.abs().max().item()), b
+
+
+def test_inference_stem_and_fast_layer_batch_1024_match_single(cuda):
+    """Byte offsets past 2^31 in the inference stem (batch 1024: 2.36 GB of output) and in the fast per-layer forward / backward
+    (conv1 geometry, batch 512): utterances 0 and B-1 must equal the utterance run alone (outputs bit-identical: the tile schedule of
+    an utterance does not depend on the batch; grad_x to rounding of nothing -- it is per-utterance too)."""
+    import qasr_ijcnlp_b200 as qw
+    from qasr_ijcnlp_b200.quantum_conv1d import fused_stem_forward
+    torch.manual_seed(1024)
+    c1 = qw.QuantumConv1d(80, 384, 3, padding=1, n_qubits=4).to(cuda)
+    c2 = qw.QuantumConv1d(384, 384, 3, stride=2, padding=1, n_qubits=4).to(cuda)
+    pos = torch.randn(1500, 384, device=cuda)
+    B = 1024
+    x = torch.randn(B, 80, 3000, device=cuda)
+    with torch.no_grad():
+        out = fused_stem_forward(c1, c2, x, pos)
+        for b in (0, B - 1):
+            one = fused_stem_forward(c1, c2, x[b:b + 1].contiguous(), pos)
+            assert (out[b:b + 1] - one).abs().max().item() <= 2e-6 * max(1.0, one.abs().max().item()), b
+    del out
+    B = 512
+    xs = x[:B].clone().requires_grad_(True)
+    y = c1(xs)
+    (gx,) = torch.autograd.grad(y, [xs], torch.ones_like(y))
+    for b in (0, B - 1):
+        xb = xs[b:b + 1].detach().clone().requires_grad_(True)
+        yb = c1(xb)
+        (gxb,) = torch.autograd.grad(yb, [xb], torch.ones_like(yb))
+        assert (y[b:b + 1] - yb).abs().max().item() <= 2e-6 * max(1.0, yb.abs().max().item()), b
+        assert (gx[b:b + 1] - gxb).abs().max().item() <= 2e-6 * max(1.0, gxb.abs().max().item()), b
